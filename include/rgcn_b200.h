@@ -1,0 +1,189 @@
+/*
+ * rgcn_b200.h -- C-ABI of librgcn_b200.so: the B200-native (sm_100a) R-GCN relational
+ * message-passing hot path (block-diagonal + basis decomposition, forward and backward) and the
+ * DistMult triple scorer.
+ *
+ * The reference (MichSchli/RelationPrediction) is pure Python/TensorFlow-1 and has no FFI; its
+ * "operator interface" for this path is the set of plugin hooks that build a TF graph.  Each entry
+ * point below cites the reference hook(s) (file:line under /root/reference/code) whose *executed*
+ * TF ops it replaces.  INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, negative = error (RGCN_ERR_*); rgcn_last_error() gives text.
+ *   - no exceptions cross the boundary; no torch types; plain pointers + explicit sizes.
+ *   - the caller owns every tensor (device pointers unless the name ends in _host); the library
+ *     owns only the opaque graph handle.  `stream` is a cudaStream_t passed as void*.
+ *   - all feature / weight tensors are dense row-major fp32; all indices are int32.
+ *   - all calls are asynchronous with respect to the host (work is enqueued on `stream`).
+ *   - a "message" is one (source row -> destination row, relation-weight id) item.  A triple
+ *     (s, r, o) yields two messages: forward  s->o with weight id r       (W_forward[r])
+ *                                    backward o->s with weight id r + R   (W_backward[r])
+ *     (reference: extras/graph_representations.py:21-27, message_gcn.py:28-42).
+ */
+#ifndef RGCN_B200_H
+#define RGCN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGCN_OK 0
+#define RGCN_ERR_INVALID (-1)   /* bad argument (shape, null pointer, index out of range)      */
+#define RGCN_ERR_CUDA (-2)      /* CUDA runtime / cuBLAS failure; text in rgcn_last_error()    */
+#define RGCN_ERR_NOMEM (-3)     /* host or device allocation failed                            */
+#define RGCN_ERR_WORKSPACE (-4) /* caller workspace too small (see *_workspace_bytes)          */
+#define RGCN_ERR_NODEVICE (-5)  /* device entry point called on a host-only graph / no GPU     */
+
+/* normalisation modes for rgcn_graph_create (extras/graph_representations.py:84-93,124-133) */
+#define RGCN_NORM_CANONICAL 0 /* 1 / (#messages of that direction into the destination)        */
+#define RGCN_NORM_EXPLICIT 1  /* caller supplies norm_f[E], norm_b[E] (e.g. tf_unsorted_compat) */
+#define RGCN_NORM_NONE 2      /* all ones ('none' branch, :70-82)                               */
+
+typedef struct rgcn_graph rgcn_graph_t; /* opaque */
+
+int rgcn_version(void);
+const char* rgcn_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
+int64_t rgcn_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph preparation.  Replaces Representation/MessageGraph
+ * (extras/graph_representations.py:21-27 index vectors, :84-93 / :124-133 normalised incidence).
+ *
+ * triples_host : int32 [E,3], columns (subject, relation, object), host memory.
+ * V            : number of entities (rows of H); R: number of relations.
+ * device       : CUDA device ordinal, or -1 to build the host-side structure only (CPU tests).
+ * Builds, deterministically (stable counting sorts; message id of triple k is k forward, E+k
+ * backward): destination-CSR sorted by (dst, weight-id), source-CSR sorted by (src, weight-id),
+ * weight-id-major list sorted by (weight-id, dst), per-message norm, and warp work lists.
+ * ---------------------------------------------------------------------------------------------- */
+int rgcn_graph_create(const int32_t* triples_host, int64_t E, int32_t V, int32_t R, int norm_mode,
+                      const float* norm_f_host, const float* norm_b_host, int device, void* stream,
+                      rgcn_graph_t** out);
+
+/* Generic message-list constructor used by the 1-D node-sharded path: rank-local
+ * destinations [0,V_dst), sources index an extended row space [0,V_src) (local rows then halo
+ * rows).  All arrays host, length M.  relw in [0, n_relw). */
+int rgcn_graph_create_messages(const int32_t* dst_host, const int32_t* src_host,
+                               const int32_t* relw_host, const float* norm_host, int64_t M,
+                               int32_t V_dst, int32_t V_src, int32_t n_relw, int device,
+                               void* stream, rgcn_graph_t** out);
+
+int rgcn_graph_destroy(rgcn_graph_t* g);
+
+/* info[0]=M messages, [1]=V_dst, [2]=V_src, [3]=n_relw, [4]=#dst work items, [5]=#src work items,
+ * [6]=#relw work items, [7]=#split dst rows, [8]=#split src rows, [9]=#(dst,relw) groups,
+ * [10]=device, [11]=bytes resident on device, [12..15] reserved. */
+int rgcn_graph_info(const rgcn_graph_t* g, int64_t info[16]);
+
+/* Export of the prepared structure to host memory, for bit-exact index tests. */
+enum {
+  RGCN_X_DST_ROWPTR = 0, /* int32 [V_dst+1] */
+  RGCN_X_DST_SRC = 1,    /* int32 [M]  source row of each message, destination-major order */
+  RGCN_X_DST_RELW = 2,   /* int32 [M]  */
+  RGCN_X_DST_NORM = 3,   /* float [M]  */
+  RGCN_X_DST_MID = 4,    /* int32 [M]  original message id (k or E+k)                      */
+  RGCN_X_SRC_ROWPTR = 5, /* int32 [V_src+1] */
+  RGCN_X_SRC_DST = 6,
+  RGCN_X_SRC_RELW = 7,
+  RGCN_X_SRC_NORM = 8,
+  RGCN_X_SRC_MID = 9,
+  RGCN_X_REL_PTR = 10, /* int32 [n_relw+1] */
+  RGCN_X_REL_DST = 11,
+  RGCN_X_REL_SRC = 12,
+  RGCN_X_REL_NORM = 13,
+  RGCN_X_REL_MID = 14,
+  RGCN_X_MSG_NORM = 15 /* float [M] norm in original message order */
+};
+int64_t rgcn_graph_export_bytes(const rgcn_graph_t* g, int which);
+int rgcn_graph_export(const rgcn_graph_t* g, int which, void* dst_host, int64_t nbytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Block-diagonal R-GCN layer ("ConcatGcn", encoders/message_gcns/gcn_basis_concat.py:35-83 +
+ * message_gcn.py:49-79).
+ *
+ *   out[v,:] = act( sum_{messages m into v} norm_m * blockdiag(W[relw_m]) . H[src_m,:]
+ *                   + dropout(H[v,:] @ W_self) )
+ *
+ * H      : [V_src, d]   (rows [0,V_dst) are the local nodes: the self-loop uses those)
+ * Wf, Wb : [R, B, s, s], s = d / B, "W . x" orientation (gcn_basis_concat.py:46-47):
+ *          y[b*s+i] = sum_j W[r,b,i,j] * x[b*s+j].      n_relw of the graph must equal 2R.
+ * Wself  : [d, d]
+ * drop_mask : uint8 [V_dst, d] keep-mask (1 = keep) or NULL; survivors are scaled by 1/keep
+ *          (tf.nn.dropout semantics, message_gcn.py:64; self-loop only).
+ * relu   : 1 for hidden layers, 0 for the last layer (common/model_builder.py:275).
+ * out    : [V_dst, d].
+ * ---------------------------------------------------------------------------------------------- */
+int64_t rgcn_block_workspace_bytes(const rgcn_graph_t* g, int32_t d, int32_t B, int backward);
+
+int rgcn_block_forward(const rgcn_graph_t* g, int32_t d, int32_t B, const float* H,
+                       const float* Wf, const float* Wb, const float* Wself,
+                       const uint8_t* drop_mask, float keep, int relu, float* out, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+
+/* Backward of the above (what tf.gradients, optimization/abstract.py:117-118, derives):
+ *   G = dOut * (out > 0 if relu);  dS = G * mask / keep
+ *   dH      [V_src, d]  (overwritten)   dWf, dWb [R,B,s,s] (overwritten)   dWself [d,d] (overwritten)
+ * `out` is the forward result (needed for the ReLU mask only when relu != 0). */
+int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, const float* H,
+                        const float* Wf, const float* Wb, const float* Wself,
+                        const uint8_t* drop_mask, float keep, int relu, const float* out,
+                        const float* dOut, float* dH, float* dWf, float* dWb, float* dWself,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Basis-decomposition R-GCN layer ("BasisGcn", encoders/message_gcns/gcn_basis.py:39-88).
+ *
+ *   m_f[k] = sum_b Cf[r_k,b] * (H[s_k,:] @ Vf[:,b,:])   (and likewise backward with Vb, Cb)
+ *   out    = act( A_f m_f + A_b m_b + dropout(H @ W_self) )
+ *
+ * computed re-associated (aggregate-then-transform): Agg_dir[v,k,b] = sum_m norm_m C[relw_m,b] H[src_m,k]
+ * followed by dense GEMMs with Vf/Vb viewed as [d_in*B, d_out].
+ * Vf, Vb : [d_in, B, d_out] (gcn_basis.py:18);  Cf, Cb : [R, B] (gcn_basis.py:17).  d_in == d_out == d.
+ * `saved` (float [V_dst, 2*d*B]) receives Agg_f | Agg_b and must be handed unchanged to backward.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t rgcn_basis_workspace_bytes(const rgcn_graph_t* g, int32_t d, int32_t B, int backward);
+
+int rgcn_basis_forward(const rgcn_graph_t* g, int32_t d, int32_t B, const float* H,
+                       const float* Vf, const float* Vb, const float* Cf, const float* Cb,
+                       const float* Wself, const uint8_t* drop_mask, float keep, int relu,
+                       float* out, float* saved, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+
+int rgcn_basis_backward(const rgcn_graph_t* g, int32_t d, int32_t B, const float* H,
+                        const float* Vf, const float* Vb, const float* Cf, const float* Cb,
+                        const float* Wself, const uint8_t* drop_mask, float keep, int relu,
+                        const float* out, const float* saved, const float* dOut, float* dH,
+                        float* dVf, float* dVb, float* dCf, float* dCb, float* dWself,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DistMult triple scorer ("BilinearDiag", decoders/bilinear_diag.py:14-34, :63-69).
+ *
+ *   energy[n] = sum_k codes[X[n,0],k] * rel[X[n,1],k] * codes[X[n,2],k]
+ *   loss_out[0] = mean_n( (1-y)x + log1p(exp(-|x|)) + max(-x,0) )            (only if Y != NULL)
+ *   loss_out[1] = mean(e1^2) + mean(r^2) + mean(e2^2) over the gathered rows  (un-scaled; the
+ *                 caller multiplies by RegularizationParameter, bilinear_diag.py:69)
+ * codes : [V, d]; rel : [Vrel, d] (the reference sizes it [EntityCount, d], model_builder.py:134);
+ * X : int32 [N,3] device; Y : float [N] device or NULL; energies : float [N]; loss_out : float [2].
+ * ---------------------------------------------------------------------------------------------- */
+int distmult_forward(const float* codes, const float* rel, int32_t V, int32_t Vrel, int32_t d,
+                     const int32_t* X, int64_t N, const float* Y, float* energies, float* loss_out,
+                     void* stream);
+
+/* Backward: given upstream scalars g_loss (d total / d loss_out[0]) and g_reg (d total / d loss_out[1]),
+ * optionally multiplied by DEVICE scalars g_scale_dev[2] (NULL = 1,1; lets an autograd engine pass
+ * its upstream gradients without a host sync), and optionally a per-triple upstream gradient
+ * g_energy[N] (NULL = none), ACCUMULATES (+=) into dcodes [V,d] and drel [Vrel,d] (the caller
+ * zeroes them when it wants plain gradients). */
+int distmult_backward(const float* codes, const float* rel, int32_t V, int32_t Vrel, int32_t d,
+                      const int32_t* X, int64_t N, const float* Y, const float* energies,
+                      float g_loss, float g_reg, const float* g_scale_dev, const float* g_energy,
+                      float* dcodes, float* drel, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGCN_B200_H */

@@ -1,0 +1,102 @@
+"""ctypes binding of librgcn_b200.so (the C-ABI declared in include/rgcn_b200.h).
+
+There is NO CPU fallback: if the library cannot be loaded the import of the compute path fails
+loudly.  (The oracle under /oracle is test infrastructure and is never imported from here.)
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librgcn_b200.so")
+
+# every symbol include/rgcn_b200.h declares (tests check the .so exports all of them)
+EXPORTED_SYMBOLS = [
+    "rgcn_version", "rgcn_last_error", "rgcn_launch_count",
+    "rgcn_graph_create", "rgcn_graph_create_messages", "rgcn_graph_destroy", "rgcn_graph_info",
+    "rgcn_graph_export_bytes", "rgcn_graph_export",
+    "rgcn_block_workspace_bytes", "rgcn_block_forward", "rgcn_block_backward",
+    "rgcn_basis_workspace_bytes", "rgcn_basis_forward", "rgcn_basis_backward",
+    "distmult_forward", "distmult_backward",
+]
+
+RGCN_NORM_CANONICAL, RGCN_NORM_EXPLICIT, RGCN_NORM_NONE = 0, 1, 2
+
+(X_DST_ROWPTR, X_DST_SRC, X_DST_RELW, X_DST_NORM, X_DST_MID, X_SRC_ROWPTR, X_SRC_DST, X_SRC_RELW,
+ X_SRC_NORM, X_SRC_MID, X_REL_PTR, X_REL_DST, X_REL_SRC, X_REL_NORM, X_REL_MID, X_MSG_NORM) = range(16)
+
+_lib = None
+
+
+class RgcnError(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    vp = c_void_p
+    lib.rgcn_version.restype = c_int
+    lib.rgcn_last_error.restype = c_char_p
+    lib.rgcn_launch_count.restype = c_int64
+    lib.rgcn_graph_create.restype = c_int
+    lib.rgcn_graph_create.argtypes = [vp, c_int64, c_int32, c_int32, c_int, vp, vp, c_int, vp,
+                                      POINTER(vp)]
+    lib.rgcn_graph_create_messages.restype = c_int
+    lib.rgcn_graph_create_messages.argtypes = [vp, vp, vp, vp, c_int64, c_int32, c_int32, c_int32,
+                                               c_int, vp, POINTER(vp)]
+    lib.rgcn_graph_destroy.restype = c_int
+    lib.rgcn_graph_destroy.argtypes = [vp]
+    lib.rgcn_graph_info.restype = c_int
+    lib.rgcn_graph_info.argtypes = [vp, POINTER(c_int64)]
+    lib.rgcn_graph_export_bytes.restype = c_int64
+    lib.rgcn_graph_export_bytes.argtypes = [vp, c_int]
+    lib.rgcn_graph_export.restype = c_int
+    lib.rgcn_graph_export.argtypes = [vp, c_int, vp, c_int64]
+    lib.rgcn_block_workspace_bytes.restype = c_int64
+    lib.rgcn_block_workspace_bytes.argtypes = [vp, c_int32, c_int32, c_int]
+    lib.rgcn_block_forward.restype = c_int
+    lib.rgcn_block_forward.argtypes = [vp, c_int32, c_int32, vp, vp, vp, vp, vp, c_float, c_int, vp,
+                                       vp, c_int64, vp]
+    lib.rgcn_block_backward.restype = c_int
+    lib.rgcn_block_backward.argtypes = [vp, c_int32, c_int32, vp, vp, vp, vp, vp, c_float, c_int, vp,
+                                        vp, vp, vp, vp, vp, vp, c_int64, vp]
+    lib.rgcn_basis_workspace_bytes.restype = c_int64
+    lib.rgcn_basis_workspace_bytes.argtypes = [vp, c_int32, c_int32, c_int]
+    lib.rgcn_basis_forward.restype = c_int
+    lib.rgcn_basis_forward.argtypes = [vp, c_int32, c_int32, vp, vp, vp, vp, vp, vp, vp, c_float,
+                                       c_int, vp, vp, vp, c_int64, vp]
+    lib.rgcn_basis_backward.restype = c_int
+    lib.rgcn_basis_backward.argtypes = [vp, c_int32, c_int32, vp, vp, vp, vp, vp, vp, vp, c_float,
+                                        c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, c_int64, vp]
+    lib.distmult_forward.restype = c_int
+    lib.distmult_forward.argtypes = [vp, vp, c_int32, c_int32, c_int32, vp, c_int64, vp, vp, vp, vp]
+    lib.distmult_backward.restype = c_int
+    lib.distmult_backward.argtypes = [vp, vp, c_int32, c_int32, c_int32, vp, c_int64, vp, vp,
+                                      c_float, c_float, vp, vp, vp, vp, vp]
+
+
+def load():
+    """Load (building first if the .so is absent) and return the ctypes library handle."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # loud failure: the CUDA library IS the product path
+        raise RgcnError("cannot load %s: %s (run `python -m relationprediction_b200.build`)"
+                        % (LIB_PATH, e)) from e
+    _declare(lib)
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().rgcn_last_error()
+        raise RgcnError("%s failed (rc=%d): %s" % (what, rc, (msg or b"").decode("utf-8", "replace")))
+
+
+def launch_count():
+    return int(load().rgcn_launch_count())

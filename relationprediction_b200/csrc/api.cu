@@ -1,0 +1,449 @@
+// api.cu -- C-ABI entry points of librgcn_b200.so (see include/rgcn_b200.h).
+// Orchestrates per-layer work on ONE stream: weight re-layout -> dense self-loop GEMM (cuBLAS fp32,
+// a plain library GEMM) -> warp-centric aggregation kernel with the fused epilogue.
+#include <cublas_v2.h>
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <string>
+
+#include "kernels.cuh"
+
+namespace {
+
+std::mutex g_cublas_mu;
+cublasHandle_t g_cublas[64] = {nullptr};
+
+int get_cublas(int device, cudaStream_t st, cublasHandle_t* out) {
+  if (device < 0 || device >= 64) {
+    rgcn_set_error("bad device ordinal");
+    return RGCN_ERR_INVALID;
+  }
+  std::lock_guard<std::mutex> lk(g_cublas_mu);
+  if (!g_cublas[device]) {
+    cublasStatus_t s = cublasCreate(&g_cublas[device]);
+    if (s != CUBLAS_STATUS_SUCCESS) {
+      g_cublas[device] = nullptr;
+      rgcn_set_error("cublasCreate failed: " + std::to_string((int)s));
+      return RGCN_ERR_CUDA;
+    }
+    // true fp32 accumulate and multiply: the 1e-4 parity bar rules out single-pass TF32
+    cublasSetMathMode(g_cublas[device], CUBLAS_DEFAULT_MATH);
+  }
+  cublasStatus_t s = cublasSetStream(g_cublas[device], st);
+  if (s != CUBLAS_STATUS_SUCCESS) {
+    rgcn_set_error("cublasSetStream failed");
+    return RGCN_ERR_CUDA;
+  }
+  *out = g_cublas[device];
+  return RGCN_OK;
+}
+
+// Row-major GEMM: C[m,n] = alpha * op(A) * op(B) + beta * C, op(A) is m x k, op(B) is k x n.
+int gemm_rm(cublasHandle_t h, bool ta, bool tb, int64_t m, int64_t n, int64_t k, float alpha,
+            const float* A, int64_t lda, const float* B, int64_t ldb, float beta, float* C,
+            int64_t ldc) {
+  if (m == 0 || n == 0) return RGCN_OK;
+  if (k == 0) {
+    // cuBLAS rejects k = 0 with some leading dimensions; emulate beta scaling (beta is 0 or 1 here)
+    if (beta == 0.f) {
+      cudaStream_t st;
+      cublasGetStream(h, &st);
+      return rgcn_check_cuda(cudaMemset2DAsync(C, ldc * sizeof(float), 0, n * sizeof(float), m, st),
+                             "memset2d");
+    }
+    return RGCN_OK;
+  }
+  cublasStatus_t s =
+      cublasSgemm(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, (int)n, (int)m,
+                  (int)k, &alpha, B, (int)ldb, A, (int)lda, &beta, C, (int)ldc);
+  if (s != CUBLAS_STATUS_SUCCESS) {
+    rgcn_set_error("cublasSgemm failed: status " + std::to_string((int)s));
+    return RGCN_ERR_CUDA;
+  }
+  return RGCN_OK;
+}
+
+inline int64_t align_up(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
+struct Carver {
+  char* base;
+  int64_t off = 0;
+  int64_t cap;
+  Carver(void* p, int64_t c) : base((char*)p), cap(c) {}
+  template <typename T>
+  T* take(int64_t count) {
+    T* r = (T*)(base + off);
+    off += align_up(count * (int64_t)sizeof(T));
+    return r;
+  }
+};
+
+int slabs_for(int d) {
+  int nv = (d + 127) / 128;
+  if (nv > 4) nv = 4;
+  return (d + nv * 128 - 1) / (nv * 128);
+}
+
+int common_checks(const rgcn_graph_t* g, int32_t d, int32_t B, const char* who) {
+  if (!g) {
+    rgcn_set_error(std::string(who) + ": null graph");
+    return RGCN_ERR_INVALID;
+  }
+  if (g->device < 0) {
+    rgcn_set_error(std::string(who) + ": graph was built host-only (device = -1)");
+    return RGCN_ERR_NODEVICE;
+  }
+  if (d <= 0 || d % 4 != 0 || B <= 0) {
+    rgcn_set_error(std::string(who) + ": need d > 0, d % 4 == 0, B > 0");
+    return RGCN_ERR_INVALID;
+  }
+  if (g->n_relw % 2 != 0) {
+    rgcn_set_error(std::string(who) + ": graph weight-id count must be 2R");
+    return RGCN_ERR_INVALID;
+  }
+  return RGCN_OK;
+}
+
+AggLaunch make_agg(const CsrSide& side, const float* X, int ldx, int d, float* scratch,
+                   int* counters) {
+  AggLaunch a;
+  a.items = side.d_items;
+  a.n_items = (int)side.items.size();
+  a.nbr = side.d_nbr;
+  a.relw = side.d_relw;
+  a.norm = side.d_norm;
+  a.X = X;
+  a.ldx = ldx;
+  a.d = d;
+  a.split_nitems = side.d_split_nitems;
+  a.scratch = scratch;
+  a.counters = counters;
+  return a;
+}
+
+}  // namespace
+
+extern "C" int64_t rgcn_launch_count(void) { return g_rgcn_launches; }
+
+// ------------------------------------------------------------------------------------------------
+// Block-diagonal layer
+// ------------------------------------------------------------------------------------------------
+extern "C" int64_t rgcn_block_workspace_bytes(const rgcn_graph_t* g, int32_t d, int32_t B,
+                                              int backward) {
+  if (!g || d <= 0 || B <= 0 || d % B != 0) {
+    rgcn_set_error("rgcn_block_workspace_bytes: bad arguments");
+    return RGCN_ERR_INVALID;
+  }
+  const int64_t s = d / B;
+  const int64_t wt = (int64_t)g->n_relw * s * d;
+  const int slabs = slabs_for(d);
+  int64_t bytes = 0;
+  if (!backward) {
+    bytes += align_up(wt * 4);
+    bytes += align_up((int64_t)g->by_dst.split_rows.size() * d * 4);
+    bytes += align_up((int64_t)g->by_dst.split_rows.size() * slabs * 4);
+  } else {
+    bytes += 2 * align_up(wt * 4);
+    bytes += 2 * align_up((int64_t)g->V_dst * d * 4);
+    bytes += align_up((int64_t)g->by_src.split_rows.size() * d * 4);
+    bytes += align_up((int64_t)g->by_src.split_rows.size() * slabs * 4);
+  }
+  return bytes + 256;
+}
+
+extern "C" int rgcn_block_forward(const rgcn_graph_t* g, int32_t d, int32_t B, const float* H,
+                                  const float* Wf, const float* Wb, const float* Wself,
+                                  const uint8_t* drop_mask, float keep, int relu, float* out,
+                                  void* workspace, int64_t workspace_bytes, void* stream) {
+  int rc = common_checks(g, d, B, "rgcn_block_forward");
+  if (rc) return rc;
+  if (d % B != 0) {
+    rgcn_set_error("rgcn_block_forward: d must be a multiple of B (gcn_basis_concat.py:15)");
+    return RGCN_ERR_INVALID;
+  }
+  if (!H || !Wf || !Wb || !Wself || !out || !workspace || keep <= 0.f) {
+    rgcn_set_error("rgcn_block_forward: null pointer or keep <= 0");
+    return RGCN_ERR_INVALID;
+  }
+  if (workspace_bytes < rgcn_block_workspace_bytes(g, d, B, 0)) {
+    rgcn_set_error("rgcn_block_forward: workspace too small");
+    return RGCN_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = rgcn_check_cuda(cudaSetDevice(g->device), "cudaSetDevice");
+  if (rc) return rc;
+  const int s = d / B, R = g->n_relw / 2;
+  const int slabs = slabs_for(d);
+  const int64_t n_split = (int64_t)g->by_dst.split_rows.size();
+  Carver ws(workspace, workspace_bytes);
+  float* Wt = ws.take<float>((int64_t)g->n_relw * s * d);
+  float* scratch = ws.take<float>(n_split * d);
+  int* counters = ws.take<int>(n_split * slabs);
+
+  rc = launch_block_relayout(Wf, Wb, R, B, s, /*transpose=*/0, Wt, st);
+  if (rc) return rc;
+  if (n_split > 0) {
+    rc = rgcn_check_cuda(
+        cudaMemsetAsync(scratch, 0, (char*)(counters + n_split * slabs) - (char*)scratch, st),
+        "memset(scratch)");
+    if (rc) return rc;
+  }
+  cublasHandle_t h;
+  rc = get_cublas(g->device, st, &h);
+  if (rc) return rc;
+  // self-loop term S = H[0:V_dst] @ W_self written straight into `out` (gcn_basis_concat.py:65-66)
+  rc = gemm_rm(h, false, false, g->V_dst, d, d, 1.f, H, d, Wself, d, 0.f, out, d);
+  if (rc) return rc;
+  AggLaunch a = make_agg(g->by_dst, H, d, d, scratch, counters);
+  return launch_block_agg(a, s, Wt, out, drop_mask, 1.0f / keep, relu, st);
+}
+
+extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, const float* H,
+                                   const float* Wf, const float* Wb, const float* Wself,
+                                   const uint8_t* drop_mask, float keep, int relu, const float* out,
+                                   const float* dOut, float* dH, float* dWf, float* dWb,
+                                   float* dWself, void* workspace, int64_t workspace_bytes,
+                                   void* stream) {
+  int rc = common_checks(g, d, B, "rgcn_block_backward");
+  if (rc) return rc;
+  if (d % B != 0) {
+    rgcn_set_error("rgcn_block_backward: d must be a multiple of B");
+    return RGCN_ERR_INVALID;
+  }
+  if (!H || !Wf || !Wb || !Wself || !dOut || !dH || !dWf || !dWb || !dWself || !workspace ||
+      (relu && !out) || keep <= 0.f) {
+    rgcn_set_error("rgcn_block_backward: null pointer or keep <= 0");
+    return RGCN_ERR_INVALID;
+  }
+  if (workspace_bytes < rgcn_block_workspace_bytes(g, d, B, 1)) {
+    rgcn_set_error("rgcn_block_backward: workspace too small");
+    return RGCN_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = rgcn_check_cuda(cudaSetDevice(g->device), "cudaSetDevice");
+  if (rc) return rc;
+  const int s = d / B, R = g->n_relw / 2;
+  const int slabs = slabs_for(d);
+  const int64_t n_split = (int64_t)g->by_src.split_rows.size();
+  const int64_t wt = (int64_t)g->n_relw * s * d;
+  Carver ws(workspace, workspace_bytes);
+  float* Wtt = ws.take<float>(wt);
+  float* dWt = ws.take<float>(wt);
+  float* G = ws.take<float>((int64_t)g->V_dst * d);
+  float* dS = ws.take<float>((int64_t)g->V_dst * d);
+  float* scratch = ws.take<float>(n_split * d);
+  int* counters = ws.take<int>(n_split * slabs);
+  if (!drop_mask) dS = G;
+
+  // G = dOut * relu'(out);  dS = G * mask / keep   (message_gcn.py:64 dropout is on the self loop only)
+  rc = launch_grad_prologue(dOut, out, drop_mask, 1.0f / keep, relu, (int64_t)g->V_dst * d, G, dS, st);
+  if (rc) return rc;
+  cublasHandle_t h;
+  rc = get_cublas(g->device, st, &h);
+  if (rc) return rc;
+  // dW_self = H[0:V_dst]^T dS
+  rc = gemm_rm(h, true, false, d, d, g->V_dst, 1.f, H, d, dS, d, 0.f, dWself, d);
+  if (rc) return rc;
+  // dH[0:V_dst] = dS W_self^T ; halo rows start at zero
+  rc = gemm_rm(h, false, true, g->V_dst, d, d, 1.f, dS, d, Wself, d, 0.f, dH, d);
+  if (rc) return rc;
+  if (g->V_src > g->V_dst) {
+    rc = rgcn_check_cuda(cudaMemsetAsync(dH + (size_t)g->V_dst * d, 0,
+                                         (size_t)(g->V_src - g->V_dst) * d * sizeof(float), st),
+                         "memset(dH halo)");
+    if (rc) return rc;
+  }
+  // dH[u] += sum_{m: src_m = u} norm_m W[relw_m]^T G[dst_m]   (same kernel, transposed table)
+  rc = launch_block_relayout(Wf, Wb, R, B, s, /*transpose=*/1, Wtt, st);
+  if (rc) return rc;
+  if (n_split > 0) {
+    rc = rgcn_check_cuda(
+        cudaMemsetAsync(scratch, 0, (char*)(counters + n_split * slabs) - (char*)scratch, st),
+        "memset(scratch)");
+    if (rc) return rc;
+  }
+  AggLaunch a = make_agg(g->by_src, G, d, d, scratch, counters);
+  rc = launch_block_agg(a, s, Wtt, dH, nullptr, 1.f, 0, st);
+  if (rc) return rc;
+  // dW[w] = sum_{m: relw_m = w} norm_m G[dst_m] (x)_block H[src_m]
+  rc = rgcn_check_cuda(cudaMemsetAsync(dWt, 0, wt * sizeof(float), st), "memset(dWt)");
+  if (rc) return rc;
+  rc = launch_block_dw(g->by_rel.d_items, (int)g->by_rel.items.size(), g->by_rel.d_dst,
+                       g->by_rel.d_src, g->by_rel.d_norm, H, d, G, d, d, s, dWt, st);
+  if (rc) return rc;
+  return launch_block_unlayout(dWt, R, B, s, dWf, dWb, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Basis layer
+// ------------------------------------------------------------------------------------------------
+extern "C" int64_t rgcn_basis_workspace_bytes(const rgcn_graph_t* g, int32_t d, int32_t B,
+                                              int backward) {
+  if (!g || d <= 0 || B <= 0) {
+    rgcn_set_error("rgcn_basis_workspace_bytes: bad arguments");
+    return RGCN_ERR_INVALID;
+  }
+  int64_t bytes = align_up((int64_t)g->n_relw * B * 4);  // concatenated coefficient table
+  if (backward) {
+    bytes += align_up((int64_t)g->n_relw * B * 4);           // dC (concatenated)
+    bytes += 2 * align_up((int64_t)g->V_dst * d * 4);        // G, dS
+    bytes += align_up((int64_t)g->V_dst * 2 * d * B * 4);    // dAgg
+    bytes += align_up((int64_t)g->V_src * 2 * d * B * 4);    // P (planar)
+  }
+  return bytes + 256;
+}
+
+extern "C" int rgcn_basis_forward(const rgcn_graph_t* g, int32_t d, int32_t B, const float* H,
+                                  const float* Vf, const float* Vb, const float* Cf,
+                                  const float* Cb, const float* Wself, const uint8_t* drop_mask,
+                                  float keep, int relu, float* out, float* saved, void* workspace,
+                                  int64_t workspace_bytes, void* stream) {
+  int rc = common_checks(g, d, B, "rgcn_basis_forward");
+  if (rc) return rc;
+  if (!H || !Vf || !Vb || !Cf || !Cb || !Wself || !out || !saved || !workspace || keep <= 0.f) {
+    rgcn_set_error("rgcn_basis_forward: null pointer or keep <= 0");
+    return RGCN_ERR_INVALID;
+  }
+  if (workspace_bytes < rgcn_basis_workspace_bytes(g, d, B, 0)) {
+    rgcn_set_error("rgcn_basis_forward: workspace too small");
+    return RGCN_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = rgcn_check_cuda(cudaSetDevice(g->device), "cudaSetDevice");
+  if (rc) return rc;
+  const int R = g->n_relw / 2;
+  const int64_t dB = (int64_t)d * B;
+  Carver ws(workspace, workspace_bytes);
+  float* Ccat = ws.take<float>((int64_t)g->n_relw * B);
+  rc = rgcn_check_cuda(cudaMemcpyAsync(Ccat, Cf, (size_t)R * B * 4, cudaMemcpyDeviceToDevice, st), "copy Cf");
+  if (!rc) rc = rgcn_check_cuda(cudaMemcpyAsync(Ccat + (size_t)R * B, Cb, (size_t)R * B * 4, cudaMemcpyDeviceToDevice, st), "copy Cb");
+  if (rc) return rc;
+  // Agg[v][dir][k*B+b] = sum_m norm_m C[relw_m,b] H[src_m,k]
+  rc = launch_zero_rows(saved, 2 * dB, g->by_dst.d_split_rows, (int)g->by_dst.split_rows.size(), st);
+  if (rc) return rc;
+  AggLaunch a = make_agg(g->by_dst, H, d, d, nullptr, nullptr);
+  rc = launch_basis_agg(a, Ccat, B, g->n_relw, /*layout=*/0, saved, st);
+  if (rc) return rc;
+  cublasHandle_t h;
+  rc = get_cublas(g->device, st, &h);
+  if (rc) return rc;
+  rc = gemm_rm(h, false, false, g->V_dst, d, d, 1.f, H, d, Wself, d, 0.f, out, d);
+  if (rc) return rc;
+  rc = launch_mask_relu(out, drop_mask, 1.0f / keep, 0, (int64_t)g->V_dst * d, st);
+  if (rc) return rc;
+  // out += Agg_f @ Vf.reshape(d*B, d) + Agg_b @ Vb.reshape(d*B, d)    (gcn_basis.py:60-68 re-associated)
+  rc = gemm_rm(h, false, false, g->V_dst, d, dB, 1.f, saved, 2 * dB, Vf, d, 1.f, out, d);
+  if (rc) return rc;
+  rc = gemm_rm(h, false, false, g->V_dst, d, dB, 1.f, saved + dB, 2 * dB, Vb, d, 1.f, out, d);
+  if (rc) return rc;
+  return launch_mask_relu(out, nullptr, 1.f, relu, (int64_t)g->V_dst * d, st);
+}
+
+extern "C" int rgcn_basis_backward(const rgcn_graph_t* g, int32_t d, int32_t B, const float* H,
+                                   const float* Vf, const float* Vb, const float* Cf,
+                                   const float* Cb, const float* Wself, const uint8_t* drop_mask,
+                                   float keep, int relu, const float* out, const float* saved,
+                                   const float* dOut, float* dH, float* dVf, float* dVb, float* dCf,
+                                   float* dCb, float* dWself, void* workspace,
+                                   int64_t workspace_bytes, void* stream) {
+  int rc = common_checks(g, d, B, "rgcn_basis_backward");
+  if (rc) return rc;
+  if (!H || !Vf || !Vb || !Cf || !Cb || !Wself || !saved || !dOut || !dH || !dVf || !dVb || !dCf ||
+      !dCb || !dWself || !workspace || (relu && !out) || keep <= 0.f) {
+    rgcn_set_error("rgcn_basis_backward: null pointer or keep <= 0");
+    return RGCN_ERR_INVALID;
+  }
+  if (workspace_bytes < rgcn_basis_workspace_bytes(g, d, B, 1)) {
+    rgcn_set_error("rgcn_basis_backward: workspace too small");
+    return RGCN_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = rgcn_check_cuda(cudaSetDevice(g->device), "cudaSetDevice");
+  if (rc) return rc;
+  const int R = g->n_relw / 2;
+  const int64_t dB = (int64_t)d * B;
+  Carver ws(workspace, workspace_bytes);
+  float* Ccat = ws.take<float>((int64_t)g->n_relw * B);
+  float* dCcat = ws.take<float>((int64_t)g->n_relw * B);
+  float* G = ws.take<float>((int64_t)g->V_dst * d);
+  float* dS = ws.take<float>((int64_t)g->V_dst * d);
+  float* dAgg = ws.take<float>((int64_t)g->V_dst * 2 * dB);
+  float* P = ws.take<float>((int64_t)g->V_src * 2 * dB);
+  if (!drop_mask) dS = G;
+  rc = rgcn_check_cuda(cudaMemcpyAsync(Ccat, Cf, (size_t)R * B * 4, cudaMemcpyDeviceToDevice, st), "copy Cf");
+  if (!rc) rc = rgcn_check_cuda(cudaMemcpyAsync(Ccat + (size_t)R * B, Cb, (size_t)R * B * 4, cudaMemcpyDeviceToDevice, st), "copy Cb");
+  if (rc) return rc;
+
+  rc = launch_grad_prologue(dOut, out, drop_mask, 1.0f / keep, relu, (int64_t)g->V_dst * d, G, dS, st);
+  if (rc) return rc;
+  cublasHandle_t h;
+  rc = get_cublas(g->device, st, &h);
+  if (rc) return rc;
+  rc = gemm_rm(h, true, false, d, d, g->V_dst, 1.f, H, d, dS, d, 0.f, dWself, d);
+  if (rc) return rc;
+  rc = gemm_rm(h, false, true, g->V_dst, d, d, 1.f, dS, d, Wself, d, 0.f, dH, d);
+  if (rc) return rc;
+  if (g->V_src > g->V_dst) {
+    rc = rgcn_check_cuda(cudaMemsetAsync(dH + (size_t)g->V_dst * d, 0,
+                                         (size_t)(g->V_src - g->V_dst) * d * sizeof(float), st),
+                         "memset(dH halo)");
+    if (rc) return rc;
+  }
+  // dV_dir.reshape(d*B, d) = Agg_dir^T G
+  rc = gemm_rm(h, true, false, dB, d, g->V_dst, 1.f, saved, 2 * dB, G, d, 0.f, dVf, d);
+  if (rc) return rc;
+  rc = gemm_rm(h, true, false, dB, d, g->V_dst, 1.f, saved + dB, 2 * dB, G, d, 0.f, dVb, d);
+  if (rc) return rc;
+  // dAgg_dir = G V_dir.reshape(d*B, d)^T
+  rc = gemm_rm(h, false, true, g->V_dst, dB, d, 1.f, G, d, Vf, d, 0.f, dAgg, 2 * dB);
+  if (rc) return rc;
+  rc = gemm_rm(h, false, true, g->V_dst, dB, d, 1.f, G, d, Vb, d, 0.f, dAgg + dB, 2 * dB);
+  if (rc) return rc;
+  // dC[w,b] = sum_m norm_m < H[src_m], dAgg[dst_m][dir][:,b] >
+  rc = rgcn_check_cuda(cudaMemsetAsync(dCcat, 0, (size_t)g->n_relw * B * 4, st), "memset(dC)");
+  if (rc) return rc;
+  AggLaunch a = make_agg(g->by_dst, H, d, d, nullptr, nullptr);
+  rc = launch_basis_dc(a, dAgg, B, g->n_relw, dCcat, st);
+  if (rc) return rc;
+  rc = rgcn_check_cuda(cudaMemcpyAsync(dCf, dCcat, (size_t)R * B * 4, cudaMemcpyDeviceToDevice, st), "copy dCf");
+  if (!rc) rc = rgcn_check_cuda(cudaMemcpyAsync(dCb, dCcat + (size_t)R * B, (size_t)R * B * 4, cudaMemcpyDeviceToDevice, st), "copy dCb");
+  if (rc) return rc;
+  // P[u][dir][b*d+n] = sum_{m: src_m=u} norm_m C[relw_m,b] G[dst_m,n];  dH += P_dir V_dir.reshape(d, B*d)^T
+  rc = launch_zero_rows(P, 2 * dB, g->by_src.d_split_rows, (int)g->by_src.split_rows.size(), st);
+  if (rc) return rc;
+  AggLaunch as = make_agg(g->by_src, G, d, d, nullptr, nullptr);
+  rc = launch_basis_agg(as, Ccat, B, g->n_relw, /*layout=*/1, P, st);
+  if (rc) return rc;
+  rc = gemm_rm(h, false, true, g->V_src, d, dB, 1.f, P, 2 * dB, Vf, dB, 1.f, dH, d);
+  if (rc) return rc;
+  return gemm_rm(h, false, true, g->V_src, d, dB, 1.f, P + dB, 2 * dB, Vb, dB, 1.f, dH, d);
+}
+
+// ------------------------------------------------------------------------------------------------
+// DistMult
+// ------------------------------------------------------------------------------------------------
+extern "C" int distmult_forward(const float* codes, const float* rel, int32_t V, int32_t Vrel,
+                                int32_t d, const int32_t* X, int64_t N, const float* Y,
+                                float* energies, float* loss_out, void* stream) {
+  if (!codes || !rel || (N > 0 && (!X || !energies)) || !loss_out || d <= 0 || d % 4 != 0 || V <= 0 ||
+      Vrel <= 0 || N < 0) {
+    rgcn_set_error("distmult_forward: bad arguments (need d % 4 == 0, non-null pointers)");
+    return RGCN_ERR_INVALID;
+  }
+  return launch_distmult_forward(codes, rel, d, X, N, Y, energies, loss_out, (cudaStream_t)stream);
+}
+
+extern "C" int distmult_backward(const float* codes, const float* rel, int32_t V, int32_t Vrel,
+                                 int32_t d, const int32_t* X, int64_t N, const float* Y,
+                                 const float* energies, float g_loss, float g_reg,
+                                 const float* g_scale_dev, const float* g_energy, float* dcodes,
+                                 float* drel, void* stream) {
+  if (!codes || !rel || (N > 0 && !X) || !dcodes || !drel || d <= 0 || d % 4 != 0 || V <= 0 ||
+      Vrel <= 0 || N < 0 || (Y && !energies)) {
+    rgcn_set_error("distmult_backward: bad arguments");
+    return RGCN_ERR_INVALID;
+  }
+  return launch_distmult_backward(codes, rel, d, X, N, Y, energies, g_loss, g_reg, g_scale_dev,
+                                  g_energy, dcodes, drel, (cudaStream_t)stream);
+}

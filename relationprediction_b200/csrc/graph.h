@@ -1,0 +1,63 @@
+// graph.h -- internal definition of the opaque rgcn_graph handle (host structure + device mirrors).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rgcn_b200.h"
+
+// A warp work item: messages [beg,end) of ONE row (destination row, source row or weight id).
+// split = -1 when the row is covered by this single item, otherwise the index of the row in the
+// split-row list (rows with more than `item_max` messages are cut into several items whose partial
+// sums are combined with vector reductions in L2; the last arriver applies the epilogue).
+struct WorkItem {
+  int32_t beg, end, row, split;
+};
+
+struct CsrSide {
+  // host
+  std::vector<int32_t> rowptr;  // [rows+1]
+  std::vector<int32_t> nbr;     // [M] the "other end" (gather index)
+  std::vector<int32_t> relw;    // [M]
+  std::vector<float> norm;      // [M]
+  std::vector<int32_t> mid;     // [M] original message id
+  std::vector<WorkItem> items;
+  std::vector<int32_t> split_nitems;  // per split row: how many items cover it
+  std::vector<int32_t> split_rows;    // per split row: the row id
+  // device mirrors
+  int32_t* d_nbr = nullptr;
+  int32_t* d_relw = nullptr;
+  float* d_norm = nullptr;
+  WorkItem* d_items = nullptr;
+  int32_t* d_split_nitems = nullptr;
+  int32_t* d_split_rows = nullptr;
+};
+
+struct RelSide {
+  std::vector<int32_t> ptr;  // [n_relw+1]
+  std::vector<int32_t> dst, src, mid;
+  std::vector<float> norm;
+  std::vector<WorkItem> items;  // row = weight id, split unused
+  int32_t* d_dst = nullptr;
+  int32_t* d_src = nullptr;
+  float* d_norm = nullptr;
+  WorkItem* d_items = nullptr;
+};
+
+struct rgcn_graph {
+  int64_t M = 0;
+  int32_t V_dst = 0, V_src = 0, n_relw = 0;
+  int device = -1;
+  int item_max = 128;
+  int64_t n_groups = 0;       // number of (dst, relw) runs in destination-major order
+  int64_t device_bytes = 0;
+  std::vector<float> msg_norm;  // [M] original order
+  CsrSide by_dst;               // rows = destinations, nbr = source
+  CsrSide by_src;               // rows = sources,      nbr = destination
+  RelSide by_rel;               // weight-id major, sorted by (relw, dst)
+};
+
+void rgcn_set_error(const std::string& s);
+int rgcn_check_cuda(cudaError_t e, const char* what);

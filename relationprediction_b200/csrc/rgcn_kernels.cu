@@ -1,0 +1,894 @@
+// rgcn_kernels.cu -- sm_100a kernels of the R-GCN relational message-passing hot path.
+//
+// Design: every kernel is WARP-CENTRIC.  A warp owns one work item = a run of at
+// most `item_max` messages of ONE row of a sorted message list (graph.cu).  A lane owns NV float4
+// "quads" of the feature row (columns c0 + 4*(lane + 32k)), so one message = NV coalesced 128-bit
+// loads per lane (a 2000/2048-byte row is 4 LDG.128 per lane), U messages are kept in flight per
+// lane, and all reductions over messages happen in registers: no atomics per message, none at all
+// for rows that fit one item.  Rows cut into several items combine their partial sums with vector
+// reductions (red.global.add.v4.f32) into an L2-resident scratch row; the last arriver applies the
+// epilogue.
+//
+// Block-diagonal trick: messages of a row are sorted by weight id, and blockdiag(W_r) is linear, so
+// for a run of messages with the same (row, weight id) we first sum norm_m * x_m and apply W_r
+// ONCE per run (FB15k-237: 544k messages -> 150k runs).  The weight tables are re-laid out per
+// call into [w][j][d] ("j-major") so the per-run weight read is s*NV coalesced 128-bit loads that
+// hit L2/L1, and the per-edge [E,B,s,s] weight gather of the reference
+// (gcn_basis_concat.py:38-39) is never materialised.
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+
+int64_t g_rgcn_launches = 0;
+
+#define FULL 0xffffffffu
+
+namespace {
+
+constexpr int U_MSG = 4;  // messages in flight per lane
+
+__device__ __forceinline__ float4 ldg4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ float4 ldcg4(const float* p) {
+  return __ldcg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void red4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void red1(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void fma4(float4& a, float s, const float4& x) {
+  a.x = fmaf(s, x.x, a.x);
+  a.y = fmaf(s, x.y, a.y);
+  a.z = fmaf(s, x.z, a.z);
+  a.w = fmaf(s, x.w, a.w);
+}
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+template <int S>
+__device__ __forceinline__ int blk_base(int col, int s_rt) {
+  if constexpr (S > 0) return (col / S) * S;
+  return (col / s_rt) * s_rt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block-diagonal aggregation.
+// ------------------------------------------------------------------------------------------------
+template <int S, int NV>
+__device__ __forceinline__ void block_apply(float4 (&acc)[NV], const float4 (&xs)[NV], float* xbuf,
+                                            const float* __restrict__ wr, int d, int s, int c0,
+                                            int lane) {
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int lc = 4 * (lane + 32 * k);
+    if (c0 + lc < d) *reinterpret_cast<float4*>(xbuf + lc) = xs[k];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < (S > 0 ? S : 1); ++j) {
+    // runtime-s variant loops below
+    if (S > 0) {
+      const float* wj = wr + (size_t)j * d;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int lc = 4 * (lane + 32 * k);
+        const int col = c0 + lc;
+        if (col < d) {
+          const float4 w = ldg4(wj + col);
+          if (S % 4 == 0) {
+            const float x = xbuf[blk_base<S>(col, s) - c0 + j];
+            acc[k].x = fmaf(w.x, x, acc[k].x);
+            acc[k].y = fmaf(w.y, x, acc[k].y);
+            acc[k].z = fmaf(w.z, x, acc[k].z);
+            acc[k].w = fmaf(w.w, x, acc[k].w);
+          } else {
+            acc[k].x = fmaf(w.x, xbuf[blk_base<S>(col + 0, s) - c0 + j], acc[k].x);
+            acc[k].y = fmaf(w.y, xbuf[blk_base<S>(col + 1, s) - c0 + j], acc[k].y);
+            acc[k].z = fmaf(w.z, xbuf[blk_base<S>(col + 2, s) - c0 + j], acc[k].z);
+            acc[k].w = fmaf(w.w, xbuf[blk_base<S>(col + 3, s) - c0 + j], acc[k].w);
+          }
+        }
+      }
+    }
+  }
+  if (S == 0) {
+    for (int j = 0; j < s; ++j) {
+      const float* wj = wr + (size_t)j * d;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int lc = 4 * (lane + 32 * k);
+        const int col = c0 + lc;
+        if (col < d) {
+          const float4 w = ldg4(wj + col);
+          acc[k].x = fmaf(w.x, xbuf[blk_base<0>(col + 0, s) - c0 + j], acc[k].x);
+          acc[k].y = fmaf(w.y, xbuf[blk_base<0>(col + 1, s) - c0 + j], acc[k].y);
+          acc[k].z = fmaf(w.z, xbuf[blk_base<0>(col + 2, s) - c0 + j], acc[k].z);
+          acc[k].w = fmaf(w.w, xbuf[blk_base<0>(col + 3, s) - c0 + j], acc[k].w);
+        }
+      }
+    }
+  }
+}
+
+template <int S, int NV>
+__global__ void __launch_bounds__(RGCN_THREADS, 2)
+    k_block_agg(AggLaunch a, int s_rt, const float* __restrict__ Wt, float* __restrict__ out,
+                const uint8_t* __restrict__ mask, float inv_keep, int relu) {
+  __shared__ __align__(16) float xbuf_all[RGCN_WARPS_PER_BLOCK][NV * 128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * RGCN_WARPS_PER_BLOCK + warp;
+  if (item >= a.n_items) return;
+  const int s = S > 0 ? S : s_rt;
+  const int d = a.d;
+  const int c0 = blockIdx.y * (NV * 128);
+  float* xbuf = xbuf_all[warp];
+  const int4 itv = __ldg(reinterpret_cast<const int4*>(a.items) + item);
+  const int beg = itv.x, end = itv.y, row = itv.z, split = itv.w;
+
+  float4 acc[NV], xs[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc[k] = xs[k] = zero4();
+  int cur = -1;
+
+  for (int base = beg; base < end; base += 32) {
+    const int n = min(32, end - base);
+    int my_nbr = 0, my_rw = 0;
+    float my_nm = 0.f;
+    if (lane < n) {
+      my_nbr = __ldg(a.nbr + base + lane);
+      my_rw = __ldg(a.relw + base + lane);
+      my_nm = __ldg(a.norm + base + lane);
+    }
+    for (int t = 0; t < n; t += U_MSG) {
+      float4 x[U_MSG][NV];
+      int rw[U_MSG];
+      float nm[U_MSG];
+#pragma unroll
+      for (int u = 0; u < U_MSG; ++u) {
+        const int tt = min(t + u, n - 1);  // tail: re-read the last row, weight forced to 0 below
+        const int src = __shfl_sync(FULL, my_nbr, tt);
+        rw[u] = __shfl_sync(FULL, my_rw, tt);
+        nm[u] = __shfl_sync(FULL, my_nm, tt);
+        const float* xr = a.X + (size_t)src * a.ldx + c0;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const int lc = 4 * (lane + 32 * k);
+          x[u][k] = (c0 + lc < d) ? ldg4(xr + lc) : zero4();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U_MSG; ++u) {
+        if (t + u < n) {
+          if (rw[u] != cur) {
+            if (cur >= 0)
+              block_apply<S, NV>(acc, xs, xbuf, Wt + (size_t)cur * s * d, d, s, c0, lane);
+            cur = rw[u];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) xs[k] = zero4();
+          }
+#pragma unroll
+          for (int k = 0; k < NV; ++k) fma4(xs[k], nm[u], x[u][k]);
+        }
+      }
+    }
+  }
+  if (cur >= 0) block_apply<S, NV>(acc, xs, xbuf, Wt + (size_t)cur * s * d, d, s, c0, lane);
+
+  // ---- epilogue ----
+  bool do_epilogue = true;
+  if (split >= 0) {
+    float* sc = a.scratch + (size_t)split * d + c0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int lc = 4 * (lane + 32 * k);
+      if (c0 + lc < d) red4(sc + lc, acc[k]);
+    }
+    __threadfence();
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) {
+      const int old = atomicAdd(a.counters + (size_t)split * gridDim.y + blockIdx.y, 1);
+      last = (old == __ldg(a.split_nitems + split) - 1);
+    }
+    last = __shfl_sync(FULL, last, 0);
+    do_epilogue = last != 0;
+    if (do_epilogue) {
+      __threadfence();
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int lc = 4 * (lane + 32 * k);
+        if (c0 + lc < d) acc[k] = ldcg4(sc + lc);
+      }
+    }
+  }
+  if (do_epilogue) {
+    float* po = out + (size_t)row * d + c0;
+    const uint8_t* pm = mask ? mask + (size_t)row * d + c0 : nullptr;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int lc = 4 * (lane + 32 * k);
+      if (c0 + lc < d) {
+        float4 sl = *reinterpret_cast<const float4*>(po + lc);
+        if (pm) {
+          const uchar4 mk = *reinterpret_cast<const uchar4*>(pm + lc);
+          sl.x = mk.x ? sl.x * inv_keep : 0.f;
+          sl.y = mk.y ? sl.y * inv_keep : 0.f;
+          sl.z = mk.z ? sl.z * inv_keep : 0.f;
+          sl.w = mk.w ? sl.w * inv_keep : 0.f;
+        }
+        float4 r = make_float4(acc[k].x + sl.x, acc[k].y + sl.y, acc[k].z + sl.z, acc[k].w + sl.w);
+        if (relu) {
+          r.x = fmaxf(r.x, 0.f);
+          r.y = fmaxf(r.y, 0.f);
+          r.z = fmaxf(r.z, 0.f);
+          r.w = fmaxf(r.w, 0.f);
+        }
+        *reinterpret_cast<float4*>(po + lc) = r;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block-diagonal weight gradient (weight-id major list sorted by (weight id, dst)).
+// Runs of messages with the same destination share G[dst]: sum norm*H[src] first, then ONE outer
+// product per run.  Accumulators acc[JC][NV] live in registers; partial results of the items of one
+// weight id are combined with vector reductions into dWt (zeroed by the caller).
+// ------------------------------------------------------------------------------------------------
+template <int S, int JC, int NV>
+__global__ void __launch_bounds__(RGCN_THREADS, 1)
+    k_block_dw(const WorkItem* __restrict__ items, int n_items, const int32_t* __restrict__ r_dst,
+               const int32_t* __restrict__ r_src, const float* __restrict__ r_norm,
+               const float* __restrict__ H, int ldh, const float* __restrict__ G, int ldg, int d,
+               int s_rt, float* __restrict__ dWt) {
+  __shared__ __align__(16) float xbuf_all[RGCN_WARPS_PER_BLOCK][NV * 128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * RGCN_WARPS_PER_BLOCK + warp;
+  if (item >= n_items) return;
+  const int s = S > 0 ? S : s_rt;
+  const int c0 = blockIdx.y * (NV * 128);
+  float* xbuf = xbuf_all[warp];
+  const int4 itv = __ldg(reinterpret_cast<const int4*>(items) + item);
+  const int beg = itv.x, end = itv.y, w = itv.z;
+
+  for (int j0 = 0; j0 < s; j0 += JC) {
+    float4 acc[JC][NV], hs[NV];
+#pragma unroll
+    for (int jj = 0; jj < JC; ++jj)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) acc[jj][k] = zero4();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) hs[k] = zero4();
+    int cur = -1;
+
+    auto flush = [&](int dstv) {
+      float4 g[NV];
+      const float* gr = G + (size_t)dstv * ldg + c0;
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int lc = 4 * (lane + 32 * k);
+        if (c0 + lc < d) {
+          g[k] = ldg4(gr + lc);
+          *reinterpret_cast<float4*>(xbuf + lc) = hs[k];
+        } else {
+          g[k] = zero4();
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int jj = 0; jj < JC; ++jj) {
+        const int j = j0 + jj;
+        if (j < s) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            const int lc = 4 * (lane + 32 * k);
+            const int col = c0 + lc;
+            if (col < d) {
+              if (S > 0 && S % 4 == 0) {
+                const float x = xbuf[blk_base<S>(col, s) - c0 + j];
+                fma4(acc[jj][k], x, g[k]);
+              } else {
+                acc[jj][k].x = fmaf(g[k].x, xbuf[blk_base<S>(col + 0, s) - c0 + j], acc[jj][k].x);
+                acc[jj][k].y = fmaf(g[k].y, xbuf[blk_base<S>(col + 1, s) - c0 + j], acc[jj][k].y);
+                acc[jj][k].z = fmaf(g[k].z, xbuf[blk_base<S>(col + 2, s) - c0 + j], acc[jj][k].z);
+                acc[jj][k].w = fmaf(g[k].w, xbuf[blk_base<S>(col + 3, s) - c0 + j], acc[jj][k].w);
+              }
+            }
+          }
+        }
+      }
+    };
+
+    for (int base = beg; base < end; base += 32) {
+      const int n = min(32, end - base);
+      int my_dst = 0, my_src = 0;
+      float my_nm = 0.f;
+      if (lane < n) {
+        my_dst = __ldg(r_dst + base + lane);
+        my_src = __ldg(r_src + base + lane);
+        my_nm = __ldg(r_norm + base + lane);
+      }
+      for (int t = 0; t < n; t += U_MSG) {
+        float4 x[U_MSG][NV];
+        int dv[U_MSG];
+        float nm[U_MSG];
+#pragma unroll
+        for (int u = 0; u < U_MSG; ++u) {
+          const int tt = min(t + u, n - 1);
+          const int src = __shfl_sync(FULL, my_src, tt);
+          dv[u] = __shfl_sync(FULL, my_dst, tt);
+          nm[u] = __shfl_sync(FULL, my_nm, tt);
+          const float* xr = H + (size_t)src * ldh + c0;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            const int lc = 4 * (lane + 32 * k);
+            x[u][k] = (c0 + lc < d) ? ldg4(xr + lc) : zero4();
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U_MSG; ++u) {
+          if (t + u < n) {
+            if (dv[u] != cur) {
+              if (cur >= 0) flush(cur);
+              cur = dv[u];
+#pragma unroll
+              for (int k = 0; k < NV; ++k) hs[k] = zero4();
+            }
+#pragma unroll
+            for (int k = 0; k < NV; ++k) fma4(hs[k], nm[u], x[u][k]);
+          }
+        }
+      }
+    }
+    if (cur >= 0) flush(cur);
+
+#pragma unroll
+    for (int jj = 0; jj < JC; ++jj) {
+      const int j = j0 + jj;
+      if (j < s) {
+        float* pw = dWt + ((size_t)w * s + j) * d + c0;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const int lc = 4 * (lane + 32 * k);
+          if (c0 + lc < d) red4(pw + lc, acc[jj][k]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight-table re-layouts (tiny, L2-resident).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_block_relayout(const float* __restrict__ Wf, const float* __restrict__ Wb, int R,
+                                 int B, int s, int transpose, float* __restrict__ Wt) {
+  const int d = B * s;
+  const int64_t per = (int64_t)d * s;
+  const int64_t total = 2 * (int64_t)R * per;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    // destination index: [w][q][col]   with col = b*s + p
+    const int w = (int)(idx / per);
+    const int rem = (int)(idx % per);
+    const int q = rem / d;
+    const int col = rem % d;
+    const int b = col / s, p = col % s;
+    // forward  (transpose=0): Wt[w][j=q][b*s+i=p] = W[b][i=p][j=q]
+    // backward (transpose=1): Wt[w][i=q][b*s+j=p] = W[b][i=q][j=p]
+    const int i = transpose ? q : p;
+    const int j = transpose ? p : q;
+    const float* W = (w < R) ? Wf + (size_t)w * per : Wb + (size_t)(w - R) * per;
+    Wt[idx] = __ldg(W + ((size_t)b * s + i) * s + j);
+  }
+}
+
+__global__ void k_block_unlayout(const float* __restrict__ dWt, int R, int B, int s,
+                                 float* __restrict__ dWf, float* __restrict__ dWb) {
+  const int d = B * s;
+  const int64_t per = (int64_t)d * s;
+  const int64_t total = 2 * (int64_t)R * per;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    // destination index: [w][b][i][j]
+    const int w = (int)(idx / per);
+    const int rem = (int)(idx % per);
+    const int b = rem / (s * s);
+    const int i = (rem / s) % s;
+    const int j = rem % s;
+    const float v = __ldg(dWt + ((size_t)w * s + j) * d + b * s + i);
+    if (w < R)
+      dWf[(size_t)w * per + rem] = v;
+    else
+      dWb[(size_t)(w - R) * per + rem] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Basis aggregation:  Agg[row][dir][k,b] = sum_m norm_m * C[relw_m, b] * X[nbr_m, k]
+// ------------------------------------------------------------------------------------------------
+template <int BC, int NV, int LAYOUT>
+__global__ void __launch_bounds__(RGCN_THREADS, 1)
+    k_basis_agg(AggLaunch a, const float* __restrict__ C, int B, int half, float* __restrict__ Agg) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * RGCN_WARPS_PER_BLOCK + warp;
+  if (item >= a.n_items) return;
+  const int d = a.d;
+  const int c0 = blockIdx.y * (NV * 128);
+  const int4 itv = __ldg(reinterpret_cast<const int4*>(a.items) + item);
+  const int beg = itv.x, end = itv.y, row = itv.z, split = itv.w;
+  const size_t dB = (size_t)d * B;
+  float* arow = Agg + (size_t)row * 2 * dB;
+
+  for (int b0 = 0; b0 < B; b0 += BC) {
+    float4 acc[BC][NV], xs[NV];
+#pragma unroll
+    for (int b = 0; b < BC; ++b)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) acc[b][k] = zero4();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) xs[k] = zero4();
+    int cur = -1, curdir = -1, written = 0;
+
+    auto write_out = [&](int dir) {
+      float* ad = arow + (size_t)dir * dB;
+#pragma unroll
+      for (int b = 0; b < BC; ++b) {
+        if (b0 + b < B) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            const int col = c0 + 4 * (lane + 32 * k);
+            if (col < d) {
+              if (LAYOUT == 1) {
+                float* p = ad + (size_t)(b0 + b) * d + col;
+                if (split >= 0)
+                  red4(p, acc[b][k]);
+                else
+                  *reinterpret_cast<float4*>(p) = acc[b][k];
+              } else {
+                float* p = ad + (size_t)col * B + (b0 + b);
+                if (split >= 0) {
+                  red1(p, acc[b][k].x);
+                  red1(p + B, acc[b][k].y);
+                  red1(p + 2 * B, acc[b][k].z);
+                  red1(p + 3 * B, acc[b][k].w);
+                } else {
+                  p[0] = acc[b][k].x;
+                  p[B] = acc[b][k].y;
+                  p[2 * B] = acc[b][k].z;
+                  p[3 * B] = acc[b][k].w;
+                }
+              }
+            }
+          }
+        }
+      }
+      written |= (1 << dir);
+    };
+    auto flush = [&](int w) {
+      const int dir = (w >= half) ? 1 : 0;
+      if (dir != curdir) {
+        if (curdir >= 0) write_out(curdir);
+#pragma unroll
+        for (int b = 0; b < BC; ++b)
+#pragma unroll
+          for (int k = 0; k < NV; ++k) acc[b][k] = zero4();
+        curdir = dir;
+      }
+#pragma unroll
+      for (int b = 0; b < BC; ++b) {
+        const float cb = (b0 + b < B) ? __ldg(C + (size_t)w * B + b0 + b) : 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) fma4(acc[b][k], cb, xs[k]);
+      }
+    };
+
+    for (int base = beg; base < end; base += 32) {
+      const int n = min(32, end - base);
+      int my_nbr = 0, my_rw = 0;
+      float my_nm = 0.f;
+      if (lane < n) {
+        my_nbr = __ldg(a.nbr + base + lane);
+        my_rw = __ldg(a.relw + base + lane);
+        my_nm = __ldg(a.norm + base + lane);
+      }
+      for (int t = 0; t < n; t += U_MSG) {
+        float4 x[U_MSG][NV];
+        int rw[U_MSG];
+        float nm[U_MSG];
+#pragma unroll
+        for (int u = 0; u < U_MSG; ++u) {
+          const int tt = min(t + u, n - 1);
+          const int src = __shfl_sync(FULL, my_nbr, tt);
+          rw[u] = __shfl_sync(FULL, my_rw, tt);
+          nm[u] = __shfl_sync(FULL, my_nm, tt);
+          const float* xr = a.X + (size_t)src * a.ldx + c0;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            const int lc = 4 * (lane + 32 * k);
+            x[u][k] = (c0 + lc < d) ? ldg4(xr + lc) : zero4();
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U_MSG; ++u) {
+          if (t + u < n) {
+            if (rw[u] != cur) {
+              if (cur >= 0) flush(cur);
+              cur = rw[u];
+#pragma unroll
+              for (int k = 0; k < NV; ++k) xs[k] = zero4();
+            }
+#pragma unroll
+            for (int k = 0; k < NV; ++k) fma4(xs[k], nm[u], x[u][k]);
+          }
+        }
+      }
+    }
+    if (cur >= 0) flush(cur);
+    if (curdir >= 0) write_out(curdir);
+    if (split < 0) {
+      // directions that received no message: explicit zeros (Agg is not pre-zeroed for these rows)
+#pragma unroll
+      for (int b = 0; b < BC; ++b)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[b][k] = zero4();
+      if (!(written & 1)) write_out(0);
+      if (!(written & 2)) write_out(1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Basis coefficient gradient.
+// ------------------------------------------------------------------------------------------------
+template <int BC, int NV>
+__global__ void __launch_bounds__(RGCN_THREADS, 1)
+    k_basis_dc(AggLaunch a, const float* __restrict__ dAgg, int B, int half, float* __restrict__ dC) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * RGCN_WARPS_PER_BLOCK + warp;
+  if (item >= a.n_items) return;
+  const int d = a.d;
+  const int c0 = blockIdx.y * (NV * 128);
+  const int4 itv = __ldg(reinterpret_cast<const int4*>(a.items) + item);
+  const int beg = itv.x, end = itv.y, row = itv.z;
+  if (beg == end) return;
+  const size_t dB = (size_t)d * B;
+  const float* drow = dAgg + (size_t)row * 2 * dB;
+
+  for (int b0 = 0; b0 < B; b0 += BC) {
+    float4 da[BC][NV], xs[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) xs[k] = zero4();
+    int cur = -1, loaded = -1;
+
+    auto flush = [&](int w) {
+      const int dir = (w >= half) ? 1 : 0;
+      if (dir != loaded) {
+        const float* dd = drow + (size_t)dir * dB;
+#pragma unroll
+        for (int b = 0; b < BC; ++b)
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            const int col = c0 + 4 * (lane + 32 * k);
+            if (col < d && b0 + b < B) {
+              const float* p = dd + (size_t)col * B + (b0 + b);
+              da[b][k] = make_float4(__ldg(p), __ldg(p + B), __ldg(p + 2 * B), __ldg(p + 3 * B));
+            } else {
+              da[b][k] = zero4();
+            }
+          }
+        loaded = dir;
+      }
+#pragma unroll
+      for (int b = 0; b < BC; ++b) {
+        float p = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          p = fmaf(xs[k].x, da[b][k].x, p);
+          p = fmaf(xs[k].y, da[b][k].y, p);
+          p = fmaf(xs[k].z, da[b][k].z, p);
+          p = fmaf(xs[k].w, da[b][k].w, p);
+        }
+        p = warp_sum(p);
+        if (lane == 0 && b0 + b < B) atomicAdd(dC + (size_t)w * B + b0 + b, p);
+      }
+    };
+
+    for (int base = beg; base < end; base += 32) {
+      const int n = min(32, end - base);
+      int my_nbr = 0, my_rw = 0;
+      float my_nm = 0.f;
+      if (lane < n) {
+        my_nbr = __ldg(a.nbr + base + lane);
+        my_rw = __ldg(a.relw + base + lane);
+        my_nm = __ldg(a.norm + base + lane);
+      }
+      for (int t = 0; t < n; t += U_MSG) {
+        float4 x[U_MSG][NV];
+        int rw[U_MSG];
+        float nm[U_MSG];
+#pragma unroll
+        for (int u = 0; u < U_MSG; ++u) {
+          const int tt = min(t + u, n - 1);
+          const int src = __shfl_sync(FULL, my_nbr, tt);
+          rw[u] = __shfl_sync(FULL, my_rw, tt);
+          nm[u] = __shfl_sync(FULL, my_nm, tt);
+          const float* xr = a.X + (size_t)src * a.ldx + c0;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            const int lc = 4 * (lane + 32 * k);
+            x[u][k] = (c0 + lc < d) ? ldg4(xr + lc) : zero4();
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U_MSG; ++u) {
+          if (t + u < n) {
+            if (rw[u] != cur) {
+              if (cur >= 0) flush(cur);
+              cur = rw[u];
+#pragma unroll
+              for (int k = 0; k < NV; ++k) xs[k] = zero4();
+            }
+#pragma unroll
+            for (int k = 0; k < NV; ++k) fma4(xs[k], nm[u], x[u][k]);
+          }
+        }
+      }
+    }
+    if (cur >= 0) flush(cur);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Elementwise helpers.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_grad_prologue(const float* __restrict__ dOut, const float* __restrict__ out,
+                                const uint8_t* __restrict__ mask, float inv_keep, int relu,
+                                int64_t n4, float* __restrict__ G, float* __restrict__ dS) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 g = reinterpret_cast<const float4*>(dOut)[i];
+    if (relu) {
+      const float4 o = reinterpret_cast<const float4*>(out)[i];
+      g.x = o.x > 0.f ? g.x : 0.f;
+      g.y = o.y > 0.f ? g.y : 0.f;
+      g.z = o.z > 0.f ? g.z : 0.f;
+      g.w = o.w > 0.f ? g.w : 0.f;
+    }
+    reinterpret_cast<float4*>(G)[i] = g;
+    if (mask) {
+      const uchar4 mk = reinterpret_cast<const uchar4*>(mask)[i];
+      float4 s;
+      s.x = mk.x ? g.x * inv_keep : 0.f;
+      s.y = mk.y ? g.y * inv_keep : 0.f;
+      s.z = mk.z ? g.z * inv_keep : 0.f;
+      s.w = mk.w ? g.w * inv_keep : 0.f;
+      reinterpret_cast<float4*>(dS)[i] = s;
+    }
+  }
+}
+
+__global__ void k_mask_relu(float* __restrict__ x, const uint8_t* __restrict__ mask, float inv_keep,
+                            int relu, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(x)[i];
+    if (mask) {
+      const uchar4 mk = reinterpret_cast<const uchar4*>(mask)[i];
+      v.x = mk.x ? v.x * inv_keep : 0.f;
+      v.y = mk.y ? v.y * inv_keep : 0.f;
+      v.z = mk.z ? v.z * inv_keep : 0.f;
+      v.w = mk.w ? v.w * inv_keep : 0.f;
+    }
+    if (relu) {
+      v.x = fmaxf(v.x, 0.f);
+      v.y = fmaxf(v.y, 0.f);
+      v.z = fmaxf(v.z, 0.f);
+      v.w = fmaxf(v.w, 0.f);
+    }
+    reinterpret_cast<float4*>(x)[i] = v;
+  }
+}
+
+__global__ void k_zero_rows(float* __restrict__ A, int64_t width4, const int32_t* __restrict__ rows,
+                            int n_rows) {
+  const int r = blockIdx.x;
+  if (r >= n_rows) return;
+  float4* p = reinterpret_cast<float4*>(A + (size_t)__ldg(rows + r) * width4 * 4);
+  for (int64_t i = threadIdx.x; i < width4; i += blockDim.x) p[i] = zero4();
+}
+
+int grid_for(int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  const int64_t cap = 148 * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+int check_launch(const char* what) {
+  ++g_rgcn_launches;
+  return rgcn_check_cuda(cudaGetLastError(), what);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Launchers
+// ------------------------------------------------------------------------------------------------
+static int pick_nv(int d) {
+  int nv = (d + 127) / 128;
+  return nv > 4 ? 4 : nv;
+}
+
+template <int S>
+static int launch_block_agg_s(const AggLaunch& a, int s, const float* Wt, float* out,
+                              const uint8_t* mask, float inv_keep, int relu, cudaStream_t st) {
+  const int nv = pick_nv(a.d);
+  const int slabs = (a.d + nv * 128 - 1) / (nv * 128);
+  dim3 grid((a.n_items + RGCN_WARPS_PER_BLOCK - 1) / RGCN_WARPS_PER_BLOCK, slabs);
+  if (a.n_items == 0) return RGCN_OK;
+  switch (nv) {
+    case 1: k_block_agg<S, 1><<<grid, RGCN_THREADS, 0, st>>>(a, s, Wt, out, mask, inv_keep, relu); break;
+    case 2: k_block_agg<S, 2><<<grid, RGCN_THREADS, 0, st>>>(a, s, Wt, out, mask, inv_keep, relu); break;
+    case 3: k_block_agg<S, 3><<<grid, RGCN_THREADS, 0, st>>>(a, s, Wt, out, mask, inv_keep, relu); break;
+    default: k_block_agg<S, 4><<<grid, RGCN_THREADS, 0, st>>>(a, s, Wt, out, mask, inv_keep, relu); break;
+  }
+  return check_launch("k_block_agg");
+}
+
+int launch_block_agg(const AggLaunch& a, int s, const float* Wt, float* out, const uint8_t* mask,
+                     float inv_keep, int relu, cudaStream_t st) {
+  const int nv = pick_nv(a.d);
+  if (a.d > nv * 128 && (nv * 128) % s != 0) {
+    rgcn_set_error("block layer: d > 512 needs a block size s that divides 512");
+    return RGCN_ERR_INVALID;
+  }
+  switch (s) {
+    case 4: return launch_block_agg_s<4>(a, s, Wt, out, mask, inv_keep, relu, st);
+    case 5: return launch_block_agg_s<5>(a, s, Wt, out, mask, inv_keep, relu, st);
+    case 8: return launch_block_agg_s<8>(a, s, Wt, out, mask, inv_keep, relu, st);
+    case 16: return launch_block_agg_s<16>(a, s, Wt, out, mask, inv_keep, relu, st);
+    default: return launch_block_agg_s<0>(a, s, Wt, out, mask, inv_keep, relu, st);
+  }
+}
+
+template <int S, int JC, int NV>
+static int launch_block_dw_t(const WorkItem* items, int n_items, const int32_t* r_dst,
+                             const int32_t* r_src, const float* r_norm, const float* H, int ldh,
+                             const float* G, int ldg, int d, int s, float* dWt, cudaStream_t st) {
+  const int slabs = (d + NV * 128 - 1) / (NV * 128);
+  if (slabs > 1 && (NV * 128) % s != 0) {
+    rgcn_set_error("block layer backward: column slab not aligned to the block size");
+    return RGCN_ERR_INVALID;
+  }
+  dim3 grid((n_items + RGCN_WARPS_PER_BLOCK - 1) / RGCN_WARPS_PER_BLOCK, slabs);
+  k_block_dw<S, JC, NV><<<grid, RGCN_THREADS, 0, st>>>(items, n_items, r_dst, r_src, r_norm, H, ldh,
+                                                        G, ldg, d, s, dWt);
+  return check_launch("k_block_dw");
+}
+
+int launch_block_dw(const WorkItem* items, int n_items, const int32_t* r_dst, const int32_t* r_src,
+                    const float* r_norm, const float* H, int ldh, const float* G, int ldg, int d,
+                    int s, float* dWt, cudaStream_t st) {
+  if (n_items == 0) return RGCN_OK;
+#define DW(S_, JC_, NV_) \
+  return launch_block_dw_t<S_, JC_, NV_>(items, n_items, r_dst, r_src, r_norm, H, ldh, G, ldg, d, s, dWt, st)
+  const int nv = pick_nv(d);
+  if (s == 5) {
+    switch (nv) { case 1: DW(5, 5, 1); case 2: DW(5, 5, 2); case 3: DW(5, 5, 3); default: DW(5, 5, 4); }
+  } else if (s == 4) {
+    switch (nv) { case 1: DW(4, 4, 1); case 2: DW(4, 4, 2); case 3: DW(4, 4, 3); default: DW(4, 4, 4); }
+  } else if (s == 8) {
+    if (nv == 1) DW(8, 8, 1);
+    DW(8, 8, 2);
+  } else if (s == 16) {
+    DW(16, 16, 1);
+  } else {
+    switch (nv) { case 1: DW(0, 4, 1); case 2: DW(0, 4, 2); case 3: DW(0, 4, 3); default: DW(0, 4, 4); }
+  }
+#undef DW
+}
+
+int launch_block_relayout(const float* Wf, const float* Wb, int R, int B, int s, int transpose,
+                          float* Wt, cudaStream_t st) {
+  const int64_t total = 2 * (int64_t)R * B * s * s;
+  k_block_relayout<<<grid_for(total, 256), 256, 0, st>>>(Wf, Wb, R, B, s, transpose, Wt);
+  return check_launch("k_block_relayout");
+}
+
+int launch_block_unlayout(const float* dWt, int R, int B, int s, float* dWf, float* dWb,
+                          cudaStream_t st) {
+  const int64_t total = 2 * (int64_t)R * B * s * s;
+  k_block_unlayout<<<grid_for(total, 256), 256, 0, st>>>(dWt, R, B, s, dWf, dWb);
+  return check_launch("k_block_unlayout");
+}
+
+template <int BC, int LAYOUT>
+static int launch_basis_agg_t(const AggLaunch& a, const float* C, int B, int n_relw, float* Agg,
+                              cudaStream_t st) {
+  const int nv = pick_nv(a.d);
+  const int slabs = (a.d + nv * 128 - 1) / (nv * 128);
+  dim3 grid((a.n_items + RGCN_WARPS_PER_BLOCK - 1) / RGCN_WARPS_PER_BLOCK, slabs);
+  const int half = n_relw / 2;
+  switch (nv) {
+    case 1: k_basis_agg<BC, 1, LAYOUT><<<grid, RGCN_THREADS, 0, st>>>(a, C, B, half, Agg); break;
+    case 2: k_basis_agg<BC, 2, LAYOUT><<<grid, RGCN_THREADS, 0, st>>>(a, C, B, half, Agg); break;
+    case 3: k_basis_agg<BC, 3, LAYOUT><<<grid, RGCN_THREADS, 0, st>>>(a, C, B, half, Agg); break;
+    default: k_basis_agg<BC, 4, LAYOUT><<<grid, RGCN_THREADS, 0, st>>>(a, C, B, half, Agg); break;
+  }
+  return check_launch("k_basis_agg");
+}
+
+int launch_basis_agg(const AggLaunch& a, const float* C, int B, int n_relw, int layout, float* Agg,
+                     cudaStream_t st) {
+  if (a.n_items == 0) return RGCN_OK;
+  // bases per pass: all of them when they fit the register budget, else passes of 4
+  if (layout == 0) {
+    if (B == 1) return launch_basis_agg_t<1, 0>(a, C, B, n_relw, Agg, st);
+    if (B == 2) return launch_basis_agg_t<2, 0>(a, C, B, n_relw, Agg, st);
+    if (B <= 4) return launch_basis_agg_t<4, 0>(a, C, B, n_relw, Agg, st);
+    if (B == 5) return launch_basis_agg_t<5, 0>(a, C, B, n_relw, Agg, st);
+    return launch_basis_agg_t<4, 0>(a, C, B, n_relw, Agg, st);
+  } else {
+    if (B == 1) return launch_basis_agg_t<1, 1>(a, C, B, n_relw, Agg, st);
+    if (B == 2) return launch_basis_agg_t<2, 1>(a, C, B, n_relw, Agg, st);
+    if (B <= 4) return launch_basis_agg_t<4, 1>(a, C, B, n_relw, Agg, st);
+    if (B == 5) return launch_basis_agg_t<5, 1>(a, C, B, n_relw, Agg, st);
+    return launch_basis_agg_t<4, 1>(a, C, B, n_relw, Agg, st);
+  }
+}
+
+template <int BC>
+static int launch_basis_dc_t(const AggLaunch& a, const float* dAgg, int B, int n_relw, float* dC,
+                             cudaStream_t st) {
+  const int nv = pick_nv(a.d);
+  const int slabs = (a.d + nv * 128 - 1) / (nv * 128);
+  dim3 grid((a.n_items + RGCN_WARPS_PER_BLOCK - 1) / RGCN_WARPS_PER_BLOCK, slabs);
+  const int half = n_relw / 2;
+  switch (nv) {
+    case 1: k_basis_dc<BC, 1><<<grid, RGCN_THREADS, 0, st>>>(a, dAgg, B, half, dC); break;
+    case 2: k_basis_dc<BC, 2><<<grid, RGCN_THREADS, 0, st>>>(a, dAgg, B, half, dC); break;
+    case 3: k_basis_dc<BC, 3><<<grid, RGCN_THREADS, 0, st>>>(a, dAgg, B, half, dC); break;
+    default: k_basis_dc<BC, 4><<<grid, RGCN_THREADS, 0, st>>>(a, dAgg, B, half, dC); break;
+  }
+  return check_launch("k_basis_dc");
+}
+
+int launch_basis_dc(const AggLaunch& a, const float* dAgg, int B, int n_relw, float* dC,
+                    cudaStream_t st) {
+  if (a.n_items == 0) return RGCN_OK;
+  if (B == 1) return launch_basis_dc_t<1>(a, dAgg, B, n_relw, dC, st);
+  if (B == 2) return launch_basis_dc_t<2>(a, dAgg, B, n_relw, dC, st);
+  if (B == 5) return launch_basis_dc_t<5>(a, dAgg, B, n_relw, dC, st);
+  return launch_basis_dc_t<4>(a, dAgg, B, n_relw, dC, st);
+}
+
+int launch_grad_prologue(const float* dOut, const float* out, const uint8_t* mask, float inv_keep,
+                         int relu, int64_t n, float* G, float* dS, cudaStream_t st) {
+  if (n == 0) return RGCN_OK;
+  k_grad_prologue<<<grid_for(n / 4, 256), 256, 0, st>>>(dOut, out, mask, inv_keep, relu, n / 4, G, dS);
+  return check_launch("k_grad_prologue");
+}
+
+int launch_mask_relu(float* x, const uint8_t* mask, float inv_keep, int relu, int64_t n,
+                     cudaStream_t st) {
+  if (n == 0 || (!mask && !relu)) return RGCN_OK;
+  k_mask_relu<<<grid_for(n / 4, 256), 256, 0, st>>>(x, mask, inv_keep, relu, n / 4);
+  return check_launch("k_mask_relu");
+}
+
+int launch_zero_rows(float* A, int64_t width, const int32_t* rows, int n_rows, cudaStream_t st) {
+  if (n_rows == 0) return RGCN_OK;
+  k_zero_rows<<<n_rows, 256, 0, st>>>(A, width / 4, rows, n_rows);
+  return check_launch("k_zero_rows");
+}

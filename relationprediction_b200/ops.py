@@ -1,0 +1,293 @@
+"""Host-side operators over the C-ABI: graph handle + autograd Functions.
+
+PyTorch is used for storage (CUDA tensors), streams and autograd bookkeeping only: every
+forward/backward below is ONE call into librgcn_b200.so (include/rgcn_b200.h).  There is no CPU or
+eager-torch fallback: tensors that are not CUDA fp32 raise.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_NORM = {"canonical": _lib.RGCN_NORM_CANONICAL, "explicit": _lib.RGCN_NORM_EXPLICIT,
+         "none": _lib.RGCN_NORM_NONE}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _np_ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else ctypes.c_void_p(0)
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_cuda_f32(name, t, shape=None):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32):
+        raise _lib.RgcnError("%s must be a CUDA float32 tensor (no CPU fallback exists)" % name)
+    if not t.is_contiguous():
+        raise _lib.RgcnError("%s must be contiguous" % name)
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise _lib.RgcnError("%s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
+
+
+class Graph:
+    """Prepared message-passing graph (opaque C handle).
+
+    Replaces Representation/MessageGraph (extras/graph_representations.py): triples [E,3] (s,r,o)
+    -> 2E messages, per-direction 1/in-degree normalisation, three sorted views + warp work lists.
+    `device=None` builds the host structure only (used by the CPU tests of the index work).
+    """
+
+    def __init__(self, triples, n_entities, n_relations, norm_mode="canonical", norm_f=None,
+                 norm_b=None, device=None, _handle=None):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p(0)
+        self.device = device
+        if _handle is not None:
+            self._h = _handle
+        else:
+            tri = np.ascontiguousarray(np.asarray(triples, dtype=np.int32).reshape(-1, 3))
+            nf = None if norm_f is None else np.ascontiguousarray(norm_f, dtype=np.float32)
+            nb = None if norm_b is None else np.ascontiguousarray(norm_b, dtype=np.float32)
+            dev = -1 if device is None else int(device)
+            st = _stream(device) if device is not None else ctypes.c_void_p(0)
+            rc = self._lib.rgcn_graph_create(_np_ptr(tri), tri.shape[0], int(n_entities),
+                                             int(n_relations), _NORM[norm_mode], _np_ptr(nf),
+                                             _np_ptr(nb), dev, st, ctypes.byref(self._h))
+            _lib.check(rc, "rgcn_graph_create")
+        info = self.info()
+        self.M, self.V_dst, self.V_src, self.n_relw = info[0], info[1], info[2], info[3]
+
+    @classmethod
+    def from_messages(cls, dst, src, relw, norm, V_dst, V_src, n_relw, device=None):
+        lib = _lib.load()
+        dst = np.ascontiguousarray(dst, dtype=np.int32)
+        src = np.ascontiguousarray(src, dtype=np.int32)
+        relw = np.ascontiguousarray(relw, dtype=np.int32)
+        norm = np.ascontiguousarray(norm, dtype=np.float32)
+        h = ctypes.c_void_p(0)
+        dev = -1 if device is None else int(device)
+        st = _stream(device) if device is not None else ctypes.c_void_p(0)
+        rc = lib.rgcn_graph_create_messages(_np_ptr(dst), _np_ptr(src), _np_ptr(relw), _np_ptr(norm),
+                                            dst.shape[0], int(V_dst), int(V_src), int(n_relw), dev,
+                                            st, ctypes.byref(h))
+        _lib.check(rc, "rgcn_graph_create_messages")
+        return cls(None, 0, 0, device=device, _handle=h)
+
+    def info(self):
+        arr = (ctypes.c_int64 * 16)()
+        _lib.check(self._lib.rgcn_graph_info(self._h, arr), "rgcn_graph_info")
+        return [int(x) for x in arr]
+
+    def export(self, which):
+        n = self._lib.rgcn_graph_export_bytes(self._h, which)
+        if n < 0:
+            _lib.check(int(n), "rgcn_graph_export_bytes")
+        dtype = np.float32 if which in (_lib.X_DST_NORM, _lib.X_SRC_NORM, _lib.X_REL_NORM,
+                                        _lib.X_MSG_NORM) else np.int32
+        out = np.empty(n // 4, dtype=dtype)
+        _lib.check(self._lib.rgcn_graph_export(self._h, which, _np_ptr(out), n), "rgcn_graph_export")
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.rgcn_graph_destroy(self._h)
+            self._h = ctypes.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _mask_arg(mask, V, d):
+    if mask is None:
+        return None
+    if not (mask.is_cuda and mask.dtype == torch.uint8 and mask.is_contiguous()
+            and tuple(mask.shape) == (V, d)):
+        raise _lib.RgcnError("drop_mask must be a contiguous CUDA uint8 [V_dst, d] keep-mask")
+    return mask
+
+
+class _BlockLayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, H, Wf, Wb, Wself, graph, n_blocks, drop_mask, keep, relu):
+        lib = _lib.load()
+        d = H.shape[1]
+        R = graph.n_relw // 2
+        s = d // n_blocks
+        _check_cuda_f32("H", H, (graph.V_src, d))
+        _check_cuda_f32("W_forward", Wf, (R, n_blocks, s, s))
+        _check_cuda_f32("W_backward", Wb, (R, n_blocks, s, s))
+        _check_cuda_f32("W_self", Wself, (d, d))
+        mask = _mask_arg(drop_mask, graph.V_dst, d)
+        dev = H.device
+        out = torch.empty(graph.V_dst, d, dtype=torch.float32, device=dev)
+        nb = lib.rgcn_block_workspace_bytes(graph.handle, d, n_blocks, 0)
+        if nb < 0:
+            _lib.check(int(nb), "rgcn_block_workspace_bytes")
+        ws = _workspace(nb, dev)
+        rc = lib.rgcn_block_forward(graph.handle, d, n_blocks, _ptr(H), _ptr(Wf), _ptr(Wb),
+                                    _ptr(Wself), _ptr(mask), float(keep), int(bool(relu)), _ptr(out),
+                                    _ptr(ws), ws.numel(), _stream(dev))
+        _lib.check(rc, "rgcn_block_forward")
+        ctx.graph, ctx.n_blocks, ctx.keep, ctx.relu = graph, n_blocks, float(keep), bool(relu)
+        ctx.mask = mask
+        ctx.save_for_backward(H, Wf, Wb, Wself, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        lib = _lib.load()
+        H, Wf, Wb, Wself, out = ctx.saved_tensors
+        graph, B = ctx.graph, ctx.n_blocks
+        d = H.shape[1]
+        dOut = dOut.contiguous()
+        _check_cuda_f32("dOut", dOut, (graph.V_dst, d))
+        dev = H.device
+        dH = torch.empty_like(H)
+        dWf, dWb, dWself = torch.empty_like(Wf), torch.empty_like(Wb), torch.empty_like(Wself)
+        nb = lib.rgcn_block_workspace_bytes(graph.handle, d, B, 1)
+        ws = _workspace(nb, dev)
+        rc = lib.rgcn_block_backward(graph.handle, d, B, _ptr(H), _ptr(Wf), _ptr(Wb), _ptr(Wself),
+                                     _ptr(ctx.mask), ctx.keep, int(ctx.relu), _ptr(out), _ptr(dOut),
+                                     _ptr(dH), _ptr(dWf), _ptr(dWb), _ptr(dWself), _ptr(ws),
+                                     ws.numel(), _stream(dev))
+        _lib.check(rc, "rgcn_block_backward")
+        return dH, dWf, dWb, dWself, None, None, None, None, None
+
+
+def block_layer(H, W_forward, W_backward, W_self, graph, n_blocks, drop_mask=None, keep=1.0,
+                relu=True):
+    """Block-diagonal R-GCN layer (ConcatGcn, gcn_basis_concat.py:35-83), differentiable."""
+    return _BlockLayerFn.apply(H, W_forward, W_backward, W_self, graph, int(n_blocks), drop_mask,
+                               keep, relu)
+
+
+class _BasisLayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, H, Vf, Vb, Cf, Cb, Wself, graph, drop_mask, keep, relu):
+        lib = _lib.load()
+        d = H.shape[1]
+        R = graph.n_relw // 2
+        B = Cf.shape[1]
+        _check_cuda_f32("H", H, (graph.V_src, d))
+        _check_cuda_f32("W_forward", Vf, (d, B, d))
+        _check_cuda_f32("W_backward", Vb, (d, B, d))
+        _check_cuda_f32("C_forward", Cf, (R, B))
+        _check_cuda_f32("C_backward", Cb, (R, B))
+        _check_cuda_f32("W_self", Wself, (d, d))
+        mask = _mask_arg(drop_mask, graph.V_dst, d)
+        dev = H.device
+        out = torch.empty(graph.V_dst, d, dtype=torch.float32, device=dev)
+        saved = torch.empty(graph.V_dst, 2 * d * B, dtype=torch.float32, device=dev)
+        nb = lib.rgcn_basis_workspace_bytes(graph.handle, d, B, 0)
+        if nb < 0:
+            _lib.check(int(nb), "rgcn_basis_workspace_bytes")
+        ws = _workspace(nb, dev)
+        rc = lib.rgcn_basis_forward(graph.handle, d, B, _ptr(H), _ptr(Vf), _ptr(Vb), _ptr(Cf),
+                                    _ptr(Cb), _ptr(Wself), _ptr(mask), float(keep), int(bool(relu)),
+                                    _ptr(out), _ptr(saved), _ptr(ws), ws.numel(), _stream(dev))
+        _lib.check(rc, "rgcn_basis_forward")
+        ctx.graph, ctx.keep, ctx.relu, ctx.mask = graph, float(keep), bool(relu), mask
+        ctx.save_for_backward(H, Vf, Vb, Cf, Cb, Wself, out, saved)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        lib = _lib.load()
+        H, Vf, Vb, Cf, Cb, Wself, out, saved = ctx.saved_tensors
+        graph = ctx.graph
+        d, B = H.shape[1], Cf.shape[1]
+        dOut = dOut.contiguous()
+        dev = H.device
+        dH = torch.empty_like(H)
+        dVf, dVb = torch.empty_like(Vf), torch.empty_like(Vb)
+        dCf, dCb, dWself = torch.empty_like(Cf), torch.empty_like(Cb), torch.empty_like(Wself)
+        nb = lib.rgcn_basis_workspace_bytes(graph.handle, d, B, 1)
+        ws = _workspace(nb, dev)
+        rc = lib.rgcn_basis_backward(graph.handle, d, B, _ptr(H), _ptr(Vf), _ptr(Vb), _ptr(Cf),
+                                     _ptr(Cb), _ptr(Wself), _ptr(ctx.mask), ctx.keep, int(ctx.relu),
+                                     _ptr(out), _ptr(saved), _ptr(dOut), _ptr(dH), _ptr(dVf),
+                                     _ptr(dVb), _ptr(dCf), _ptr(dCb), _ptr(dWself), _ptr(ws),
+                                     ws.numel(), _stream(dev))
+        _lib.check(rc, "rgcn_basis_backward")
+        return dH, dVf, dVb, dCf, dCb, dWself, None, None, None, None
+
+
+def basis_layer(H, W_forward, W_backward, C_forward, C_backward, W_self, graph, drop_mask=None,
+                keep=1.0, relu=True):
+    """Basis-decomposition R-GCN layer (BasisGcn, gcn_basis.py:39-88), differentiable."""
+    return _BasisLayerFn.apply(H, W_forward, W_backward, C_forward, C_backward, W_self, graph,
+                               drop_mask, keep, relu)
+
+
+class _DistMultFn(torch.autograd.Function):
+    """Returns (energies[N], loss, reg): loss = mean sigmoid-CE (0 if Y is None), reg = un-scaled L2."""
+
+    @staticmethod
+    def forward(ctx, codes, rel, X, Y):
+        lib = _lib.load()
+        _check_cuda_f32("codes", codes)
+        _check_cuda_f32("relation table", rel)
+        if not (X.is_cuda and X.dtype == torch.int32 and X.is_contiguous() and X.dim() == 2
+                and X.shape[1] == 3):
+            raise _lib.RgcnError("X must be a contiguous CUDA int32 [N,3] tensor")
+        if Y is not None:
+            _check_cuda_f32("Y", Y, (X.shape[0],))
+        V, d = codes.shape
+        dev = codes.device
+        N = X.shape[0]
+        energies = torch.empty(N, dtype=torch.float32, device=dev)
+        loss2 = torch.empty(2, dtype=torch.float32, device=dev)
+        rc = lib.distmult_forward(_ptr(codes), _ptr(rel), V, rel.shape[0], d, _ptr(X), N, _ptr(Y),
+                                  _ptr(energies), _ptr(loss2), _stream(dev))
+        _lib.check(rc, "distmult_forward")
+        ctx.has_y = Y is not None
+        ctx.save_for_backward(codes, rel, X, Y if Y is not None else torch.empty(0, device=dev),
+                              energies)
+        return energies, loss2[0], loss2[1]
+
+    @staticmethod
+    def backward(ctx, g_energy, g_loss, g_reg):
+        lib = _lib.load()
+        codes, rel, X, Y, energies = ctx.saved_tensors
+        Y = Y if ctx.has_y else None
+        V, d = codes.shape
+        dev = codes.device
+        dcodes = torch.zeros_like(codes)
+        drel = torch.zeros_like(rel)
+        ge = None
+        if g_energy is not None:
+            ge = g_energy.contiguous()
+        # upstream scalar gradients stay on the device (no host sync): passed as g_scale_dev[2]
+        gs = torch.zeros(2, dtype=torch.float32, device=dev)
+        if g_loss is not None:
+            gs[0] = g_loss
+        if g_reg is not None:
+            gs[1] = g_reg
+        rc = lib.distmult_backward(_ptr(codes), _ptr(rel), V, rel.shape[0], d, _ptr(X), X.shape[0],
+                                   _ptr(Y), _ptr(energies), 1.0, 1.0, _ptr(gs), _ptr(ge),
+                                   _ptr(dcodes), _ptr(drel), _stream(dev))
+        _lib.check(rc, "distmult_backward")
+        return dcodes, drel, None, None
+
+
+def distmult(codes, rel, X, Y=None):
+    """DistMult energies + sigmoid cross-entropy + L2 term (bilinear_diag.py:14-34,63-69)."""
+    return _DistMultFn.apply(codes, rel, X, Y)

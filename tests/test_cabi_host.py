@@ -1,0 +1,112 @@
+"""CPU: the C-ABI library builds, loads, exports every symbol include/rgcn_b200.h declares, and its
+host-side graph preparation is bit-exact against an independent numpy restatement (oracle)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import rgcn_oracle as oracle
+from relationprediction_b200 import _lib
+from relationprediction_b200.ops import Graph
+from conftest import synthetic_kg, ROOT
+
+
+def test_library_loads_and_exports_header_symbols():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "rgcn_b200.h")).read()
+    declared = set(re.findall(r"\b((?:rgcn|distmult)_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.rgcn_version() >= 100
+
+
+def _check_views(g, dst, src, relw, norm, V_dst, V_src, n_relw):
+    ref = oracle.sorted_views(dst, src, relw, norm, V_dst, V_src, n_relw)
+    pairs = [(_lib.X_DST_ROWPTR, "dst_rowptr"), (_lib.X_DST_SRC, "dst_src"), (_lib.X_DST_RELW, "dst_relw"),
+             (_lib.X_DST_NORM, "dst_norm"), (_lib.X_DST_MID, "dst_mid"), (_lib.X_SRC_ROWPTR, "src_rowptr"),
+             (_lib.X_SRC_DST, "src_dst"), (_lib.X_SRC_RELW, "src_relw"), (_lib.X_SRC_NORM, "src_norm"),
+             (_lib.X_SRC_MID, "src_mid"), (_lib.X_REL_PTR, "rel_ptr"), (_lib.X_REL_DST, "rel_dst"),
+             (_lib.X_REL_SRC, "rel_src"), (_lib.X_REL_NORM, "rel_norm"), (_lib.X_REL_MID, "rel_mid")]
+    for which, key in pairs:
+        got = g.export(which)
+        np.testing.assert_array_equal(got, ref[key], err_msg=key)  # bit-exact, floats included
+    np.testing.assert_array_equal(g.export(_lib.X_MSG_NORM), norm)
+
+
+def test_toy_graph_prep_bit_exact(toy):
+    tr = np.array(toy["train"], dtype=np.int32)
+    V, R = toy["V"], toy["R"]
+    g = Graph(tr, V, R)  # host only
+    dst, src, relw, norm = oracle.messages_from_triples(tr, R, V)
+    assert g.M == 86 and g.V_dst == g.V_src == 16 and g.n_relw == 18
+    _check_views(g, dst, src, relw, norm, V, V, 2 * R)
+    np.testing.assert_array_equal(g.export(_lib.X_MSG_NORM)[:43], np.float32(toy["norm_f_canonical"]))
+    np.testing.assert_array_equal(g.export(_lib.X_MSG_NORM)[43:], np.float32(toy["norm_b_canonical"]))
+
+
+def test_explicit_norm_mode_carries_tf_compat_values(toy):
+    tr = np.array(toy["train"], dtype=np.int32)
+    nf, nb = oracle.graph_norms(tr, 16, "tf_unsorted_compat")
+    g = Graph(tr, 16, 9, norm_mode="explicit", norm_f=nf, norm_b=nb)
+    np.testing.assert_array_equal(g.export(_lib.X_MSG_NORM), np.concatenate([nf, nb]))
+    g2 = Graph(tr, 16, 9, norm_mode="none")
+    assert (g2.export(_lib.X_MSG_NORM) == 1).all()
+
+
+@pytest.mark.parametrize("skewed", [False, True])
+def test_synthetic_graph_prep_bit_exact_and_work_items(skewed):
+    V, R, E = 3000, 37, 40000
+    tr = synthetic_kg(V, R, E, seed=7, skewed=skewed)
+    g = Graph(tr, V, R)
+    dst, src, relw, norm = oracle.messages_from_triples(tr, R, V)
+    _check_views(g, dst, src, relw, norm, V, V, 2 * R)
+    info = g.info()
+    # (dst, relw) run count
+    p = np.lexsort((relw, dst))
+    runs = 1 + int(((dst[p][1:] != dst[p][:-1]) | (relw[p][1:] != relw[p][:-1])).sum())
+    assert info[9] == runs
+    item_max = info[12]
+    deg = np.bincount(dst, minlength=V)
+    n_items = int(sum(1 if x <= item_max else -(-x // (-(-x // -(-x // item_max)))) for x in deg))
+    assert info[7] == int((deg > item_max).sum())
+    assert info[4] >= V and abs(info[4] - n_items) <= info[7]
+
+
+def test_empty_and_ragged_graphs():
+    g = Graph(np.zeros((0, 3), np.int32), 5, 2)
+    assert g.M == 0 and g.info()[4] == 5  # one (empty) work item per destination row
+    assert g.export(_lib.X_DST_ROWPTR).tolist() == [0] * 6
+    # a node that only sends, a self loop, duplicate triples
+    tr = np.array([[0, 1, 0], [0, 1, 0], [3, 0, 0], [4, 1, 2]], np.int32)
+    g = Graph(tr, 5, 2)
+    dst, src, relw, norm = oracle.messages_from_triples(tr, 2, 5)
+    _check_views(g, dst, src, relw, norm, 5, 5, 4)
+
+
+def test_message_constructor_with_halo_rows():
+    rng = np.random.RandomState(0)
+    V_dst, V_src, n_relw, M = 50, 80, 6, 700
+    dst = rng.randint(0, V_dst, M).astype(np.int32)
+    src = rng.randint(0, V_src, M).astype(np.int32)
+    relw = rng.randint(0, n_relw, M).astype(np.int32)
+    norm = rng.rand(M).astype(np.float32)
+    g = Graph.from_messages(dst, src, relw, norm, V_dst, V_src, n_relw)
+    assert (g.V_dst, g.V_src, g.n_relw, g.M) == (V_dst, V_src, n_relw, M)
+    _check_views(g, dst, src, relw, norm, V_dst, V_src, n_relw)
+
+
+def test_error_codes_instead_of_exceptions():
+    lib = _lib.load()
+    with pytest.raises(_lib.RgcnError, match="out of range"):
+        Graph(np.array([[0, 0, 9]], np.int32), 5, 2)
+    with pytest.raises(_lib.RgcnError, match="out of range"):
+        Graph(np.array([[0, 7, 1]], np.int32), 5, 2)
+    g = Graph(np.array([[0, 0, 1]], np.int32), 5, 2)  # host-only graph
+    buf = ctypes.create_string_buffer(1024)
+    rc = lib.rgcn_block_forward(g.handle, 8, 2, buf, buf, buf, buf, None, 1.0, 1, buf, buf, 1024, None)
+    assert rc == -5  # RGCN_ERR_NODEVICE: no silent CPU path
+    assert b"host-only" in lib.rgcn_last_error()
+    assert lib.rgcn_graph_export(g.handle, 99, buf, 1024) == -1
