@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py -- R-GCN layer fwd+bwd throughput (M-edges/s) on B200, one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+A "step" is ONE pass of the hot path over one graph: one block-diagonal R-GCN layer forward +
+backward (dH, dW_forward, dW_backward, dW_self) on synthetic data of the named shape.
+Metric (BASELINE.json): M-edges/s = triples E / (t_fwd + t_bwd) / 1e6, graph prep excluded from
+`value` (device-resident inputs) and INCLUDED in `e2e` (host buffers in, host buffers out).
+
+Workloads
+  fb15k237   (default, BASELINE configs[1]) V=14541 R=237 E=272115, d=500, B=100 (s=5): the
+             FB15k-237 evaluation graph shape of settings/gcn_block.exp; synthetic skewed KG.
+  synthetic  (BASELINE configs[4] scaled to one GPU by --scale) V=10M*scale, R=1000, E=100M*scale,
+             d=512, B=64 (s=8), uniform endpoints: the HBM-bound regime.
+With --gpus N > 1 the node set is sharded 1-D (relationprediction_b200/parallel.py), weak scaling:
+the graph grows with N (V*N nodes, E*N triples), one halo all-to-all per layer direction.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def synthetic_kg(V, R, E, seed=1234, skewed=False):
+    """SURVEY.md 8(d) generator (PCG64(seed)): uniform, or skewed s,o = floor(V*u^3) under a fixed
+    random relabelling and r = floor(R*u^2)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    if not skewed:
+        s = rng.integers(0, V, E)
+        o = rng.integers(0, V, E)
+        r = rng.integers(0, R, E)
+    else:
+        perm = rng.permutation(V)
+        s = perm[np.minimum((V * rng.random(E) ** 3).astype(np.int64), V - 1)]
+        o = perm[np.minimum((V * rng.random(E) ** 3).astype(np.int64), V - 1)]
+        r = np.minimum((R * rng.random(E) ** 2).astype(np.int64), R - 1)
+    return np.stack([s, r, o], 1).astype(np.int32)
+
+
+def workload_spec(args, world):
+    if args.workload == "fb15k237":
+        return dict(name="fb15k237-evalgraph gcn_block d=500 B=100 (BASELINE configs[1])",
+                    V=14541 * world, R=237, E=272115 * world, d=500, B=100, skewed=True)
+    if args.workload == "fb15k237-train":
+        return dict(name="fb15k237 train-step graph E=15000 gcn_block d=500 B=100",
+                    V=14541 * world, R=237, E=15000 * world, d=500, B=100, skewed=True)
+    if args.workload == "synthetic":
+        V = int(10_000_000 * args.scale) * world
+        E = int(100_000_000 * args.scale) * world
+        return dict(name="synthetic KG x%.3g of 10M nodes/1k rel/100M edges d=512 B=64 (BASELINE configs[4])"
+                    % args.scale, V=V, R=1000, E=E, d=512, B=64, skewed=args.skewed)
+    raise SystemExit("unknown workload " + args.workload)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            j = json.load(fh)
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                               f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:  # region shorter than one sample: take whatever was seen
+            for ts, line in self.rows[-3:]:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[0]))
+                    mx.append(float(f[1]))
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def oracle_step_factory(spec, sample_E, seed=0):
+    """The reference's CPU path restated (oracle/rgcn_oracle.py), on a bounded sample of the workload:
+    same V, d, B, R; `sample_E` triples drawn from the same generator."""
+    import torch
+
+    from oracle import rgcn_oracle as oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    V, R, d, B = spec["V"], spec["R"], spec["d"], spec["B"]
+    tr = synthetic_kg(V, R, sample_E, seed=1234, skewed=spec["skewed"])
+    rng = np.random.RandomState(seed)
+    H = rng.normal(0, 1, (V, d)).astype(np.float32)
+    dOut = rng.normal(0, 1, (V, d)).astype(np.float32)
+    w = oracle.init_block_layer(rng, R, d, B)
+    nf, nb = oracle.graph_norms(tr, V)
+
+    def step():
+        oracle.layer_fwd_bwd("block", H, tr, w, nf, nb, dOut, None, 1.0, True, torch.float32)
+    return step
+
+
+def time_cpu(step, steps, warmup):
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / steps
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  TensorFlow 1.4 cannot be
+    installed here (no wheel for py3.12, no network), so this times the oracle port (the one other
+    place bench.py may execute oracle/), all host threads, on a bounded sample of our arm's config."""
+    if rank != 0:
+        return
+    spec = workload_spec(args, 1)
+    sample_E = min(spec["E"], args.cpu_sample_edges)
+    step = oracle_step_factory(spec, sample_E)
+    sec = time_cpu(step, args.steps, max(1, min(args.warmup, 1)))
+    val = sample_E / sec / 1e6
+    cores = os.cpu_count() or 1
+    sample = "%d of %d triples of the same synthetic KG (same V, R, d, B), fp32, %d torch threads" % (
+        sample_E, spec["E"], cores)
+    line = {"impl": "reference", "metric": "R-GCN layer fwd+bwd M-edges/sec", "value": val,
+            "unit": "M-edges/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": spec["name"], "V": spec["V"], "R": spec["R"], "E": sample_E,
+                       "d": spec["d"], "B": spec["B"],
+                       "note": "reference TF1 CPU path restated op-for-op in torch-CPU (TensorFlow 1.4 not installable)"},
+            "cpu_baseline": {"value": val, "unit": "M-edges/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "M-edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="fb15k237", choices=["fb15k237", "fb15k237-train", "synthetic"])
+    ap.add_argument("--scale", type=float, default=0.05, help="synthetic workload: fraction of 10M/100M")
+    ap.add_argument("--skewed", action="store_true", help="synthetic workload: skewed endpoints")
+    ap.add_argument("--cpu-sample-edges", type=int, default=20000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+
+    import torch
+    import torch.distributed as dist
+
+    from relationprediction_b200 import _lib, ops
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    spec = workload_spec(args, world)
+    V, R, E, d, B = spec["V"], spec["R"], spec["E"], spec["d"], spec["B"]
+    s = d // B
+    t_gen = time.perf_counter()
+    triples = synthetic_kg(V, R, E, seed=1234, skewed=spec["skewed"])
+    t_gen = time.perf_counter() - t_gen
+
+    gen = torch.Generator(device=dev).manual_seed(1 + rank)
+    if world == 1:
+        t0 = time.perf_counter()
+        graph = ops.Graph(triples, V, R, device=local_rank)
+        prep_ms = (time.perf_counter() - t0) * 1e3
+        layer = None
+        V_loc, V_src = V, V
+    else:
+        from relationprediction_b200 import parallel
+        t0 = time.perf_counter()
+        layer = parallel.ShardedGraph(triples, V, R, rank, world, dev)
+        prep_ms = (time.perf_counter() - t0) * 1e3
+        graph = layer.graph
+        V_loc, V_src = layer.n_local, layer.n_local + layer.n_halo
+    info = graph.info()
+
+    H = torch.randn(V_loc, d, device=dev, generator=gen)
+    dOut = torch.randn(V_loc, d, device=dev, generator=gen)
+    std = 3.0 / np.sqrt(R + s)  # glorot_variance([R, s]) used as std (gcn_basis_concat.py:22)
+    wgen = torch.Generator(device=dev).manual_seed(2)  # replicated weights: same seed on every rank
+    Wf = (torch.randn(R, B, s, s, device=dev, generator=wgen) * std).requires_grad_(True)
+    Wb = (torch.randn(R, B, s, s, device=dev, generator=wgen) * std).requires_grad_(True)
+    Ws = (torch.randn(d, d, device=dev, generator=wgen) * std).requires_grad_(True)
+    Hreq = H.clone().requires_grad_(True)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        for t in (Hreq, Wf, Wb, Ws):
+            t.grad = None
+        if world == 1:
+            out = ops.block_layer(Hreq, Wf, Wb, Ws, graph, B, None, 1.0, True)
+            out.backward(dOut)
+        else:
+            out = layer.block_layer(Hreq, Wf, Wb, Ws, B, None, 1.0, True)
+            out.backward(dOut)
+            layer.allreduce_weight_grads([Wf, Wb, Ws])
+        return out
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = _lib.launch_count()
+    sync_all()
+    wall0 = time.time()
+    for i in range(args.steps):
+        flush_buf.zero_()  # L2 flush between timed iterations (outside the event pair)
+        ev0[i].record()
+        step()
+        ev1[i].record()
+    sync_all()
+    wall1 = time.time()
+    launches = _lib.launch_count() - launches0
+    total_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = E / (ms_per_step * 1e-3) / 1e6
+    clocks = sampler.stop(wall0, wall1) if sampler else None
+
+    # ---- e2e: same layer fwd+bwd through the public API with HOST buffers (single GPU path) ----
+    e2e = None
+    if world == 1:
+        tri_pin = torch.from_numpy(triples).pin_memory()
+        H_pin = H.cpu().pin_memory()
+        dOut_pin = dOut.cpu().pin_memory()
+        out_host = torch.empty(V, d).pin_memory()
+        dH_host = torch.empty(V, d).pin_memory()
+        dW_host = [torch.empty_like(t, device="cpu").pin_memory() for t in (Wf, Wb, Ws)]
+        h2d = tri_pin.numel() * 4 + H_pin.numel() * 4 + dOut_pin.numel() * 4
+        d2h = (out_host.numel() + dH_host.numel() + sum(t.numel() for t in dW_host)) * 4
+        prep_times = []
+
+        def e2e_step():
+            tp = time.perf_counter()
+            g2 = ops.Graph(tri_pin.numpy(), V, R, device=local_rank)  # host sort + H2D of the structure
+            prep_times.append(time.perf_counter() - tp)
+            h = H_pin.to(dev, non_blocking=True).requires_grad_(True)
+            do = dOut_pin.to(dev, non_blocking=True)
+            for t in (Wf, Wb, Ws):
+                t.grad = None
+            o = ops.block_layer(h, Wf, Wb, Ws, g2, B, None, 1.0, True)
+            o.backward(do)
+            out_host.copy_(o.detach(), non_blocking=True)
+            dH_host.copy_(h.grad, non_blocking=True)
+            for hh, t in zip(dW_host, (Wf, Wb, Ws)):
+                hh.copy_(t.grad, non_blocking=True)
+            torch.cuda.synchronize()
+
+        n_e2e = max(3, min(args.steps, 10))
+        e2e_step()
+        prep_times.clear()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        e2e_ms = (time.perf_counter() - t0) / n_e2e * 1e3
+        e2e = {"value": E / (e2e_ms * 1e-3) / 1e6, "unit": "M-edges/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
+               "host_graph_prep_ms": float(np.mean(prep_times) * 1e3), "steps": n_e2e,
+               "what": "host triples -> graph prep -> H2D(H, dOut) -> fwd+bwd -> D2H(out, dH, dW*)"}
+
+    # ---- per-stage timing + roofline of the dominant kernel (separate pass, events inside the lib) ----
+    roofline, stages = None, None
+    if world == 1:
+        _lib.profile_enable(True)
+        acc = {}
+        n_prof = 5
+        for _ in range(n_prof):
+            flush_buf.zero_()
+            step()
+            torch.cuda.synchronize()
+            for name, ms in _lib.profile_read():
+                acc[name] = acc.get(name, 0.0) + ms / n_prof
+        _lib.profile_enable(False)
+        stages = {k: round(v, 5) for k, v in acc.items()}
+        M = 2 * E
+        wt_bytes = 2 * R * s * d * 4
+        alg = {
+            "block_agg_fwd": M * (4 * d + 12) + 8 * V * d + wt_bytes + 16 * info[4],
+            "block_agg_dH": M * (4 * d + 12) + 8 * V * d + wt_bytes + 16 * info[5],
+            "block_dW": M * (4 * d + 12) + info[9] * 4 * d + 2 * wt_bytes + 16 * info[6],
+        }
+        mine = {k: v for k, v in acc.items() if k in alg}
+        if mine:
+            top = max(mine, key=mine.get)
+            peak, peak_src = peaks()
+            achieved = alg[top] / (mine[top] * 1e-3) / 1e9
+            roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": None, "algorithmic_bytes": int(alg[top]),
+                        "kernel_ms": mine[top], "peak_source": peak_src,
+                        "note": "algorithmic bytes count every row gather as HBM bytes; with H resident in "
+                                "the 126 MB L2 (H = %.0f MB here) frac can exceed 1" % (V * d * 4 / 1e6),
+                        "all": {k: {"ms": mine[k], "GB/s": alg[k] / (mine[k] * 1e-3) / 1e9} for k in mine}}
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        spec1 = workload_spec(args, 1)
+        sample_E = min(spec1["E"], args.cpu_sample_edges)
+        cstep = oracle_step_factory(spec1, sample_E)
+        sec = time_cpu(cstep, 3, 1)
+        cpu_baseline = {"value": sample_E / sec / 1e6, "unit": "M-edges/s", "cores": os.cpu_count() or 1,
+                        "kind": "port",
+                        "sample": "%d of %d triples of the same synthetic KG, 3 timed fwd+bwd passes of the "
+                                  "torch-CPU restatement (TensorFlow 1.4 not installable)" % (sample_E, spec1["E"])}
+
+    if rank == 0:
+        line = {"metric": "R-GCN layer fwd+bwd M-edges/sec", "value": value, "unit": "M-edges/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": spec["name"], "V": V, "R": R, "E": E, "d": d, "B": B, "s": s,
+                           "skewed": spec["skewed"], "dropout": "off (keep=1)", "relu": True,
+                           "l2": "flushed between timed iterations (256 MB memset outside the event pair)",
+                           "parallelism": "1d-node-shard x%d" % world if world > 1 else "single",
+                           "messages": info[0], "dst_runs": info[9], "split_rows": info[7]},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu_baseline, "stages_ms": stages, "graph_prep_ms": prep_ms,
+                "wall_s_timed_region": wall1 - wall0}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

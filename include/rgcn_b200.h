@@ -48,6 +48,12 @@ const char* rgcn_last_error(void);
 /* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
 int64_t rgcn_launch_count(void);
 
+/* Optional per-kernel timing (bench.py roofline): when enabled, every layer entry point records a
+ * CUDA event on its stream after each internal stage.  rgcn_profile_read() synchronises, writes
+ * the stage durations (ms) and their '\n'-separated names, clears the log and returns the count. */
+int rgcn_profile_enable(int enable);
+int rgcn_profile_read(float* ms_out, int max_entries, char* names_out, int names_cap);
+
 /* ------------------------------------------------------------------------------------------------
  * Graph preparation.  Replaces Representation/MessageGraph
  * (extras/graph_representations.py:21-27 index vectors, :84-93 / :124-133 normalised incidence).

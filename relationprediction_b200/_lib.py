@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "librgcn_b200.so")
 
 # every symbol include/rgcn_b200.h declares (tests check the .so exports all of them)
 EXPORTED_SYMBOLS = [
-    "rgcn_version", "rgcn_last_error", "rgcn_launch_count",
+    "rgcn_version", "rgcn_last_error", "rgcn_launch_count", "rgcn_profile_enable", "rgcn_profile_read",
     "rgcn_graph_create", "rgcn_graph_create_messages", "rgcn_graph_destroy", "rgcn_graph_info",
     "rgcn_graph_export_bytes", "rgcn_graph_export",
     "rgcn_block_workspace_bytes", "rgcn_block_forward", "rgcn_block_backward",
@@ -37,6 +37,10 @@ def _declare(lib):
     lib.rgcn_version.restype = c_int
     lib.rgcn_last_error.restype = c_char_p
     lib.rgcn_launch_count.restype = c_int64
+    lib.rgcn_profile_enable.restype = c_int
+    lib.rgcn_profile_enable.argtypes = [c_int]
+    lib.rgcn_profile_read.restype = c_int
+    lib.rgcn_profile_read.argtypes = [vp, c_int, vp, c_int]
     lib.rgcn_graph_create.restype = c_int
     lib.rgcn_graph_create.argtypes = [vp, c_int64, c_int32, c_int32, c_int, vp, vp, c_int, vp,
                                       POINTER(vp)]
@@ -96,6 +100,19 @@ def check(rc, what=""):
     if rc != 0:
         msg = load().rgcn_last_error()
         raise RgcnError("%s failed (rc=%d): %s" % (what, rc, (msg or b"").decode("utf-8", "replace")))
+
+
+def profile_enable(on=True):
+    load().rgcn_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """[(stage name, ms)] recorded since the last read (see rgcn_profile_enable)."""
+    ms = (c_float * 96)()
+    names = ctypes.create_string_buffer(4096)
+    n = load().rgcn_profile_read(ms, 96, names, 4096)
+    nm = names.value.decode().split("\n")
+    return [(nm[i], float(ms[i])) for i in range(n)]
 
 
 def launch_count():

@@ -4,6 +4,7 @@
 #include <cublas_v2.h>
 #include <cuda_runtime.h>
 
+#include <cstring>
 #include <mutex>
 #include <string>
 
@@ -63,6 +64,29 @@ int gemm_rm(cublasHandle_t h, bool ta, bool tb, int64_t m, int64_t n, int64_t k,
   }
   return RGCN_OK;
 }
+
+// ---- optional stage timing -------------------------------------------------------------------
+struct Profile {
+  bool enabled = false;
+  static const int kMax = 96;
+  cudaEvent_t ev[kMax];
+  const char* name[kMax];
+  bool created = false;
+  int n = 0;
+} g_prof;
+
+void prof_mark(const char* name, cudaStream_t st) {
+  if (!g_prof.enabled) return;
+  if (!g_prof.created) {
+    for (int i = 0; i < Profile::kMax; ++i) cudaEventCreate(&g_prof.ev[i]);
+    g_prof.created = true;
+  }
+  if (g_prof.n >= Profile::kMax) return;
+  g_prof.name[g_prof.n] = name;
+  cudaEventRecord(g_prof.ev[g_prof.n], st);
+  ++g_prof.n;
+}
+#define MARK(name_) prof_mark(name_, st)
 
 inline int64_t align_up(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
@@ -126,6 +150,36 @@ AggLaunch make_agg(const CsrSide& side, const float* X, int ldx, int d, float* s
 
 extern "C" int64_t rgcn_launch_count(void) { return g_rgcn_launches; }
 
+extern "C" int rgcn_profile_enable(int enable) {
+  g_prof.enabled = enable != 0;
+  g_prof.n = 0;
+  return RGCN_OK;
+}
+
+extern "C" int rgcn_profile_read(float* ms_out, int max_entries, char* names_out, int names_cap) {
+  int count = 0;
+  std::string names;
+  for (int i = 1; i < g_prof.n; ++i) {
+    // a mark named "start" opens a new call: no duration is attributed to it
+    if (std::string(g_prof.name[i]) == "start") continue;
+    if (count >= max_entries) break;
+    if (cudaEventSynchronize(g_prof.ev[i]) != cudaSuccess) break;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof.ev[i - 1], g_prof.ev[i]) != cudaSuccess) break;
+    if (ms_out) ms_out[count] = ms;
+    names += g_prof.name[i];
+    names += "\n";
+    ++count;
+  }
+  if (names_out && names_cap > 0) {
+    size_t n = names.size() < (size_t)names_cap - 1 ? names.size() : (size_t)names_cap - 1;
+    memcpy(names_out, names.data(), n);
+    names_out[n] = 0;
+  }
+  g_prof.n = 0;
+  return count;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Block-diagonal layer
 // ------------------------------------------------------------------------------------------------
@@ -181,8 +235,10 @@ extern "C" int rgcn_block_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
   float* scratch = ws.take<float>(n_split * d);
   int* counters = ws.take<int>(n_split * slabs);
 
+  MARK("start");
   rc = launch_block_relayout(Wf, Wb, R, B, s, /*transpose=*/0, Wt, st);
   if (rc) return rc;
+  MARK("block_relayout");
   if (n_split > 0) {
     rc = rgcn_check_cuda(
         cudaMemsetAsync(scratch, 0, (char*)(counters + n_split * slabs) - (char*)scratch, st),
@@ -195,8 +251,11 @@ extern "C" int rgcn_block_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
   // self-loop term S = H[0:V_dst] @ W_self written straight into `out` (gcn_basis_concat.py:65-66)
   rc = gemm_rm(h, false, false, g->V_dst, d, d, 1.f, H, d, Wself, d, 0.f, out, d);
   if (rc) return rc;
+  MARK("gemm_self_loop");
   AggLaunch a = make_agg(g->by_dst, H, d, d, scratch, counters);
-  return launch_block_agg(a, s, Wt, out, drop_mask, 1.0f / keep, relu, st);
+  rc = launch_block_agg(a, s, Wt, out, drop_mask, 1.0f / keep, relu, st);
+  MARK("block_agg_fwd");
+  return rc;
 }
 
 extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, const float* H,
@@ -237,14 +296,17 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   if (!drop_mask) dS = G;
 
   // G = dOut * relu'(out);  dS = G * mask / keep   (message_gcn.py:64 dropout is on the self loop only)
+  MARK("start");
   rc = launch_grad_prologue(dOut, out, drop_mask, 1.0f / keep, relu, (int64_t)g->V_dst * d, G, dS, st);
   if (rc) return rc;
+  MARK("grad_prologue");
   cublasHandle_t h;
   rc = get_cublas(g->device, st, &h);
   if (rc) return rc;
   // dW_self = H[0:V_dst]^T dS
   rc = gemm_rm(h, true, false, d, d, g->V_dst, 1.f, H, d, dS, d, 0.f, dWself, d);
   if (rc) return rc;
+  MARK("gemm_dWself");
   // dH[0:V_dst] = dS W_self^T ; halo rows start at zero
   rc = gemm_rm(h, false, true, g->V_dst, d, d, 1.f, dS, d, Wself, d, 0.f, dH, d);
   if (rc) return rc;
@@ -254,9 +316,11 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
                          "memset(dH halo)");
     if (rc) return rc;
   }
+  MARK("gemm_dH_self");
   // dH[u] += sum_{m: src_m = u} norm_m W[relw_m]^T G[dst_m]   (same kernel, transposed table)
   rc = launch_block_relayout(Wf, Wb, R, B, s, /*transpose=*/1, Wtt, st);
   if (rc) return rc;
+  MARK("block_relayout_T");
   if (n_split > 0) {
     rc = rgcn_check_cuda(
         cudaMemsetAsync(scratch, 0, (char*)(counters + n_split * slabs) - (char*)scratch, st),
@@ -266,13 +330,17 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   AggLaunch a = make_agg(g->by_src, G, d, d, scratch, counters);
   rc = launch_block_agg(a, s, Wtt, dH, nullptr, 1.f, 0, st);
   if (rc) return rc;
+  MARK("block_agg_dH");
   // dW[w] = sum_{m: relw_m = w} norm_m G[dst_m] (x)_block H[src_m]
   rc = rgcn_check_cuda(cudaMemsetAsync(dWt, 0, wt * sizeof(float), st), "memset(dWt)");
   if (rc) return rc;
   rc = launch_block_dw(g->by_rel.d_items, (int)g->by_rel.items.size(), g->by_rel.d_dst,
                        g->by_rel.d_src, g->by_rel.d_norm, H, d, G, d, d, s, dWt, st);
   if (rc) return rc;
-  return launch_block_unlayout(dWt, R, B, s, dWf, dWb, st);
+  MARK("block_dW");
+  rc = launch_block_unlayout(dWt, R, B, s, dWf, dWb, st);
+  MARK("block_unlayout");
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
