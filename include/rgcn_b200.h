@@ -48,6 +48,12 @@ const char* rgcn_last_error(void);
 /* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
 int64_t rgcn_launch_count(void);
 
+/* Library options.  "block_algo": 0 = destination-major aggregation (deterministic summation order,
+ * epilogue fused), 1 = weight-id-major aggregation (block weights in registers, vector reductions
+ * in L2; fastest, fp32 summation order not reproducible run to run), -1 = auto (default).
+ * The environment variable RGCN_BLOCK_ALGO overrides the option. */
+int rgcn_set_option(const char* name, int64_t value);
+
 /* Optional per-kernel timing (bench.py roofline): when enabled, every layer entry point records a
  * CUDA event on its stream after each internal stage.  rgcn_profile_read() synchronises, writes
  * the stage durations (ms) and their '\n'-separated names, clears the log and returns the count. */
@@ -63,7 +69,8 @@ int rgcn_profile_read(float* ms_out, int max_entries, char* names_out, int names
  * device       : CUDA device ordinal, or -1 to build the host-side structure only (CPU tests).
  * Builds, deterministically (stable counting sorts; message id of triple k is k forward, E+k
  * backward): destination-CSR sorted by (dst, weight-id), source-CSR sorted by (src, weight-id),
- * weight-id-major list sorted by (weight-id, dst), per-message norm, and warp work lists.
+ * two weight-id-major lists sorted by (supertile(dst), weight-id, dst) and (supertile(src),
+ * weight-id, src), per-message norm, and warp work lists.
  * ---------------------------------------------------------------------------------------------- */
 int rgcn_graph_create(const int32_t* triples_host, int64_t E, int32_t V, int32_t R, int norm_mode,
                       const float* norm_f_host, const float* norm_b_host, int device, void* stream,
@@ -81,7 +88,8 @@ int rgcn_graph_destroy(rgcn_graph_t* g);
 
 /* info[0]=M messages, [1]=V_dst, [2]=V_src, [3]=n_relw, [4]=#dst work items, [5]=#src work items,
  * [6]=#relw work items, [7]=#split dst rows, [8]=#split src rows, [9]=#(dst,relw) groups,
- * [10]=device, [11]=bytes resident on device, [12..15] reserved. */
+ * [10]=device, [11]=bytes resident on device, [12]=item_max, [13]=supertile rows, [14]=#supertiles,
+ * [15]=#relw work items of the source-keyed view. */
 int rgcn_graph_info(const rgcn_graph_t* g, int64_t info[16]);
 
 /* Export of the prepared structure to host memory, for bit-exact index tests. */
@@ -96,12 +104,17 @@ enum {
   RGCN_X_SRC_RELW = 7,
   RGCN_X_SRC_NORM = 8,
   RGCN_X_SRC_MID = 9,
-  RGCN_X_REL_PTR = 10, /* int32 [n_relw+1] */
+  RGCN_X_REL_PTR = 10, /* int32 [n_super*n_relw+1]: weight-id major view keyed (supertile(dst), relw, dst) */
   RGCN_X_REL_DST = 11,
   RGCN_X_REL_SRC = 12,
   RGCN_X_REL_NORM = 13,
   RGCN_X_REL_MID = 14,
-  RGCN_X_MSG_NORM = 15 /* float [M] norm in original message order */
+  RGCN_X_MSG_NORM = 15, /* float [M] norm in original message order */
+  RGCN_X_REL2_PTR = 16, /* second weight-id major view keyed (supertile(src), relw, src) */
+  RGCN_X_REL2_SRC = 17,
+  RGCN_X_REL2_DST = 18,
+  RGCN_X_REL2_NORM = 19,
+  RGCN_X_REL2_MID = 20
 };
 int64_t rgcn_graph_export_bytes(const rgcn_graph_t* g, int which);
 int rgcn_graph_export(const rgcn_graph_t* g, int which, void* dst_host, int64_t nbytes);

@@ -78,7 +78,7 @@ def messages_from_triples(triples, n_relations, n_vertices, mode="canonical"):
     return dst, src, relw, norm
 
 
-def sorted_views(dst, src, relw, norm, V_dst, V_src, n_relw):
+def sorted_views(dst, src, relw, norm, V_dst, V_src, n_relw, supertile_rows=32768):
     """Reference (numpy lexsort, stable) for the three sorted message views the library builds.
     Not in the TF reference (it uses COO matrices); this pins the bit-exact index work of the
     graph-prep step against an independent implementation."""
@@ -91,9 +91,13 @@ def sorted_views(dst, src, relw, norm, V_dst, V_src, n_relw):
     p = np.lexsort((mid, relw, src))
     out["src_rowptr"] = np.concatenate([[0], np.cumsum(np.bincount(src, minlength=V_src))]).astype(np.int32)
     out["src_dst"], out["src_relw"], out["src_norm"], out["src_mid"] = dst[p], relw[p], norm[p], mid[p]
-    p = np.lexsort((mid, dst, relw))
-    out["rel_ptr"] = np.concatenate([[0], np.cumsum(np.bincount(relw, minlength=n_relw))]).astype(np.int32)
-    out["rel_dst"], out["rel_src"], out["rel_norm"], out["rel_mid"] = dst[p], src[p], norm[p], mid[p]
+    # weight-id major views keyed (supertile(row), relw, row)
+    for name, row, nbr, n_rows in (("rel", dst, src, V_dst), ("rel2", src, dst, V_src)):
+        n_super = max(1, -(-n_rows // supertile_rows))
+        key = (row // supertile_rows).astype(np.int64) * n_relw + relw
+        p = np.lexsort((mid, row, key))
+        out[name + "_ptr"] = np.concatenate([[0], np.cumsum(np.bincount(key, minlength=n_super * n_relw))]).astype(np.int32)
+        out[name + "_row"], out[name + "_nbr"], out[name + "_norm"], out[name + "_mid"] = row[p], nbr[p], norm[p], mid[p]
     return out
 
 

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "librgcn_b200.so")
 # every symbol include/rgcn_b200.h declares (tests check the .so exports all of them)
 EXPORTED_SYMBOLS = [
     "rgcn_version", "rgcn_last_error", "rgcn_launch_count", "rgcn_profile_enable", "rgcn_profile_read",
+    "rgcn_set_option",
     "rgcn_graph_create", "rgcn_graph_create_messages", "rgcn_graph_destroy", "rgcn_graph_info",
     "rgcn_graph_export_bytes", "rgcn_graph_export",
     "rgcn_block_workspace_bytes", "rgcn_block_forward", "rgcn_block_backward",
@@ -23,7 +24,8 @@ EXPORTED_SYMBOLS = [
 RGCN_NORM_CANONICAL, RGCN_NORM_EXPLICIT, RGCN_NORM_NONE = 0, 1, 2
 
 (X_DST_ROWPTR, X_DST_SRC, X_DST_RELW, X_DST_NORM, X_DST_MID, X_SRC_ROWPTR, X_SRC_DST, X_SRC_RELW,
- X_SRC_NORM, X_SRC_MID, X_REL_PTR, X_REL_DST, X_REL_SRC, X_REL_NORM, X_REL_MID, X_MSG_NORM) = range(16)
+ X_SRC_NORM, X_SRC_MID, X_REL_PTR, X_REL_DST, X_REL_SRC, X_REL_NORM, X_REL_MID, X_MSG_NORM,
+ X_REL2_PTR, X_REL2_SRC, X_REL2_DST, X_REL2_NORM, X_REL2_MID) = range(21)
 
 _lib = None
 
@@ -37,6 +39,8 @@ def _declare(lib):
     lib.rgcn_version.restype = c_int
     lib.rgcn_last_error.restype = c_char_p
     lib.rgcn_launch_count.restype = c_int64
+    lib.rgcn_set_option.restype = c_int
+    lib.rgcn_set_option.argtypes = [c_char_p, c_int64]
     lib.rgcn_profile_enable.restype = c_int
     lib.rgcn_profile_enable.argtypes = [c_int]
     lib.rgcn_profile_read.restype = c_int
@@ -100,6 +104,10 @@ def check(rc, what=""):
     if rc != 0:
         msg = load().rgcn_last_error()
         raise RgcnError("%s failed (rc=%d): %s" % (what, rc, (msg or b"").decode("utf-8", "replace")))
+
+
+def set_option(name, value):
+    check(load().rgcn_set_option(name.encode(), int(value)), "rgcn_set_option")
 
 
 def profile_enable(on=True):

@@ -4,6 +4,7 @@
 #include <cublas_v2.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -148,6 +149,26 @@ AggLaunch make_agg(const CsrSide& side, const float* X, int ldx, int d, float* s
 
 }  // namespace
 
+// block_algo: 0 = destination-major (deterministic, fused epilogue), 1 = weight-id major (weights in
+// registers + L2 vector reductions), -1 = auto (weight-id major whenever the block size supports it)
+static int g_block_algo = -1;
+
+static bool use_rel_major(int d, int s) {
+  int algo = g_block_algo;
+  if (const char* e = std::getenv("RGCN_BLOCK_ALGO")) algo = std::atoi(e);
+  if (algo == 0) return false;
+  return block_rel_supported(d, s);
+}
+
+extern "C" int rgcn_set_option(const char* name, int64_t value) {
+  if (name && std::string(name) == "block_algo") {
+    g_block_algo = (int)value;
+    return RGCN_OK;
+  }
+  rgcn_set_error("rgcn_set_option: unknown option");
+  return RGCN_ERR_INVALID;
+}
+
 extern "C" int64_t rgcn_launch_count(void) { return g_rgcn_launches; }
 
 extern "C" int rgcn_profile_enable(int enable) {
@@ -252,6 +273,18 @@ extern "C" int rgcn_block_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
   rc = gemm_rm(h, false, false, g->V_dst, d, d, 1.f, H, d, Wself, d, 0.f, out, d);
   if (rc) return rc;
   MARK("gemm_self_loop");
+  if (use_rel_major(d, s)) {
+    // out = dropout(S);  out[dst] += W_r . sum(norm x)  (L2 vector reductions);  out = relu(out)
+    rc = launch_mask_relu(out, drop_mask, 1.0f / keep, 0, (int64_t)g->V_dst * d, st);
+    if (rc) return rc;
+    rc = launch_block_rel(g->by_rel.d_items, (int)g->by_rel.items.size(), g->by_rel.d_row,
+                          g->by_rel.d_nbr, g->by_rel.d_norm, H, d, d, s, Wt, out, st);
+    if (rc) return rc;
+    MARK("block_agg_fwd");
+    rc = launch_mask_relu(out, nullptr, 1.f, relu, (int64_t)g->V_dst * d, st);
+    MARK("relu_epilogue");
+    return rc;
+  }
   AggLaunch a = make_agg(g->by_dst, H, d, d, scratch, counters);
   rc = launch_block_agg(a, s, Wt, out, drop_mask, 1.0f / keep, relu, st);
   MARK("block_agg_fwd");
@@ -327,15 +360,21 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
         "memset(scratch)");
     if (rc) return rc;
   }
-  AggLaunch a = make_agg(g->by_src, G, d, d, scratch, counters);
-  rc = launch_block_agg(a, s, Wtt, dH, nullptr, 1.f, 0, st);
+  if (use_rel_major(d, s)) {
+    rc = launch_block_rel(g->by_rel_src.d_items, (int)g->by_rel_src.items.size(),
+                          g->by_rel_src.d_row, g->by_rel_src.d_nbr, g->by_rel_src.d_norm, G, d, d, s,
+                          Wtt, dH, st);
+  } else {
+    AggLaunch a = make_agg(g->by_src, G, d, d, scratch, counters);
+    rc = launch_block_agg(a, s, Wtt, dH, nullptr, 1.f, 0, st);
+  }
   if (rc) return rc;
   MARK("block_agg_dH");
   // dW[w] = sum_{m: relw_m = w} norm_m G[dst_m] (x)_block H[src_m]
   rc = rgcn_check_cuda(cudaMemsetAsync(dWt, 0, wt * sizeof(float), st), "memset(dWt)");
   if (rc) return rc;
-  rc = launch_block_dw(g->by_rel.d_items, (int)g->by_rel.items.size(), g->by_rel.d_dst,
-                       g->by_rel.d_src, g->by_rel.d_norm, H, d, G, d, d, s, dWt, st);
+  rc = launch_block_dw(g->by_rel.d_items, (int)g->by_rel.items.size(), g->by_rel.d_row,
+                       g->by_rel.d_nbr, g->by_rel.d_norm, H, d, G, d, d, s, dWt, st);
   if (rc) return rc;
   MARK("block_dW");
   rc = launch_block_unlayout(dWt, R, B, s, dWf, dWb, st);

@@ -110,6 +110,33 @@ void fill_side(CsrSide& side, const std::vector<int32_t>& perm, const int32_t* o
   }
 }
 
+void build_rel_side(RelSide& side, const int32_t* row, int32_t n_rows, const int32_t* nbr,
+                    const int32_t* relw, const float* norm, int64_t M, int32_t n_relw,
+                    int supertile_rows, int item_max) {
+  const int32_t n_super = std::max(1, (n_rows + supertile_rows - 1) / supertile_rows);
+  side.n_super = n_super;
+  std::vector<int32_t> key(M);
+  for (int64_t m = 0; m < M; ++m) key[m] = (row[m] / supertile_rows) * n_relw + relw[m];
+  std::vector<int32_t> perm;
+  sort_two_keys(key.data(), n_super * n_relw, row, std::max(n_rows, 1), M, perm, side.ptr);
+  side.mid = perm;
+  side.row.resize(M);
+  side.nbr.resize(M);
+  side.norm.resize(M);
+  for (int64_t i = 0; i < M; ++i) {
+    const int32_t m = perm[i];
+    side.row[i] = row[m];
+    side.nbr[i] = nbr[m];
+    side.norm[i] = norm[m];
+  }
+  side.items.clear();
+  for (int32_t k = 0; k < n_super * n_relw; ++k) {
+    const int32_t beg = side.ptr[k], end = side.ptr[k + 1];
+    for (int32_t b = beg; b < end; b += item_max)
+      side.items.push_back({b, std::min(end, b + item_max), k % n_relw, k / n_relw});
+  }
+}
+
 template <typename T>
 int upload(T** dptr, const std::vector<T>& h, cudaStream_t st, int64_t& bytes) {
   size_t n = h.size() * sizeof(T);
@@ -156,6 +183,10 @@ int build(const int32_t* dst, const int32_t* src, const int32_t* relw, const flo
       int v = std::atoi(e);
       if (v >= 8) g->item_max = v;
     }
+    if (const char* e = std::getenv("RGCN_SUPERTILE_ROWS")) {
+      int v = std::atoi(e);
+      if (v >= 1) g->supertile_rows = v;
+    }
     g->msg_norm.assign(norm, norm + M);
 
     std::vector<int32_t> perm;
@@ -182,20 +213,10 @@ int build(const int32_t* dst, const int32_t* src, const int32_t* relw, const flo
     fill_side(g->by_src, perm, dst, relw, norm);
     build_items(g->by_src.rowptr, V_src, g->item_max, g->by_src.items, &g->by_src.split_nitems,
                 &g->by_src.split_rows, /*emit_empty=*/true);
-    // weight-id major, secondary key destination
-    sort_two_keys(relw, n_relw, dst, std::max(V_dst, 1), M, perm, g->by_rel.ptr);
-    g->by_rel.mid = perm;
-    g->by_rel.dst.resize(M);
-    g->by_rel.src.resize(M);
-    g->by_rel.norm.resize(M);
-    for (int64_t i = 0; i < M; ++i) {
-      int32_t m = perm[i];
-      g->by_rel.dst[i] = dst[m];
-      g->by_rel.src[i] = src[m];
-      g->by_rel.norm[i] = norm[m];
-    }
-    build_items(g->by_rel.ptr, n_relw, g->item_max, g->by_rel.items, nullptr, nullptr,
-                /*emit_empty=*/false);
+    // weight-id major views (see RelSide)
+    build_rel_side(g->by_rel, dst, V_dst, src, relw, norm, M, n_relw, g->supertile_rows, g->item_max);
+    build_rel_side(g->by_rel_src, src, V_src, dst, relw, norm, M, n_relw, g->supertile_rows,
+                   g->item_max);
   } catch (const std::bad_alloc&) {
     delete g;
     rgcn_set_error("host allocation failed in graph build");
@@ -218,10 +239,12 @@ int build(const int32_t* dst, const int32_t* src, const int32_t* relw, const flo
     if (!rc) rc = upload(&g->by_src.d_items, g->by_src.items, st, bytes);
     if (!rc) rc = upload(&g->by_src.d_split_nitems, g->by_src.split_nitems, st, bytes);
     if (!rc) rc = upload(&g->by_src.d_split_rows, g->by_src.split_rows, st, bytes);
-    if (!rc) rc = upload(&g->by_rel.d_dst, g->by_rel.dst, st, bytes);
-    if (!rc) rc = upload(&g->by_rel.d_src, g->by_rel.src, st, bytes);
-    if (!rc) rc = upload(&g->by_rel.d_norm, g->by_rel.norm, st, bytes);
-    if (!rc) rc = upload(&g->by_rel.d_items, g->by_rel.items, st, bytes);
+    for (RelSide* rs : {&g->by_rel, &g->by_rel_src}) {
+      if (!rc) rc = upload(&rs->d_row, rs->row, st, bytes);
+      if (!rc) rc = upload(&rs->d_nbr, rs->nbr, st, bytes);
+      if (!rc) rc = upload(&rs->d_norm, rs->norm, st, bytes);
+      if (!rc) rc = upload(&rs->d_items, rs->items, st, bytes);
+    }
     // the host vectors are pageable: make sure the copies are done before anyone frees/modifies them
     if (!rc) rc = rgcn_check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize(graph upload)");
     g->device_bytes = bytes;
@@ -328,10 +351,12 @@ extern "C" int rgcn_graph_destroy(rgcn_graph_t* g) {
     cudaFree(g->by_src.d_items);
     cudaFree(g->by_src.d_split_nitems);
     cudaFree(g->by_src.d_split_rows);
-    cudaFree(g->by_rel.d_dst);
-    cudaFree(g->by_rel.d_src);
-    cudaFree(g->by_rel.d_norm);
-    cudaFree(g->by_rel.d_items);
+    for (RelSide* rs : {&g->by_rel, &g->by_rel_src}) {
+      cudaFree(rs->d_row);
+      cudaFree(rs->d_nbr);
+      cudaFree(rs->d_norm);
+      cudaFree(rs->d_items);
+    }
   }
   delete g;
   return RGCN_OK;
@@ -356,6 +381,9 @@ extern "C" int rgcn_graph_info(const rgcn_graph_t* g, int64_t info[16]) {
   info[10] = g->device;
   info[11] = g->device_bytes;
   info[12] = g->item_max;
+  info[13] = g->supertile_rows;
+  info[14] = g->by_rel.n_super;
+  info[15] = (int64_t)g->by_rel_src.items.size();
   return RGCN_OK;
 }
 
@@ -381,10 +409,15 @@ bool pick(const rgcn_graph_t* g, int which, View& v) {
     case RGCN_X_SRC_NORM: v = view(g->by_src.norm); return true;
     case RGCN_X_SRC_MID: v = view(g->by_src.mid); return true;
     case RGCN_X_REL_PTR: v = view(g->by_rel.ptr); return true;
-    case RGCN_X_REL_DST: v = view(g->by_rel.dst); return true;
-    case RGCN_X_REL_SRC: v = view(g->by_rel.src); return true;
+    case RGCN_X_REL_DST: v = view(g->by_rel.row); return true;
+    case RGCN_X_REL_SRC: v = view(g->by_rel.nbr); return true;
     case RGCN_X_REL_NORM: v = view(g->by_rel.norm); return true;
     case RGCN_X_REL_MID: v = view(g->by_rel.mid); return true;
+    case RGCN_X_REL2_PTR: v = view(g->by_rel_src.ptr); return true;
+    case RGCN_X_REL2_SRC: v = view(g->by_rel_src.row); return true;
+    case RGCN_X_REL2_DST: v = view(g->by_rel_src.nbr); return true;
+    case RGCN_X_REL2_NORM: v = view(g->by_rel_src.norm); return true;
+    case RGCN_X_REL2_MID: v = view(g->by_rel_src.mid); return true;
     case RGCN_X_MSG_NORM: v = view(g->msg_norm); return true;
     default: return false;
   }

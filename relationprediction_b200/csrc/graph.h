@@ -35,13 +35,19 @@ struct CsrSide {
   int32_t* d_split_rows = nullptr;
 };
 
+// Weight-id major view: messages sorted by (supertile(row), weight id, row) where `row` is the row
+// the message ACCUMULATES into (destination for the forward / dW pass, source for the dH pass) and
+// `nbr` the row it gathers.  A supertile is a contiguous range of `supertile_rows` rows: keeping the
+// accumulation target of consecutive work items inside one L2-sized window lets the vector
+// reductions (red.global.add.v4.f32) resolve in L2 instead of HBM read-modify-write.
 struct RelSide {
-  std::vector<int32_t> ptr;  // [n_relw+1]
-  std::vector<int32_t> dst, src, mid;
+  std::vector<int32_t> ptr;  // [n_super * n_relw + 1]
+  std::vector<int32_t> row, nbr, mid;
   std::vector<float> norm;
-  std::vector<WorkItem> items;  // row = weight id, split unused
-  int32_t* d_dst = nullptr;
-  int32_t* d_src = nullptr;
+  std::vector<WorkItem> items;  // row = weight id, split = supertile index
+  int32_t n_super = 1;
+  int32_t* d_row = nullptr;
+  int32_t* d_nbr = nullptr;
   float* d_norm = nullptr;
   WorkItem* d_items = nullptr;
 };
@@ -56,7 +62,9 @@ struct rgcn_graph {
   std::vector<float> msg_norm;  // [M] original order
   CsrSide by_dst;               // rows = destinations, nbr = source
   CsrSide by_src;               // rows = sources,      nbr = destination
-  RelSide by_rel;               // weight-id major, sorted by (relw, dst)
+  RelSide by_rel;               // weight-id major, row = dst, nbr = src  (forward, dW)
+  RelSide by_rel_src;           // weight-id major, row = src, nbr = dst  (backward w.r.t. H)
+  int supertile_rows = 32768;
 };
 
 void rgcn_set_error(const std::string& s);

@@ -30,6 +30,13 @@ struct AggLaunch {
 int launch_block_agg(const AggLaunch& a, int s, const float* Wt, float* out, const uint8_t* mask,
                      float inv_keep, int relu, cudaStream_t st);
 
+// Weight-id major variant of the above (weights in registers, vector reductions into `out`, which
+// must already hold the self-loop term).  Supported block sizes: block_rel_supported().
+bool block_rel_supported(int d, int s);
+int launch_block_rel(const WorkItem* items, int n_items, const int32_t* r_row, const int32_t* r_nbr,
+                     const float* r_norm, const float* X, int ldx, int d, int s, const float* Wt,
+                     float* out, cudaStream_t st);
+
 // Block-diagonal weight gradient, weight-id major:
 //   dWt[w][j][b*s+i] += sum_{m: relw_m = w} norm_m * G[dst_m, b*s+i] * H[src_m, b*s+j]
 int launch_block_dw(const WorkItem* items, int n_items, const int32_t* r_dst, const int32_t* r_src,

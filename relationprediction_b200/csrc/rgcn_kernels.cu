@@ -65,7 +65,7 @@ __device__ __forceinline__ int blk_base(int col, int s_rt) {
 template <int S, int NV>
 __device__ __forceinline__ void block_apply(float4 (&acc)[NV], const float4 (&xs)[NV], float* xbuf,
                                             const float* __restrict__ wr, int d, int s, int c0,
-                                            int lane) {
+                                            int lane, const int (&xo)[NV][4]) {
   __syncwarp();
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -73,49 +73,33 @@ __device__ __forceinline__ void block_apply(float4 (&acc)[NV], const float4 (&xs
     if (c0 + lc < d) *reinterpret_cast<float4*>(xbuf + lc) = xs[k];
   }
   __syncwarp();
+  auto body = [&](int j) {
+    const float* wj = wr + (size_t)j * d;
 #pragma unroll
-  for (int j = 0; j < (S > 0 ? S : 1); ++j) {
-    // runtime-s variant loops below
-    if (S > 0) {
-      const float* wj = wr + (size_t)j * d;
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        const int lc = 4 * (lane + 32 * k);
-        const int col = c0 + lc;
-        if (col < d) {
-          const float4 w = ldg4(wj + col);
-          if (S % 4 == 0) {
-            const float x = xbuf[blk_base<S>(col, s) - c0 + j];
-            acc[k].x = fmaf(w.x, x, acc[k].x);
-            acc[k].y = fmaf(w.y, x, acc[k].y);
-            acc[k].z = fmaf(w.z, x, acc[k].z);
-            acc[k].w = fmaf(w.w, x, acc[k].w);
-          } else {
-            acc[k].x = fmaf(w.x, xbuf[blk_base<S>(col + 0, s) - c0 + j], acc[k].x);
-            acc[k].y = fmaf(w.y, xbuf[blk_base<S>(col + 1, s) - c0 + j], acc[k].y);
-            acc[k].z = fmaf(w.z, xbuf[blk_base<S>(col + 2, s) - c0 + j], acc[k].z);
-            acc[k].w = fmaf(w.w, xbuf[blk_base<S>(col + 3, s) - c0 + j], acc[k].w);
-          }
+    for (int k = 0; k < NV; ++k) {
+      const int col = c0 + 4 * (lane + 32 * k);
+      if (col < d) {
+        const float4 w = ldg4(wj + col);
+        if (S > 0 && S % 4 == 0) {
+          const float x = xbuf[xo[k][0] + j];
+          acc[k].x = fmaf(w.x, x, acc[k].x);
+          acc[k].y = fmaf(w.y, x, acc[k].y);
+          acc[k].z = fmaf(w.z, x, acc[k].z);
+          acc[k].w = fmaf(w.w, x, acc[k].w);
+        } else {
+          acc[k].x = fmaf(w.x, xbuf[xo[k][0] + j], acc[k].x);
+          acc[k].y = fmaf(w.y, xbuf[xo[k][1] + j], acc[k].y);
+          acc[k].z = fmaf(w.z, xbuf[xo[k][2] + j], acc[k].z);
+          acc[k].w = fmaf(w.w, xbuf[xo[k][3] + j], acc[k].w);
         }
       }
     }
-  }
-  if (S == 0) {
-    for (int j = 0; j < s; ++j) {
-      const float* wj = wr + (size_t)j * d;
+  };
+  if (S > 0) {
 #pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        const int lc = 4 * (lane + 32 * k);
-        const int col = c0 + lc;
-        if (col < d) {
-          const float4 w = ldg4(wj + col);
-          acc[k].x = fmaf(w.x, xbuf[blk_base<0>(col + 0, s) - c0 + j], acc[k].x);
-          acc[k].y = fmaf(w.y, xbuf[blk_base<0>(col + 1, s) - c0 + j], acc[k].y);
-          acc[k].z = fmaf(w.z, xbuf[blk_base<0>(col + 2, s) - c0 + j], acc[k].z);
-          acc[k].w = fmaf(w.w, xbuf[blk_base<0>(col + 3, s) - c0 + j], acc[k].w);
-        }
-      }
-    }
+    for (int j = 0; j < (S > 0 ? S : 1); ++j) body(j);
+  } else {
+    for (int j = 0; j < s; ++j) body(j);
   }
 }
 
@@ -135,8 +119,13 @@ __global__ void __launch_bounds__(RGCN_THREADS, 2)
   const int beg = itv.x, end = itv.y, row = itv.z, split = itv.w;
 
   float4 acc[NV], xs[NV];
+  int xo[NV][4];  // xbuf offset of the block each owned output column belongs to
 #pragma unroll
-  for (int k = 0; k < NV; ++k) acc[k] = xs[k] = zero4();
+  for (int k = 0; k < NV; ++k) {
+    acc[k] = xs[k] = zero4();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) xo[k][c] = blk_base<S>(c0 + 4 * (lane + 32 * k) + c, s) - c0;
+  }
   int cur = -1;
 
   for (int base = beg; base < end; base += 32) {
@@ -170,7 +159,7 @@ __global__ void __launch_bounds__(RGCN_THREADS, 2)
         if (t + u < n) {
           if (rw[u] != cur) {
             if (cur >= 0)
-              block_apply<S, NV>(acc, xs, xbuf, Wt + (size_t)cur * s * d, d, s, c0, lane);
+              block_apply<S, NV>(acc, xs, xbuf, Wt + (size_t)cur * s * d, d, s, c0, lane, xo);
             cur = rw[u];
 #pragma unroll
             for (int k = 0; k < NV; ++k) xs[k] = zero4();
@@ -181,7 +170,7 @@ __global__ void __launch_bounds__(RGCN_THREADS, 2)
       }
     }
   }
-  if (cur >= 0) block_apply<S, NV>(acc, xs, xbuf, Wt + (size_t)cur * s * d, d, s, c0, lane);
+  if (cur >= 0) block_apply<S, NV>(acc, xs, xbuf, Wt + (size_t)cur * s * d, d, s, c0, lane, xo);
 
   // ---- epilogue ----
   bool do_epilogue = true;
@@ -365,6 +354,126 @@ __global__ void __launch_bounds__(RGCN_THREADS, 1)
       }
     }
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Block-diagonal aggregation, WEIGHT-ID MAJOR ("rel-major").  A warp owns <= item_max messages of
+// ONE weight id (and one column slab): the block weights W_r live in REGISTERS for the whole item
+// (loaded once, coalesced, from the j-major table), messages are walked in row order so runs with
+// the same accumulation row are summed first (one transform per run), and each run's result is
+// added to out[row] with a 128-bit vector reduction that resolves in L2 (the message list is sorted
+// by L2-sized supertiles of rows, graph.cu).  Weight traffic drops from d*s*4 bytes per run to
+// d*s*4 bytes per item; the price is a non-deterministic fp32 summation order across items.
+// ------------------------------------------------------------------------------------------------
+template <int S, int NV>
+__global__ void __launch_bounds__(RGCN_THREADS, 1)
+    k_block_rel(const WorkItem* __restrict__ items, int n_items, const int32_t* __restrict__ r_row,
+                const int32_t* __restrict__ r_nbr, const float* __restrict__ r_norm,
+                const float* __restrict__ X, int ldx, int d, const float* __restrict__ Wt,
+                float* __restrict__ out) {
+  static_assert(S > 0, "rel-major kernel needs a compile-time block size");
+  __shared__ __align__(16) float xbuf_all[RGCN_WARPS_PER_BLOCK][NV * 128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * RGCN_WARPS_PER_BLOCK + warp;
+  if (item >= n_items) return;
+  const int c0 = blockIdx.y * (NV * 128);
+  float* xbuf = xbuf_all[warp];
+  const int4 itv = __ldg(reinterpret_cast<const int4*>(items) + item);
+  const int beg = itv.x, end = itv.y, w = itv.z;
+
+  // weights of this (weight id, slab) -> registers; x offsets of the lane's outputs -> registers
+  float4 wreg[S][NV];
+  int xo[NV][4];
+  const float* wr = Wt + (size_t)w * S * d;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int col = c0 + 4 * (lane + 32 * k);
+#pragma unroll
+    for (int j = 0; j < S; ++j) wreg[j][k] = (col < d) ? ldg4(wr + (size_t)j * d + col) : zero4();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) xo[k][c] = ((col + c) / S) * S - c0;
+  }
+
+  float4 xs[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) xs[k] = zero4();
+  int cur = -1;
+
+  auto flush = [&](int row) {
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int lc = 4 * (lane + 32 * k);
+      if (c0 + lc < d) *reinterpret_cast<float4*>(xbuf + lc) = xs[k];
+    }
+    __syncwarp();
+    float* po = out + (size_t)row * d + c0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int lc = 4 * (lane + 32 * k);
+      if (c0 + lc < d) {
+        float4 y = zero4();
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          if (S % 4 == 0) {
+            const float x = xbuf[xo[k][0] + j];
+            fma4(y, x, wreg[j][k]);
+          } else {
+            y.x = fmaf(wreg[j][k].x, xbuf[xo[k][0] + j], y.x);
+            y.y = fmaf(wreg[j][k].y, xbuf[xo[k][1] + j], y.y);
+            y.z = fmaf(wreg[j][k].z, xbuf[xo[k][2] + j], y.z);
+            y.w = fmaf(wreg[j][k].w, xbuf[xo[k][3] + j], y.w);
+          }
+        }
+        red4(po + lc, y);
+      }
+    }
+  };
+
+  constexpr int U = 2;
+  for (int base = beg; base < end; base += 32) {
+    const int n = min(32, end - base);
+    int my_row = 0, my_nbr = 0;
+    float my_nm = 0.f;
+    if (lane < n) {
+      my_row = __ldg(r_row + base + lane);
+      my_nbr = __ldg(r_nbr + base + lane);
+      my_nm = __ldg(r_norm + base + lane);
+    }
+    for (int t = 0; t < n; t += U) {
+      float4 x[U][NV];
+      int rv[U];
+      float nm[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int tt = min(t + u, n - 1);
+        const int src = __shfl_sync(FULL, my_nbr, tt);
+        rv[u] = __shfl_sync(FULL, my_row, tt);
+        nm[u] = __shfl_sync(FULL, my_nm, tt);
+        const float* xr = X + (size_t)src * ldx + c0;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const int lc = 4 * (lane + 32 * k);
+          x[u][k] = (c0 + lc < d) ? ldg4(xr + lc) : zero4();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (t + u < n) {
+          if (rv[u] != cur) {
+            if (cur >= 0) flush(cur);
+            cur = rv[u];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) xs[k] = zero4();
+          }
+#pragma unroll
+          for (int k = 0; k < NV; ++k) fma4(xs[k], nm[u], x[u][k]);
+        }
+      }
+    }
+  }
+  if (cur >= 0) flush(cur);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -797,6 +906,46 @@ int launch_block_dw(const WorkItem* items, int n_items, const int32_t* r_dst, co
     switch (nv) { case 1: DW(0, 4, 1); case 2: DW(0, 4, 2); case 3: DW(0, 4, 3); default: DW(0, 4, 4); }
   }
 #undef DW
+}
+
+
+template <int S, int NV>
+static int launch_block_rel_t(const WorkItem* items, int n_items, const int32_t* r_row,
+                              const int32_t* r_nbr, const float* r_norm, const float* X, int ldx,
+                              int d, const float* Wt, float* out, cudaStream_t st) {
+  const int slabs = (d + NV * 128 - 1) / (NV * 128);
+  dim3 grid((n_items + RGCN_WARPS_PER_BLOCK - 1) / RGCN_WARPS_PER_BLOCK, slabs);
+  k_block_rel<S, NV><<<grid, RGCN_THREADS, 0, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d,
+                                                     Wt, out);
+  return check_launch("k_block_rel");
+}
+
+bool block_rel_supported(int d, int s) {
+  if (s == 5) return d <= 512;
+  if (s == 4 || s == 8 || s == 16) return true;
+  return false;
+}
+
+int launch_block_rel(const WorkItem* items, int n_items, const int32_t* r_row, const int32_t* r_nbr,
+                     const float* r_norm, const float* X, int ldx, int d, int s, const float* Wt,
+                     float* out, cudaStream_t st) {
+  if (n_items == 0) return RGCN_OK;
+#define RL(S_, NV_) \
+  return launch_block_rel_t<S_, NV_>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, st)
+  const int nv = pick_nv(d);
+  if (s == 5) {
+    switch (nv) { case 1: RL(5, 1); case 2: RL(5, 2); case 3: RL(5, 3); default: RL(5, 4); }
+  } else if (s == 4) {
+    switch (nv) { case 1: RL(4, 1); case 2: RL(4, 2); case 3: RL(4, 3); default: RL(4, 4); }
+  } else if (s == 8) {
+    if (nv == 1) RL(8, 1);
+    RL(8, 2);
+  } else if (s == 16) {
+    RL(16, 1);
+  }
+#undef RL
+  rgcn_set_error("rel-major block kernel: unsupported block size");
+  return RGCN_ERR_INVALID;
 }
 
 int launch_block_relayout(const float* Wf, const float* Wb, int R, int B, int s, int transpose,

@@ -1,0 +1,46 @@
+"""AffineTransform (reference: encoders/affine_transform.py:24-82).  With onehot_input=True it is the
+free entity embedding relu(W + b) feeding the first R-GCN layer (model_builder.py:140-146)."""
+import torch
+
+from ..model import Model
+from ..common.shared_functions import glorot_variance, make_variable, make_bias
+
+
+class AffineTransform(Model):
+    def __init__(self, shape, settings, next_component=None, use_nonlinearity=False, onehot_input=False,
+                 use_bias=True):
+        Model.__init__(self, next_component, settings)
+        self.shape = shape
+        self.use_nonlinearity = use_nonlinearity
+        self.use_bias = use_bias
+        self.onehot_input = onehot_input
+
+    def local_initialize_train(self):
+        dev = self.get_device()
+        self.W = make_variable(0, glorot_variance(self.shape), self.shape, dev)
+        self.b = make_bias(self.shape[1], dev)
+
+    def local_get_weights(self):
+        return [self.W, self.b]
+
+    def _finish(self, hidden):
+        if self.use_bias:
+            hidden = hidden + self.b
+        if self.use_nonlinearity:
+            hidden = torch.relu(hidden)
+        return hidden
+
+    def get_all_subject_codes(self, mode='train'):
+        hidden = self.W if self.onehot_input else self.next_component.get_all_subject_codes(mode=mode) @ self.W
+        return self._finish(hidden)
+
+    def get_all_object_codes(self, mode='train'):
+        hidden = self.W if self.onehot_input else self.next_component.get_all_object_codes(mode=mode) @ self.W
+        return self._finish(hidden)
+
+    def get_all_codes(self, mode='train'):
+        if self.onehot_input:
+            h = self._finish(self.W)
+            return h, None, h
+        codes = self.next_component.get_all_codes(mode=mode)
+        return self._finish(codes[0] @ self.W), codes[1], self._finish(codes[2] @ self.W)

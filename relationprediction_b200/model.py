@@ -1,0 +1,181 @@
+"""Model base class: the reference's plugin protocol (code/model.py:8-182) with TensorFlow removed.
+
+A model is a linked list of components (`next_component`); calls either delegate down the chain
+(`__delegate__`), run locally then delegate (`__local_run_delegate__`), or concatenate local results
+after the deeper component's (`__local_expand_delegate__`: deepest component first, model.py:179-182).
+Where the reference built a TF graph and executed it with session.run, components here execute
+eagerly: placeholders are `Placeholder` holders the caller feeds, weights are torch CUDA tensors, and
+the hot ops are single calls into librgcn_b200.so (relationprediction_b200/ops.py).
+"""
+import numpy as np
+import torch
+
+
+class Placeholder(object):
+    """Stand-in for tf.placeholder: a named slot the driver feeds before a run (model.py:51-56)."""
+
+    def __init__(self, name, dtype, shape):
+        self.name, self.dtype, self.shape = name, dtype, shape
+        self.value = None
+        self.version = 0
+
+    def set(self, value):
+        self.value = value
+        self.version += 1
+
+    def __repr__(self):
+        return "<Placeholder %s %s %s>" % (self.name, self.dtype, self.shape)
+
+
+class Model(object):
+    next_component = None
+    save_iter = 0
+    device = None
+
+    def __init__(self, next_component, settings):
+        self.next_component = next_component
+        self.settings = settings
+        self.entity_count = int(self.settings['EntityCount'])
+        self.relation_count = int(self.settings['RelationCount'])
+        self.edge_count = int(self.settings['EdgeCount'])
+        self.parse_settings()
+
+    def parse_settings(self):
+        pass
+
+    # ---- device plumbing (the reference had one implicit tf.Session) ----
+    def get_device(self):
+        if self.device is not None:
+            return self.device
+        if self.next_component is not None:
+            return self.next_component.get_device()
+        return torch.device("cuda", torch.cuda.current_device())
+
+    def set_device(self, device):
+        self.device = torch.device(device)
+        if self.next_component is not None:
+            self.next_component.set_device(device)
+
+    # ---- checkpoint (model.py:30-39: Saver over get_weights(), global_step = save_iter) ----
+    def save(self, save_path):
+        print("saving...")
+        torch.save([w.detach().cpu() for w in self.get_weights()], "%s-%d.pt" % (save_path, self.save_iter))
+        self.save_iter += 1
+
+    def load(self, path):
+        for w, v in zip(self.get_weights(), torch.load(path)):
+            with torch.no_grad():
+                w.copy_(v.to(w.device))
+
+    # ---- high-level scoring (model.py:46-81) ----
+    def _feed_test(self, graph_triplets, triplets):
+        inputs = self.get_test_input_variables()
+        if self.needs_graph():
+            inputs[0].set(np.asarray(graph_triplets))
+            inputs[1].set(np.asarray(triplets))
+        else:
+            inputs[0].set(np.asarray(triplets))
+        self.clear_cache()
+
+    def score(self, triplets):
+        self._feed_test(getattr(self, 'train_triplets', None), triplets)
+        with torch.no_grad():
+            return self.predict().cpu().numpy()
+
+    def score_all_subjects(self, triplets):
+        self._feed_test(getattr(self, 'test_graph', None), triplets)
+        with torch.no_grad():
+            return self.predict_all_subject_scores().cpu().numpy()
+
+    def score_all_objects(self, triplets):
+        self._feed_test(getattr(self, 'test_graph', None), triplets)
+        with torch.no_grad():
+            return self.predict_all_object_scores().cpu().numpy()
+
+    def register_for_test(self, triplets):
+        self.test_graph = triplets
+
+    def preprocess(self, triplets):
+        self.train_triplets = triplets
+
+    # ---- one eager training evaluation: feed [graph_edges, X, Y] (train.py:245) -> scalar loss ----
+    def train_loss(self, *feed):
+        for ph, value in zip(self.get_train_input_variables(), feed):
+            ph.set(value)
+        self.clear_cache()
+        return self.get_loss(mode='train') + self.get_regularization()
+
+    # ---- chain protocol ----
+    def initialize_train(self):
+        return self.__local_run_delegate__('initialize_train')
+
+    def clear_cache(self):
+        return self.__local_run_delegate__('clear_cache')
+
+    def get_weights(self):
+        return self.__local_expand_delegate__('get_weights')
+
+    def set_variable(self, name, value):
+        return self.__local_run_delegate__('set_variable', name, value)
+
+    def get_train_input_variables(self):
+        return self.__local_expand_delegate__('get_train_input_variables')
+
+    def get_test_input_variables(self):
+        return self.__local_expand_delegate__('get_test_input_variables')
+
+    def get_loss(self, mode='train'):
+        return self.__delegate__('get_loss', mode)
+
+    def get_regularization(self):
+        return self.__local_expand_delegate__('get_regularization', base=0)
+
+    def get_all_subject_codes(self, mode='train'):
+        return self.__delegate__('get_all_subject_codes', mode)
+
+    def get_all_object_codes(self, mode='train'):
+        return self.__delegate__('get_all_object_codes', mode)
+
+    def get_all_codes(self, mode='train'):
+        return self.__delegate__('get_all_codes', mode)
+
+    def predict(self):
+        return self.__delegate__('predict')
+
+    def predict_all_subject_scores(self):
+        return self.__delegate__('predict_all_subject_scores')
+
+    def predict_all_object_scores(self):
+        return self.__delegate__('predict_all_object_scores')
+
+    def get_graph(self):
+        return self.__delegate__('get_graph')
+
+    def get_additional_ops(self):
+        return self.__local_expand_delegate__('get_additional_ops')
+
+    def needs_graph(self):
+        if self.next_component is None:
+            return False
+        return self.next_component.needs_graph()
+
+    def __delegate__(self, name, *args):
+        if self.next_component is not None:
+            return getattr(self.next_component, name)(*args)
+        return None
+
+    def __local_run_delegate__(self, name, *args):
+        local = 'local_' + name
+        if hasattr(self, local):
+            getattr(self, local)(*args)
+        if self.next_component is not None:
+            getattr(self.next_component, name)(*args)
+
+    def __local_expand_delegate__(self, name, *args, base=None):
+        if base is None:
+            base = []
+        local = 'local_' + name
+        local_result = getattr(self, local)(*args) if hasattr(self, local) else base
+        if self.next_component is not None:
+            return getattr(self.next_component, name)(*args) + local_result
+        return local_result

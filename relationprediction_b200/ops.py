@@ -90,7 +90,7 @@ class Graph:
         if n < 0:
             _lib.check(int(n), "rgcn_graph_export_bytes")
         dtype = np.float32 if which in (_lib.X_DST_NORM, _lib.X_SRC_NORM, _lib.X_REL_NORM,
-                                        _lib.X_MSG_NORM) else np.int32
+                                        _lib.X_MSG_NORM, _lib.X_REL2_NORM) else np.int32
         out = np.empty(n // 4, dtype=dtype)
         _lib.check(self._lib.rgcn_graph_export(self._h, which, _np_ptr(out), n), "rgcn_graph_export")
         return out

@@ -1,0 +1,151 @@
+"""1-D node sharding of the R-GCN layer across GPUs, one process per GPU.
+
+Rank p owns the contiguous node range [V*p/P, V*(p+1)/P): its rows of H / out / dH and every MESSAGE
+whose destination it owns.  Sources are addressed in an extended local row space
+[local rows | halo rows]; the halo rows (unique remote sources) arrive with ONE all-to-all-v per
+layer forward, and their gradients return with one all-to-all-v per layer backward (then a local
+scatter-add).  Weights are replicated; their gradients are summed with one all-reduce.  The
+per-message normalisation uses GLOBAL degrees, so sharded results equal the single-GPU ones.
+
+The reference has no distributed code at all (single tf.Session, train.py:278); this module is the
+multi-GPU design for the hot path only.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def node_bounds(n_nodes, world):
+    return [(n_nodes * p) // world for p in range(world + 1)]
+
+
+def owner_of(nodes, bounds):
+    return np.searchsorted(np.asarray(bounds[1:]), nodes, side="right").astype(np.int32)
+
+
+def global_messages(triples, n_nodes, n_relations, norm_mode="canonical", norm_f=None, norm_b=None):
+    """The 2E messages with globally computed norms (same rules as rgcn_graph_create)."""
+    t = np.asarray(triples, dtype=np.int32).reshape(-1, 3)
+    s, r, o = t[:, 0], t[:, 1], t[:, 2]
+    dst = np.concatenate([o, s]).astype(np.int32)
+    src = np.concatenate([s, o]).astype(np.int32)
+    relw = np.concatenate([r, r + n_relations]).astype(np.int32)
+    if norm_mode == "canonical":
+        cf = np.bincount(o, minlength=n_nodes).astype(np.float32)
+        cb = np.bincount(s, minlength=n_nodes).astype(np.float32)
+        norm = np.concatenate([np.float32(1) / cf[o], np.float32(1) / cb[s]]).astype(np.float32)
+    elif norm_mode == "explicit":
+        norm = np.concatenate([norm_f, norm_b]).astype(np.float32)
+    else:
+        norm = np.ones(dst.shape[0], np.float32)
+    return dst, src, relw, norm
+
+
+class ShardPlan(object):
+    """Pure host-side partition description of one rank (testable without any GPU)."""
+
+    def __init__(self, triples, n_nodes, n_relations, rank, world, norm_mode="canonical", norm_f=None,
+                 norm_b=None):
+        self.rank, self.world = rank, world
+        self.n_nodes, self.n_relations = n_nodes, n_relations
+        self.bounds = node_bounds(n_nodes, world)
+        lo, hi = self.bounds[rank], self.bounds[rank + 1]
+        self.lo, self.hi = lo, hi
+        self.n_local = hi - lo
+        dst, src, relw, norm = global_messages(triples, n_nodes, n_relations, norm_mode, norm_f, norm_b)
+        odst = owner_of(dst, self.bounds)
+        osrc = owner_of(src, self.bounds)
+        mine = odst == rank
+        src_g = src[mine]
+        remote = osrc[mine] != rank
+        # halo rows: unique remote sources, ascending global id (hence grouped by owner)
+        self.halo_nodes = np.unique(src_g[remote]).astype(np.int32)
+        self.n_halo = int(self.halo_nodes.shape[0])
+        src_l = np.where(remote, self.n_local + np.searchsorted(self.halo_nodes, src_g), src_g - lo)
+        self.msg_dst = (dst[mine] - lo).astype(np.int32)
+        self.msg_src = src_l.astype(np.int32)
+        self.msg_relw = relw[mine].astype(np.int32)
+        self.msg_norm = norm[mine].astype(np.float32)
+        self.msg_global_id = np.nonzero(mine)[0]
+        halo_owner = owner_of(self.halo_nodes, self.bounds)
+        self.recv_counts = np.bincount(halo_owner, minlength=world).astype(np.int64)
+        # rows every peer needs from me = unique sources I own of messages whose destination it owns
+        need = (osrc == rank) & (odst != rank)
+        pairs = np.unique(np.stack([odst[need].astype(np.int64), src[need].astype(np.int64)], 1), axis=0) \
+            if need.any() else np.zeros((0, 2), np.int64)
+        self.send_counts = np.bincount(pairs[:, 0], minlength=world).astype(np.int64)
+        self.send_rows = (pairs[:, 1] - lo).astype(np.int64)  # grouped by peer, ascending id inside
+
+
+class _HaloExchange(torch.autograd.Function):
+    """H_local [n_local,d] -> H_ext [n_local+n_halo,d]; backward returns halo gradients to their owners."""
+
+    @staticmethod
+    def forward(ctx, H_local, plan, send_rows, group):
+        d = H_local.shape[1]
+        H_ext = torch.empty(plan.n_local + plan.n_halo, d, dtype=H_local.dtype, device=H_local.device)
+        H_ext[:plan.n_local].copy_(H_local)
+        send = H_local.index_select(0, send_rows)
+        dist.all_to_all_single(H_ext[plan.n_local:], send, output_split_sizes=plan.recv_counts.tolist(),
+                               input_split_sizes=plan.send_counts.tolist(), group=group)
+        ctx.plan, ctx.group = plan, group
+        ctx.save_for_backward(send_rows)
+        return H_ext
+
+    @staticmethod
+    def backward(ctx, dH_ext):
+        plan = ctx.plan
+        (send_rows,) = ctx.saved_tensors
+        dH_ext = dH_ext.contiguous()
+        back = torch.empty(int(plan.send_counts.sum()), dH_ext.shape[1], dtype=dH_ext.dtype,
+                           device=dH_ext.device)
+        dist.all_to_all_single(back, dH_ext[plan.n_local:].contiguous(),
+                               output_split_sizes=plan.send_counts.tolist(),
+                               input_split_sizes=plan.recv_counts.tolist(), group=ctx.group)
+        dH = dH_ext[:plan.n_local].clone()
+        dH.index_add_(0, send_rows, back)
+        return dH, None, None, None
+
+
+class ShardedGraph(object):
+    def __init__(self, triples, n_nodes, n_relations, rank, world, device, norm_mode="canonical",
+                 norm_f=None, norm_b=None, group=None):
+        self.plan = ShardPlan(triples, n_nodes, n_relations, rank, world, norm_mode, norm_f, norm_b)
+        self.device = torch.device(device)
+        self.group = group
+        p = self.plan
+        self.n_local, self.n_halo = p.n_local, p.n_halo
+        index = None
+        if self.device.type == "cuda":
+            index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.graph = ops.Graph.from_messages(p.msg_dst, p.msg_src, p.msg_relw, p.msg_norm, p.n_local,
+                                             p.n_local + p.n_halo, 2 * n_relations, device=index)
+        self.send_rows = torch.as_tensor(p.send_rows, device=self.device)
+
+    def halo_exchange(self, H_local):
+        return _HaloExchange.apply(H_local, self.plan, self.send_rows, self.group)
+
+    def block_layer(self, H_local, W_forward, W_backward, W_self, n_blocks, drop_mask=None, keep=1.0,
+                    relu=True):
+        return ops.block_layer(self.halo_exchange(H_local), W_forward, W_backward, W_self, self.graph,
+                               n_blocks, drop_mask, keep, relu)
+
+    def basis_layer(self, H_local, W_forward, W_backward, C_forward, C_backward, W_self, drop_mask=None,
+                    keep=1.0, relu=True):
+        return ops.basis_layer(self.halo_exchange(H_local), W_forward, W_backward, C_forward, C_backward,
+                               W_self, self.graph, drop_mask, keep, relu)
+
+    def allreduce_weight_grads(self, weights):
+        """One all-reduce(sum) over the replicated weights' gradients (flattened into one bucket)."""
+        grads = [w.grad for w in weights if w.grad is not None]
+        if not grads:
+            return
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        off = 0
+        for g in grads:
+            n = g.numel()
+            g.copy_(flat[off:off + n].view_as(g))
+            off += n

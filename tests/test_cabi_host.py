@@ -24,12 +24,14 @@ def test_library_loads_and_exports_header_symbols():
 
 
 def _check_views(g, dst, src, relw, norm, V_dst, V_src, n_relw):
-    ref = oracle.sorted_views(dst, src, relw, norm, V_dst, V_src, n_relw)
+    ref = oracle.sorted_views(dst, src, relw, norm, V_dst, V_src, n_relw, g.info()[13])
     pairs = [(_lib.X_DST_ROWPTR, "dst_rowptr"), (_lib.X_DST_SRC, "dst_src"), (_lib.X_DST_RELW, "dst_relw"),
              (_lib.X_DST_NORM, "dst_norm"), (_lib.X_DST_MID, "dst_mid"), (_lib.X_SRC_ROWPTR, "src_rowptr"),
              (_lib.X_SRC_DST, "src_dst"), (_lib.X_SRC_RELW, "src_relw"), (_lib.X_SRC_NORM, "src_norm"),
-             (_lib.X_SRC_MID, "src_mid"), (_lib.X_REL_PTR, "rel_ptr"), (_lib.X_REL_DST, "rel_dst"),
-             (_lib.X_REL_SRC, "rel_src"), (_lib.X_REL_NORM, "rel_norm"), (_lib.X_REL_MID, "rel_mid")]
+             (_lib.X_SRC_MID, "src_mid"), (_lib.X_REL_PTR, "rel_ptr"), (_lib.X_REL_DST, "rel_row"),
+             (_lib.X_REL_SRC, "rel_nbr"), (_lib.X_REL_NORM, "rel_norm"), (_lib.X_REL_MID, "rel_mid"),
+             (_lib.X_REL2_PTR, "rel2_ptr"), (_lib.X_REL2_SRC, "rel2_row"), (_lib.X_REL2_DST, "rel2_nbr"),
+             (_lib.X_REL2_NORM, "rel2_norm"), (_lib.X_REL2_MID, "rel2_mid")]
     for which, key in pairs:
         got = g.export(which)
         np.testing.assert_array_equal(got, ref[key], err_msg=key)  # bit-exact, floats included
@@ -73,6 +75,16 @@ def test_synthetic_graph_prep_bit_exact_and_work_items(skewed):
     n_items = int(sum(1 if x <= item_max else -(-x // (-(-x // -(-x // item_max)))) for x in deg))
     assert info[7] == int((deg > item_max).sum())
     assert info[4] >= V and abs(info[4] - n_items) <= info[7]
+
+
+def test_supertiled_weight_major_views(monkeypatch):
+    monkeypatch.setenv("RGCN_SUPERTILE_ROWS", "257")
+    V, R, E = 3000, 11, 30000
+    tr = synthetic_kg(V, R, E, seed=9, skewed=True)
+    g = Graph(tr, V, R)
+    assert g.info()[13] == 257 and g.info()[14] == 12
+    dst, src, relw, norm = oracle.messages_from_triples(tr, R, V)
+    _check_views(g, dst, src, relw, norm, V, V, 2 * R)
 
 
 def test_empty_and_ragged_graphs():
