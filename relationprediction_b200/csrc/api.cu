@@ -41,6 +41,11 @@ int get_cublas(int device, cudaStream_t st, cublasHandle_t* out) {
   return RGCN_OK;
 }
 
+// gemm_mode: 0 = cuBLAS SGEMM (fp32 FMA pipes), 1 = cuBLAS fp32 emulation via BF16x9 on the tensor
+// cores (falls back to 0 when the loaded cuBLAS does not support it)
+int g_gemm_mode = 0;
+bool g_emulation_unavailable = false;
+
 // Row-major GEMM: C[m,n] = alpha * op(A) * op(B) + beta * C, op(A) is m x k, op(B) is k x n.
 int gemm_rm(cublasHandle_t h, bool ta, bool tb, int64_t m, int64_t n, int64_t k, float alpha,
             const float* A, int64_t lda, const float* B, int64_t ldb, float beta, float* C,
@@ -56,9 +61,19 @@ int gemm_rm(cublasHandle_t h, bool ta, bool tb, int64_t m, int64_t n, int64_t k,
     }
     return RGCN_OK;
   }
-  cublasStatus_t s =
-      cublasSgemm(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, (int)n, (int)m,
-                  (int)k, &alpha, B, (int)ldb, A, (int)lda, &beta, C, (int)ldc);
+  int mode = g_gemm_mode;
+  if (const char* e = std::getenv("RGCN_GEMM_MODE")) mode = std::atoi(e);
+  cublasStatus_t s = CUBLAS_STATUS_NOT_SUPPORTED;
+  if (mode == 1 && !g_emulation_unavailable) {
+    // fp32 emulation on the bf16 tensor cores (3 x bf16 split, 9 products): fp32-level accuracy
+    s = cublasGemmEx(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, (int)n, (int)m,
+                     (int)k, &alpha, B, CUDA_R_32F, (int)ldb, A, CUDA_R_32F, (int)lda, &beta, C,
+                     CUDA_R_32F, (int)ldc, CUBLAS_COMPUTE_32F_EMULATED_16BFX9, CUBLAS_GEMM_DEFAULT);
+    if (s != CUBLAS_STATUS_SUCCESS) g_emulation_unavailable = true;
+  }
+  if (s != CUBLAS_STATUS_SUCCESS)
+    s = cublasSgemm(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, (int)n, (int)m,
+                    (int)k, &alpha, B, (int)ldb, A, (int)lda, &beta, C, (int)ldc);
   if (s != CUBLAS_STATUS_SUCCESS) {
     rgcn_set_error("cublasSgemm failed: status " + std::to_string((int)s));
     return RGCN_ERR_CUDA;
@@ -134,7 +149,7 @@ AggLaunch make_agg(const CsrSide& side, const float* X, int ldx, int d, float* s
                    int* counters) {
   AggLaunch a;
   a.items = side.d_items;
-  a.n_items = (int)side.items.size();
+  a.n_items = (int)side.n_items;
   a.nbr = side.d_nbr;
   a.relw = side.d_relw;
   a.norm = side.d_norm;
@@ -163,6 +178,10 @@ static bool use_rel_major(int d, int s) {
 extern "C" int rgcn_set_option(const char* name, int64_t value) {
   if (name && std::string(name) == "block_algo") {
     g_block_algo = (int)value;
+    return RGCN_OK;
+  }
+  if (name && std::string(name) == "gemm_mode") {
+    g_gemm_mode = (int)value;
     return RGCN_OK;
   }
   rgcn_set_error("rgcn_set_option: unknown option");
@@ -216,13 +235,13 @@ extern "C" int64_t rgcn_block_workspace_bytes(const rgcn_graph_t* g, int32_t d, 
   int64_t bytes = 0;
   if (!backward) {
     bytes += align_up(wt * 4);
-    bytes += align_up((int64_t)g->by_dst.split_rows.size() * d * 4);
-    bytes += align_up((int64_t)g->by_dst.split_rows.size() * slabs * 4);
+    bytes += align_up(g->by_dst.n_split * d * 4);
+    bytes += align_up(g->by_dst.n_split * slabs * 4);
   } else {
     bytes += 2 * align_up(wt * 4);
     bytes += 2 * align_up((int64_t)g->V_dst * d * 4);
-    bytes += align_up((int64_t)g->by_src.split_rows.size() * d * 4);
-    bytes += align_up((int64_t)g->by_src.split_rows.size() * slabs * 4);
+    bytes += align_up(g->by_src.n_split * d * 4);
+    bytes += align_up(g->by_src.n_split * slabs * 4);
   }
   return bytes + 256;
 }
@@ -250,7 +269,7 @@ extern "C" int rgcn_block_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
   if (rc) return rc;
   const int s = d / B, R = g->n_relw / 2;
   const int slabs = slabs_for(d);
-  const int64_t n_split = (int64_t)g->by_dst.split_rows.size();
+  const int64_t n_split = g->by_dst.n_split;
   Carver ws(workspace, workspace_bytes);
   float* Wt = ws.take<float>((int64_t)g->n_relw * s * d);
   float* scratch = ws.take<float>(n_split * d);
@@ -277,7 +296,7 @@ extern "C" int rgcn_block_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
     // out = dropout(S);  out[dst] += W_r . sum(norm x)  (L2 vector reductions);  out = relu(out)
     rc = launch_mask_relu(out, drop_mask, 1.0f / keep, 0, (int64_t)g->V_dst * d, st);
     if (rc) return rc;
-    rc = launch_block_rel(g->by_rel.d_items, (int)g->by_rel.items.size(), g->by_rel.d_row,
+    rc = launch_block_rel(g->by_rel.d_items, (int)g->by_rel.n_items, g->by_rel.d_row,
                           g->by_rel.d_nbr, g->by_rel.d_norm, H, d, d, s, Wt, out, st);
     if (rc) return rc;
     MARK("block_agg_fwd");
@@ -317,7 +336,7 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   if (rc) return rc;
   const int s = d / B, R = g->n_relw / 2;
   const int slabs = slabs_for(d);
-  const int64_t n_split = (int64_t)g->by_src.split_rows.size();
+  const int64_t n_split = g->by_src.n_split;
   const int64_t wt = (int64_t)g->n_relw * s * d;
   Carver ws(workspace, workspace_bytes);
   float* Wtt = ws.take<float>(wt);
@@ -361,7 +380,7 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
     if (rc) return rc;
   }
   if (use_rel_major(d, s)) {
-    rc = launch_block_rel(g->by_rel_src.d_items, (int)g->by_rel_src.items.size(),
+    rc = launch_block_rel(g->by_rel_src.d_items, (int)g->by_rel_src.n_items,
                           g->by_rel_src.d_row, g->by_rel_src.d_nbr, g->by_rel_src.d_norm, G, d, d, s,
                           Wtt, dH, st);
   } else {
@@ -373,7 +392,7 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   // dW[w] = sum_{m: relw_m = w} norm_m G[dst_m] (x)_block H[src_m]
   rc = rgcn_check_cuda(cudaMemsetAsync(dWt, 0, wt * sizeof(float), st), "memset(dWt)");
   if (rc) return rc;
-  rc = launch_block_dw(g->by_rel.d_items, (int)g->by_rel.items.size(), g->by_rel.d_row,
+  rc = launch_block_dw(g->by_rel.d_items, (int)g->by_rel.n_items, g->by_rel.d_row,
                        g->by_rel.d_nbr, g->by_rel.d_norm, H, d, G, d, d, s, dWt, st);
   if (rc) return rc;
   MARK("block_dW");
@@ -427,7 +446,7 @@ extern "C" int rgcn_basis_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
   if (!rc) rc = rgcn_check_cuda(cudaMemcpyAsync(Ccat + (size_t)R * B, Cb, (size_t)R * B * 4, cudaMemcpyDeviceToDevice, st), "copy Cb");
   if (rc) return rc;
   // Agg[v][dir][k*B+b] = sum_m norm_m C[relw_m,b] H[src_m,k]
-  rc = launch_zero_rows(saved, 2 * dB, g->by_dst.d_split_rows, (int)g->by_dst.split_rows.size(), st);
+  rc = launch_zero_rows(saved, 2 * dB, g->by_dst.d_split_rows, (int)g->by_dst.n_split, st);
   if (rc) return rc;
   AggLaunch a = make_agg(g->by_dst, H, d, d, nullptr, nullptr);
   rc = launch_basis_agg(a, Ccat, B, g->n_relw, /*layout=*/0, saved, st);
@@ -517,7 +536,7 @@ extern "C" int rgcn_basis_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   if (!rc) rc = rgcn_check_cuda(cudaMemcpyAsync(dCb, dCcat + (size_t)R * B, (size_t)R * B * 4, cudaMemcpyDeviceToDevice, st), "copy dCb");
   if (rc) return rc;
   // P[u][dir][b*d+n] = sum_{m: src_m=u} norm_m C[relw_m,b] G[dst_m,n];  dH += P_dir V_dir.reshape(d, B*d)^T
-  rc = launch_zero_rows(P, 2 * dB, g->by_src.d_split_rows, (int)g->by_src.split_rows.size(), st);
+  rc = launch_zero_rows(P, 2 * dB, g->by_src.d_split_rows, (int)g->by_src.n_split, st);
   if (rc) return rc;
   AggLaunch as = make_agg(g->by_src, G, d, d, nullptr, nullptr);
   rc = launch_basis_agg(as, Ccat, B, g->n_relw, /*layout=*/1, P, st);

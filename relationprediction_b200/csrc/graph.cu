@@ -17,7 +17,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <chrono>
+#include <cstdio>
+#include <exception>
 #include <new>
+#include <thread>
 
 static thread_local std::string g_last_error;
 
@@ -152,6 +156,34 @@ int upload(T** dptr, const std::vector<T>& h, cudaStream_t st, int64_t& bytes) {
   return rc;
 }
 
+rgcn_graph* new_graph(int64_t M, int32_t V_dst, int32_t V_src, int32_t n_relw, int device) {
+  rgcn_graph* g = new (std::nothrow) rgcn_graph();
+  if (!g) return nullptr;
+  g->M = M;
+  g->V_dst = V_dst;
+  g->V_src = V_src;
+  g->n_relw = n_relw;
+  g->device = device;
+  if (const char* e = std::getenv("RGCN_ITEM_MAX")) {
+    int v = std::atoi(e);
+    if (v >= 8) g->item_max = v;
+  }
+  if (const char* e = std::getenv("RGCN_SUPERTILE_ROWS")) {
+    int v = std::atoi(e);
+    if (v >= 1) g->supertile_rows = v;
+  }
+  // message-id permutations are only needed by rgcn_graph_export: skip them on very large graphs
+  g->keep_mid = M <= (int64_t)(16 << 20);
+  if (const char* e = std::getenv("RGCN_KEEP_MID")) g->keep_mid = std::atoi(e) != 0;
+  return g;
+}
+
+bool use_device_prep(int device) {
+  if (device < 0) return false;
+  const char* e = std::getenv("RGCN_PREP");
+  return !(e && std::string(e) == "host");
+}
+
 int build(const int32_t* dst, const int32_t* src, const int32_t* relw, const float* norm, int64_t M,
           int32_t V_dst, int32_t V_src, int32_t n_relw, int device, void* stream,
           rgcn_graph_t** out) {
@@ -164,38 +196,70 @@ int build(const int32_t* dst, const int32_t* src, const int32_t* relw, const flo
     rgcn_set_error("rgcn_graph_create: bad sizes (need 0<=M<2^31, 0<=V_dst<=V_src, n_relw>0)");
     return RGCN_ERR_INVALID;
   }
+  rgcn_graph* g = new_graph(M, V_dst, V_src, n_relw, device);
+  if (!g) return RGCN_ERR_NOMEM;
+  if (use_device_prep(device)) {
+    // GPU graph preparation (graph_device.cu): upload the raw message arrays, build there
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = rgcn_check_cuda(cudaSetDevice(device), "cudaSetDevice");
+    int32_t *d_dst = nullptr, *d_src = nullptr, *d_relw = nullptr;
+    float* d_norm = nullptr;
+    const size_t nb = (size_t)std::max<int64_t>(M, 1) * 4;
+    if (!rc) rc = rgcn_check_cuda(cudaMallocAsync((void**)&d_dst, nb, st), "cudaMallocAsync");
+    if (!rc) rc = rgcn_check_cuda(cudaMallocAsync((void**)&d_src, nb, st), "cudaMallocAsync");
+    if (!rc) rc = rgcn_check_cuda(cudaMallocAsync((void**)&d_relw, nb, st), "cudaMallocAsync");
+    if (!rc) rc = rgcn_check_cuda(cudaMallocAsync((void**)&d_norm, nb, st), "cudaMallocAsync");
+    if (!rc && M > 0) {
+      rc = rgcn_check_cuda(cudaMemcpyAsync(d_dst, dst, (size_t)M * 4, cudaMemcpyHostToDevice, st), "H2D dst");
+      if (!rc) rc = rgcn_check_cuda(cudaMemcpyAsync(d_src, src, (size_t)M * 4, cudaMemcpyHostToDevice, st), "H2D src");
+      if (!rc) rc = rgcn_check_cuda(cudaMemcpyAsync(d_relw, relw, (size_t)M * 4, cudaMemcpyHostToDevice, st), "H2D relw");
+      if (!rc) rc = rgcn_check_cuda(cudaMemcpyAsync(d_norm, norm, (size_t)M * 4, cudaMemcpyHostToDevice, st), "H2D norm");
+    }
+    if (!rc) rc = rgcn_check_messages_device(d_dst, d_src, d_relw, M, V_dst, V_src, n_relw, st);
+    if (!rc) rc = rgcn_build_on_device(g, d_dst, d_src, d_relw, d_norm, st);
+    cudaFreeAsync(d_dst, st);
+    cudaFreeAsync(d_src, st);
+    cudaFreeAsync(d_relw, st);
+    cudaFreeAsync(d_norm, st);
+    if (rc) {
+      rgcn_graph_destroy(g);
+      return rc;
+    }
+    *out = g;
+    return RGCN_OK;
+  }
   for (int64_t m = 0; m < M; ++m) {
     if (dst[m] < 0 || dst[m] >= V_dst || src[m] < 0 || src[m] >= V_src || relw[m] < 0 ||
         relw[m] >= n_relw) {
+      delete g;
       rgcn_set_error("rgcn_graph_create: index out of range at message " + std::to_string(m));
       return RGCN_ERR_INVALID;
     }
   }
-  rgcn_graph* g = new (std::nothrow) rgcn_graph();
-  if (!g) return RGCN_ERR_NOMEM;
   try {
-    g->M = M;
-    g->V_dst = V_dst;
-    g->V_src = V_src;
-    g->n_relw = n_relw;
-    g->device = device;
-    if (const char* e = std::getenv("RGCN_ITEM_MAX")) {
-      int v = std::atoi(e);
-      if (v >= 8) g->item_max = v;
-    }
-    if (const char* e = std::getenv("RGCN_SUPERTILE_ROWS")) {
-      int v = std::atoi(e);
-      if (v >= 1) g->supertile_rows = v;
-    }
     g->msg_norm.assign(norm, norm + M);
 
-    std::vector<int32_t> perm;
-    // destination-major
-    sort_two_keys(dst, V_dst, relw, n_relw, M, perm, g->by_dst.rowptr);
-    fill_side(g->by_dst, perm, src, relw, norm);
-    build_items(g->by_dst.rowptr, V_dst, g->item_max, g->by_dst.items, &g->by_dst.split_nitems,
-                &g->by_dst.split_rows, /*emit_empty=*/true);
-    {
+    const bool timing = std::getenv("RGCN_PREP_TIMING") != nullptr;
+    auto tnow = []() { return std::chrono::steady_clock::now(); };
+    auto t_begin = tnow();
+    // the four sorted views are independent: build them on four host threads
+    std::exception_ptr err[4] = {nullptr, nullptr, nullptr, nullptr};
+    auto guarded = [&](int slot, auto&& fn) {
+      return std::thread([&err, slot, fn]() {
+        try {
+          fn();
+        } catch (...) {
+          err[slot] = std::current_exception();
+        }
+      });
+    };
+    std::thread t0 = guarded(0, [&]() {  // destination-major
+      auto ta = tnow();
+      std::vector<int32_t> perm;
+      sort_two_keys(dst, V_dst, relw, n_relw, M, perm, g->by_dst.rowptr);
+      fill_side(g->by_dst, perm, src, relw, norm);
+      build_items(g->by_dst.rowptr, V_dst, g->item_max, g->by_dst.items, &g->by_dst.split_nitems,
+                  &g->by_dst.split_rows, /*emit_empty=*/true);
       int64_t groups = 0;
       for (int32_t v = 0; v < V_dst; ++v) {
         int32_t prev = -1;
@@ -207,22 +271,44 @@ int build(const int32_t* dst, const int32_t* src, const int32_t* relw, const flo
         }
       }
       g->n_groups = groups;
-    }
-    // source-major
-    sort_two_keys(src, V_src, relw, n_relw, M, perm, g->by_src.rowptr);
-    fill_side(g->by_src, perm, dst, relw, norm);
-    build_items(g->by_src.rowptr, V_src, g->item_max, g->by_src.items, &g->by_src.split_nitems,
-                &g->by_src.split_rows, /*emit_empty=*/true);
+      if (timing) fprintf(stderr, "[rgcn prep] by_dst %.2f ms\n", std::chrono::duration<double, std::milli>(tnow() - ta).count());
+    });
+    std::thread t1 = guarded(1, [&]() {  // source-major
+      std::vector<int32_t> perm;
+      sort_two_keys(src, V_src, relw, n_relw, M, perm, g->by_src.rowptr);
+      fill_side(g->by_src, perm, dst, relw, norm);
+      build_items(g->by_src.rowptr, V_src, g->item_max, g->by_src.items, &g->by_src.split_nitems,
+                  &g->by_src.split_rows, /*emit_empty=*/true);
+    });
     // weight-id major views (see RelSide)
-    build_rel_side(g->by_rel, dst, V_dst, src, relw, norm, M, n_relw, g->supertile_rows, g->item_max);
-    build_rel_side(g->by_rel_src, src, V_src, dst, relw, norm, M, n_relw, g->supertile_rows,
-                   g->item_max);
+    std::thread t2 = guarded(2, [&]() {
+      build_rel_side(g->by_rel, dst, V_dst, src, relw, norm, M, n_relw, g->supertile_rows, g->item_max);
+    });
+    std::thread t3 = guarded(3, [&]() {
+      build_rel_side(g->by_rel_src, src, V_src, dst, relw, norm, M, n_relw, g->supertile_rows,
+                     g->item_max);
+    });
+    t0.join();
+    t1.join();
+    t2.join();
+    t3.join();
+    for (auto& e : err)
+      if (e) std::rethrow_exception(e);
+    if (timing)
+      fprintf(stderr, "[rgcn prep] views %.2f ms (M=%lld)\n",
+              std::chrono::duration<double, std::milli>(tnow() - t_begin).count(), (long long)M);
   } catch (const std::bad_alloc&) {
     delete g;
     rgcn_set_error("host allocation failed in graph build");
     return RGCN_ERR_NOMEM;
   }
 
+  g->by_dst.n_items = (int64_t)g->by_dst.items.size();
+  g->by_dst.n_split = (int64_t)g->by_dst.split_rows.size();
+  g->by_src.n_items = (int64_t)g->by_src.items.size();
+  g->by_src.n_split = (int64_t)g->by_src.split_rows.size();
+  g->by_rel.n_items = (int64_t)g->by_rel.items.size();
+  g->by_rel_src.n_items = (int64_t)g->by_rel_src.items.size();
   if (device >= 0) {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = rgcn_check_cuda(cudaSetDevice(device), "cudaSetDevice");
@@ -287,6 +373,37 @@ extern "C" int rgcn_graph_create(const int32_t* triples_host, int64_t E, int32_t
     return RGCN_ERR_INVALID;
   }
   int64_t M = 2 * E;
+  if (use_device_prep(device)) {
+    if (!out) {
+      rgcn_set_error("out is null");
+      return RGCN_ERR_INVALID;
+    }
+    *out = nullptr;
+    rgcn_graph* g = new_graph(M, V, V, 2 * R, device);
+    if (!g) return RGCN_ERR_NOMEM;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = rgcn_check_cuda(cudaSetDevice(device), "cudaSetDevice");
+    int32_t* d_tri = nullptr;
+    float *d_nf = nullptr, *d_nb = nullptr;
+    if (!rc) rc = rgcn_check_cuda(cudaMallocAsync((void**)&d_tri, (size_t)std::max<int64_t>(E, 1) * 12, st), "cudaMallocAsync");
+    if (!rc && E > 0) rc = rgcn_check_cuda(cudaMemcpyAsync(d_tri, triples_host, (size_t)E * 12, cudaMemcpyHostToDevice, st), "H2D triples");
+    if (!rc && norm_mode == RGCN_NORM_EXPLICIT && E > 0) {
+      rc = rgcn_check_cuda(cudaMallocAsync((void**)&d_nf, (size_t)E * 4, st), "cudaMallocAsync");
+      if (!rc) rc = rgcn_check_cuda(cudaMallocAsync((void**)&d_nb, (size_t)E * 4, st), "cudaMallocAsync");
+      if (!rc) rc = rgcn_check_cuda(cudaMemcpyAsync(d_nf, norm_f_host, (size_t)E * 4, cudaMemcpyHostToDevice, st), "H2D norm_f");
+      if (!rc) rc = rgcn_check_cuda(cudaMemcpyAsync(d_nb, norm_b_host, (size_t)E * 4, cudaMemcpyHostToDevice, st), "H2D norm_b");
+    }
+    if (!rc) rc = rgcn_build_from_triples_device(g, d_tri, E, V, R, norm_mode, d_nf, d_nb, st);
+    cudaFreeAsync(d_tri, st);
+    if (d_nf) cudaFreeAsync(d_nf, st);
+    if (d_nb) cudaFreeAsync(d_nb, st);
+    if (rc) {
+      rgcn_graph_destroy(g);
+      return rc;
+    }
+    *out = g;
+    return RGCN_OK;
+  }
   std::vector<int32_t> dst, src, relw;
   std::vector<float> norm;
   try {
@@ -339,6 +456,11 @@ extern "C" int rgcn_graph_destroy(rgcn_graph_t* g) {
   if (!g) return RGCN_OK;
   if (g->device >= 0) {
     cudaSetDevice(g->device);
+    cudaFree(g->by_dst.d_rowptr);
+    cudaFree(g->by_src.d_rowptr);
+    cudaFree(g->by_dst.d_mid);
+    cudaFree(g->by_src.d_mid);
+    cudaFree(g->d_msg_norm);
     cudaFree(g->by_dst.d_nbr);
     cudaFree(g->by_dst.d_relw);
     cudaFree(g->by_dst.d_norm);
@@ -352,6 +474,8 @@ extern "C" int rgcn_graph_destroy(rgcn_graph_t* g) {
     cudaFree(g->by_src.d_split_nitems);
     cudaFree(g->by_src.d_split_rows);
     for (RelSide* rs : {&g->by_rel, &g->by_rel_src}) {
+      cudaFree(rs->d_ptr);
+      cudaFree(rs->d_mid);
       cudaFree(rs->d_row);
       cudaFree(rs->d_nbr);
       cudaFree(rs->d_norm);
@@ -372,18 +496,18 @@ extern "C" int rgcn_graph_info(const rgcn_graph_t* g, int64_t info[16]) {
   info[1] = g->V_dst;
   info[2] = g->V_src;
   info[3] = g->n_relw;
-  info[4] = (int64_t)g->by_dst.items.size();
-  info[5] = (int64_t)g->by_src.items.size();
-  info[6] = (int64_t)g->by_rel.items.size();
-  info[7] = (int64_t)g->by_dst.split_rows.size();
-  info[8] = (int64_t)g->by_src.split_rows.size();
+  info[4] = g->by_dst.n_items;
+  info[5] = g->by_src.n_items;
+  info[6] = g->by_rel.n_items;
+  info[7] = g->by_dst.n_split;
+  info[8] = g->by_src.n_split;
   info[9] = g->n_groups;
   info[10] = g->device;
   info[11] = g->device_bytes;
   info[12] = g->item_max;
   info[13] = g->supertile_rows;
   info[14] = g->by_rel.n_super;
-  info[15] = (int64_t)g->by_rel_src.items.size();
+  info[15] = g->by_rel_src.n_items;
   return RGCN_OK;
 }
 
@@ -424,8 +548,48 @@ bool pick(const rgcn_graph_t* g, int which, View& v) {
 }
 }  // namespace
 
+namespace {
+// device-built graphs keep no host copies: describe where each exported array lives on the device
+bool pick_device(const rgcn_graph_t* g, int which, View& v) {
+  const int64_t M4 = g->M * 4;
+  const int64_t nk = (int64_t)g->by_rel.n_super * g->n_relw + 1;
+  const int64_t nk2 = (int64_t)g->by_rel_src.n_super * g->n_relw + 1;
+  switch (which) {
+    case RGCN_X_DST_ROWPTR: v = {g->by_dst.d_rowptr, ((int64_t)g->V_dst + 1) * 4}; return true;
+    case RGCN_X_DST_SRC: v = {g->by_dst.d_nbr, M4}; return true;
+    case RGCN_X_DST_RELW: v = {g->by_dst.d_relw, M4}; return true;
+    case RGCN_X_DST_NORM: v = {g->by_dst.d_norm, M4}; return true;
+    case RGCN_X_DST_MID: v = {g->by_dst.d_mid, M4}; return g->keep_mid;
+    case RGCN_X_SRC_ROWPTR: v = {g->by_src.d_rowptr, ((int64_t)g->V_src + 1) * 4}; return true;
+    case RGCN_X_SRC_DST: v = {g->by_src.d_nbr, M4}; return true;
+    case RGCN_X_SRC_RELW: v = {g->by_src.d_relw, M4}; return true;
+    case RGCN_X_SRC_NORM: v = {g->by_src.d_norm, M4}; return true;
+    case RGCN_X_SRC_MID: v = {g->by_src.d_mid, M4}; return g->keep_mid;
+    case RGCN_X_REL_PTR: v = {g->by_rel.d_ptr, nk * 4}; return true;
+    case RGCN_X_REL_DST: v = {g->by_rel.d_row, M4}; return true;
+    case RGCN_X_REL_SRC: v = {g->by_rel.d_nbr, M4}; return true;
+    case RGCN_X_REL_NORM: v = {g->by_rel.d_norm, M4}; return true;
+    case RGCN_X_REL_MID: v = {g->by_rel.d_mid, M4}; return g->keep_mid;
+    case RGCN_X_MSG_NORM: v = {g->d_msg_norm, M4}; return g->keep_mid;
+    case RGCN_X_REL2_PTR: v = {g->by_rel_src.d_ptr, nk2 * 4}; return true;
+    case RGCN_X_REL2_SRC: v = {g->by_rel_src.d_row, M4}; return true;
+    case RGCN_X_REL2_DST: v = {g->by_rel_src.d_nbr, M4}; return true;
+    case RGCN_X_REL2_NORM: v = {g->by_rel_src.d_norm, M4}; return true;
+    case RGCN_X_REL2_MID: v = {g->by_rel_src.d_mid, M4}; return g->keep_mid;
+    default: return false;
+  }
+}
+}  // namespace
+
 extern "C" int64_t rgcn_graph_export_bytes(const rgcn_graph_t* g, int which) {
   View v;
+  if (g && g->built_on_device) {
+    if (!pick_device(g, which, v)) {
+      rgcn_set_error("rgcn_graph_export_bytes: bad selector (or message ids not kept for this graph)");
+      return RGCN_ERR_INVALID;
+    }
+    return v.n;
+  }
   if (!g || !pick(g, which, v)) {
     rgcn_set_error("rgcn_graph_export_bytes: bad handle or selector");
     return RGCN_ERR_INVALID;
@@ -435,6 +599,15 @@ extern "C" int64_t rgcn_graph_export_bytes(const rgcn_graph_t* g, int which) {
 
 extern "C" int rgcn_graph_export(const rgcn_graph_t* g, int which, void* dst_host, int64_t nbytes) {
   View v;
+  if (g && dst_host && g->built_on_device) {
+    if (!pick_device(g, which, v) || nbytes < v.n) {
+      rgcn_set_error("rgcn_graph_export: bad selector or destination too small");
+      return RGCN_ERR_INVALID;
+    }
+    cudaSetDevice(g->device);
+    if (v.n == 0) return RGCN_OK;
+    return rgcn_check_cuda(cudaMemcpy(dst_host, v.p, (size_t)v.n, cudaMemcpyDeviceToHost), "export D2H");
+  }
   if (!g || !dst_host || !pick(g, which, v)) {
     rgcn_set_error("rgcn_graph_export: bad handle, selector or destination");
     return RGCN_ERR_INVALID;

@@ -27,12 +27,15 @@ struct CsrSide {
   std::vector<int32_t> split_nitems;  // per split row: how many items cover it
   std::vector<int32_t> split_rows;    // per split row: the row id
   // device mirrors
+  int32_t* d_rowptr = nullptr;
   int32_t* d_nbr = nullptr;
   int32_t* d_relw = nullptr;
   float* d_norm = nullptr;
+  int32_t* d_mid = nullptr;  // only when keep_mid
   WorkItem* d_items = nullptr;
   int32_t* d_split_nitems = nullptr;
   int32_t* d_split_rows = nullptr;
+  int64_t n_items = 0, n_split = 0;  // valid for host- and device-built graphs
 };
 
 // Weight-id major view: messages sorted by (supertile(row), weight id, row) where `row` is the row
@@ -46,10 +49,13 @@ struct RelSide {
   std::vector<float> norm;
   std::vector<WorkItem> items;  // row = weight id, split = supertile index
   int32_t n_super = 1;
+  int32_t* d_ptr = nullptr;
   int32_t* d_row = nullptr;
   int32_t* d_nbr = nullptr;
   float* d_norm = nullptr;
+  int32_t* d_mid = nullptr;  // only when keep_mid
   WorkItem* d_items = nullptr;
+  int64_t n_items = 0;
 };
 
 struct rgcn_graph {
@@ -64,8 +70,21 @@ struct rgcn_graph {
   CsrSide by_src;               // rows = sources,      nbr = destination
   RelSide by_rel;               // weight-id major, row = dst, nbr = src  (forward, dW)
   RelSide by_rel_src;           // weight-id major, row = src, nbr = dst  (backward w.r.t. H)
-  int supertile_rows = 32768;
+  int supertile_rows = 8192;
+  bool built_on_device = false;  // structures were built by graph_device.cu (host vectors empty)
+  bool keep_mid = true;          // keep message-id permutations / original-order norm for export
+  float* d_msg_norm = nullptr;
 };
+
+// graph_device.cu
+int rgcn_build_on_device(rgcn_graph* g, const int32_t* d_dst, const int32_t* d_src,
+                         const int32_t* d_relw, const float* d_norm, cudaStream_t st);
+int rgcn_build_from_triples_device(rgcn_graph* g, const int32_t* d_triples, int64_t E, int32_t V,
+                                   int32_t R, int norm_mode, const float* d_norm_f,
+                                   const float* d_norm_b, cudaStream_t st);
+int rgcn_check_messages_device(const int32_t* d_dst, const int32_t* d_src, const int32_t* d_relw,
+                               int64_t M, int32_t V_dst, int32_t V_src, int32_t n_relw,
+                               cudaStream_t st);
 
 void rgcn_set_error(const std::string& s);
 int rgcn_check_cuda(cudaError_t e, const char* what);

@@ -248,30 +248,31 @@ __global__ void __launch_bounds__(RGCN_THREADS, 1)
   float* xbuf = xbuf_all[warp];
   const int4 itv = __ldg(reinterpret_cast<const int4*>(items) + item);
   const int beg = itv.x, end = itv.y, w = itv.z;
+  constexpr int U = 2;  // messages in flight per lane (each may also carry the G row of a new run)
+
+  int xo[NV][4];
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) xo[k][c] = blk_base<S>(c0 + 4 * (lane + 32 * k) + c, s) - c0;
 
   for (int j0 = 0; j0 < s; j0 += JC) {
-    float4 acc[JC][NV], hs[NV];
+    float4 acc[JC][NV], hs[NV], gcur[NV];
 #pragma unroll
     for (int jj = 0; jj < JC; ++jj)
 #pragma unroll
       for (int k = 0; k < NV; ++k) acc[jj][k] = zero4();
 #pragma unroll
-    for (int k = 0; k < NV; ++k) hs[k] = zero4();
+    for (int k = 0; k < NV; ++k) hs[k] = gcur[k] = zero4();
     int cur = -1;
 
-    auto flush = [&](int dstv) {
-      float4 g[NV];
-      const float* gr = G + (size_t)dstv * ldg + c0;
+    // one outer product per run: acc[j][cols] += G[run dst][cols] * (sum norm*H[src])[block(col) + j]
+    auto flush = [&]() {
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const int lc = 4 * (lane + 32 * k);
-        if (c0 + lc < d) {
-          g[k] = ldg4(gr + lc);
-          *reinterpret_cast<float4*>(xbuf + lc) = hs[k];
-        } else {
-          g[k] = zero4();
-        }
+        if (c0 + lc < d) *reinterpret_cast<float4*>(xbuf + lc) = hs[k];
       }
       __syncwarp();
 #pragma unroll
@@ -280,17 +281,14 @@ __global__ void __launch_bounds__(RGCN_THREADS, 1)
         if (j < s) {
 #pragma unroll
           for (int k = 0; k < NV; ++k) {
-            const int lc = 4 * (lane + 32 * k);
-            const int col = c0 + lc;
-            if (col < d) {
+            if (c0 + 4 * (lane + 32 * k) < d) {
               if (S > 0 && S % 4 == 0) {
-                const float x = xbuf[blk_base<S>(col, s) - c0 + j];
-                fma4(acc[jj][k], x, g[k]);
+                fma4(acc[jj][k], xbuf[xo[k][0] + j], gcur[k]);
               } else {
-                acc[jj][k].x = fmaf(g[k].x, xbuf[blk_base<S>(col + 0, s) - c0 + j], acc[jj][k].x);
-                acc[jj][k].y = fmaf(g[k].y, xbuf[blk_base<S>(col + 1, s) - c0 + j], acc[jj][k].y);
-                acc[jj][k].z = fmaf(g[k].z, xbuf[blk_base<S>(col + 2, s) - c0 + j], acc[jj][k].z);
-                acc[jj][k].w = fmaf(g[k].w, xbuf[blk_base<S>(col + 3, s) - c0 + j], acc[jj][k].w);
+                acc[jj][k].x = fmaf(gcur[k].x, xbuf[xo[k][0] + j], acc[jj][k].x);
+                acc[jj][k].y = fmaf(gcur[k].y, xbuf[xo[k][1] + j], acc[jj][k].y);
+                acc[jj][k].z = fmaf(gcur[k].z, xbuf[xo[k][2] + j], acc[jj][k].z);
+                acc[jj][k].w = fmaf(gcur[k].w, xbuf[xo[k][3] + j], acc[jj][k].w);
               }
             }
           }
@@ -307,31 +305,42 @@ __global__ void __launch_bounds__(RGCN_THREADS, 1)
         my_src = __ldg(r_src + base + lane);
         my_nm = __ldg(r_norm + base + lane);
       }
-      for (int t = 0; t < n; t += U_MSG) {
-        float4 x[U_MSG][NV];
-        int dv[U_MSG];
-        float nm[U_MSG];
+      for (int t = 0; t < n; t += U) {
+        float4 x[U][NV], gx[U][NV];
+        int dv[U];
+        float nm[U];
+        bool starts[U];
+        int prev = cur;
 #pragma unroll
-        for (int u = 0; u < U_MSG; ++u) {
+        for (int u = 0; u < U; ++u) {
           const int tt = min(t + u, n - 1);
           const int src = __shfl_sync(FULL, my_src, tt);
           dv[u] = __shfl_sync(FULL, my_dst, tt);
           nm[u] = __shfl_sync(FULL, my_nm, tt);
+          starts[u] = (t + u < n) && (dv[u] != prev);  // warp-uniform
+          prev = dv[u];
           const float* xr = H + (size_t)src * ldh + c0;
+          const float* gr = G + (size_t)dv[u] * ldg + c0;
 #pragma unroll
           for (int k = 0; k < NV; ++k) {
             const int lc = 4 * (lane + 32 * k);
-            x[u][k] = (c0 + lc < d) ? ldg4(xr + lc) : zero4();
+            const bool ok = c0 + lc < d;
+            x[u][k] = ok ? ldg4(xr + lc) : zero4();
+            // the G row of a run is fetched together with the run's first H row (no dependent load)
+            gx[u][k] = (ok && starts[u]) ? ldg4(gr + lc) : zero4();
           }
         }
 #pragma unroll
-        for (int u = 0; u < U_MSG; ++u) {
+        for (int u = 0; u < U; ++u) {
           if (t + u < n) {
-            if (dv[u] != cur) {
-              if (cur >= 0) flush(cur);
+            if (starts[u]) {
+              if (cur >= 0) flush();
               cur = dv[u];
 #pragma unroll
-              for (int k = 0; k < NV; ++k) hs[k] = zero4();
+              for (int k = 0; k < NV; ++k) {
+                hs[k] = zero4();
+                gcur[k] = gx[u][k];
+              }
             }
 #pragma unroll
             for (int k = 0; k < NV; ++k) fma4(hs[k], nm[u], x[u][k]);
@@ -339,7 +348,7 @@ __global__ void __launch_bounds__(RGCN_THREADS, 1)
         }
       }
     }
-    if (cur >= 0) flush(cur);
+    if (cur >= 0) flush();
 
 #pragma unroll
     for (int jj = 0; jj < JC; ++jj) {
@@ -355,7 +364,6 @@ __global__ void __launch_bounds__(RGCN_THREADS, 1)
     }
   }
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // Block-diagonal aggregation, WEIGHT-ID MAJOR ("rel-major").  A warp owns <= item_max messages of
