@@ -54,6 +54,15 @@ int64_t rgcn_launch_count(void);
  * The environment variable RGCN_BLOCK_ALGO overrides the option. */
 int rgcn_set_option(const char* name, int64_t value);
 
+/* Dense fp32-accurate GEMM on the tcgen05 tensor cores (3xTF32 split, TMEM accumulators):
+ *   C[M,N] = (accumulate ? C : 0) + A[M,K] * op(B),   op(B) = B[K,N] (b_is_nk = 0) or B[N,K]^T (b_is_nk = 1)
+ * all row-major fp32 device pointers; K, N and the leading dimensions must be multiples of 4.
+ * workspace: 2*N*K floats (the hi/lo split of B).  This is the kernel the layer entry points use for
+ * the self-loop terms (gcn_basis.py:70-71 / gcn_basis_concat.py:65-66). */
+int rgcn_gemm_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, int b_is_nk, float* C,
+                     int64_t ldc, int32_t M, int32_t N, int32_t K, int accumulate, void* workspace,
+                     int64_t workspace_bytes, void* stream);
+
 /* Optional per-kernel timing (bench.py roofline): when enabled, every layer entry point records a
  * CUDA event on its stream after each internal stage.  rgcn_profile_read() synchronises, writes
  * the stage durations (ms) and their '\n'-separated names, clears the log and returns the count. */

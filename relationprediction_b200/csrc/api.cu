@@ -41,9 +41,10 @@ int get_cublas(int device, cudaStream_t st, cublasHandle_t* out) {
   return RGCN_OK;
 }
 
-// gemm_mode: 0 = cuBLAS SGEMM (fp32 FMA pipes), 1 = cuBLAS fp32 emulation via BF16x9 on the tensor
+// gemm_mode: 2 (default) = own tcgen05 3xTF32 kernel (gemm_tf32x3.cu) where it applies, else cuBLAS;
+// 0 = cuBLAS SGEMM (fp32 FMA pipes), 1 = cuBLAS fp32 emulation via BF16x9 on the tensor
 // cores (falls back to 0 when the loaded cuBLAS does not support it)
-int g_gemm_mode = 0;
+int g_gemm_mode = 2;
 bool g_emulation_unavailable = false;
 
 // Row-major GEMM: C[m,n] = alpha * op(A) * op(B) + beta * C, op(A) is m x k, op(B) is k x n.
@@ -79,6 +80,27 @@ int gemm_rm(cublasHandle_t h, bool ta, bool tb, int64_t m, int64_t n, int64_t k,
     return RGCN_ERR_CUDA;
   }
   return RGCN_OK;
+}
+
+// GEMM dispatch: the tcgen05 3xTF32 kernel (gemm_tf32x3.cu) whenever the contraction runs along the
+// contiguous dimension of A (every GEMM of the layers except the V-long reductions A^T B), cuBLAS
+// otherwise.  split_ws: 2*n*k floats for the hi/lo split of B.
+int gemm_any(cublasHandle_t h, float* split_ws, bool ta, bool tb, int64_t m, int64_t n, int64_t k,
+             float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta, float* C,
+             int64_t ldc) {
+  int mode = g_gemm_mode;
+  if (const char* e = std::getenv("RGCN_GEMM_MODE")) mode = std::atoi(e);
+  const bool ok = mode == 2 && !ta && alpha == 1.f && (beta == 0.f || beta == 1.f) && k > 0 && m > 0 &&
+                  k % 4 == 0 && n % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 && split_ws &&
+                  m < 0x7fffffffLL;
+  if (!ok) return gemm_rm(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  cudaStream_t st;
+  cublasGetStream(h, &st);
+  float* hi = split_ws;
+  float* lo = split_ws + (size_t)n * k;
+  int rc = launch_gemm_split_b(B, ldb, (int)n, (int)k, tb ? 0 : 1, hi, lo, st);
+  if (rc) return rc;
+  return launch_gemm_tf32x3(A, lda, hi, lo, k, C, ldc, (int)m, (int)n, (int)k, beta != 0.f, st);
 }
 
 // ---- optional stage timing -------------------------------------------------------------------
@@ -188,6 +210,26 @@ extern "C" int rgcn_set_option(const char* name, int64_t value) {
   return RGCN_ERR_INVALID;
 }
 
+extern "C" int rgcn_gemm_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, int b_is_nk,
+                                float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
+                                int accumulate, void* workspace, int64_t workspace_bytes,
+                                void* stream) {
+  if (!A || !B || !C || !workspace || M < 0 || N <= 0 || K <= 0) {
+    rgcn_set_error("rgcn_gemm_tf32x3: bad arguments");
+    return RGCN_ERR_INVALID;
+  }
+  if (workspace_bytes < (int64_t)2 * N * K * 4) {
+    rgcn_set_error("rgcn_gemm_tf32x3: workspace too small (need 2*N*K floats)");
+    return RGCN_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* hi = (float*)workspace;
+  float* lo = hi + (size_t)N * K;
+  int rc = launch_gemm_split_b(B, ldb, N, K, b_is_nk ? 0 : 1, hi, lo, st);
+  if (rc) return rc;
+  return launch_gemm_tf32x3(A, lda, hi, lo, K, C, ldc, M, N, K, accumulate, st);
+}
+
 extern "C" int64_t rgcn_launch_count(void) { return g_rgcn_launches; }
 
 extern "C" int rgcn_profile_enable(int enable) {
@@ -232,7 +274,7 @@ extern "C" int64_t rgcn_block_workspace_bytes(const rgcn_graph_t* g, int32_t d, 
   const int64_t s = d / B;
   const int64_t wt = (int64_t)g->n_relw * s * d;
   const int slabs = slabs_for(d);
-  int64_t bytes = 0;
+  int64_t bytes = align_up((int64_t)2 * d * d * 4);  // hi/lo split of W_self for the tensor-core GEMM
   if (!backward) {
     bytes += align_up(wt * 4);
     bytes += align_up(g->by_dst.n_split * d * 4);
@@ -271,6 +313,7 @@ extern "C" int rgcn_block_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
   const int slabs = slabs_for(d);
   const int64_t n_split = g->by_dst.n_split;
   Carver ws(workspace, workspace_bytes);
+  float* split_ws = ws.take<float>((int64_t)2 * d * d);
   float* Wt = ws.take<float>((int64_t)g->n_relw * s * d);
   float* scratch = ws.take<float>(n_split * d);
   int* counters = ws.take<int>(n_split * slabs);
@@ -289,7 +332,7 @@ extern "C" int rgcn_block_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
   rc = get_cublas(g->device, st, &h);
   if (rc) return rc;
   // self-loop term S = H[0:V_dst] @ W_self written straight into `out` (gcn_basis_concat.py:65-66)
-  rc = gemm_rm(h, false, false, g->V_dst, d, d, 1.f, H, d, Wself, d, 0.f, out, d);
+  rc = gemm_any(h, split_ws, false, false, g->V_dst, d, d, 1.f, H, d, Wself, d, 0.f, out, d);
   if (rc) return rc;
   MARK("gemm_self_loop");
   if (use_rel_major(d, s)) {
@@ -339,6 +382,7 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   const int64_t n_split = g->by_src.n_split;
   const int64_t wt = (int64_t)g->n_relw * s * d;
   Carver ws(workspace, workspace_bytes);
+  float* split_ws = ws.take<float>((int64_t)2 * d * d);
   float* Wtt = ws.take<float>(wt);
   float* dWt = ws.take<float>(wt);
   float* G = ws.take<float>((int64_t)g->V_dst * d);
@@ -356,11 +400,11 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   rc = get_cublas(g->device, st, &h);
   if (rc) return rc;
   // dW_self = H[0:V_dst]^T dS
-  rc = gemm_rm(h, true, false, d, d, g->V_dst, 1.f, H, d, dS, d, 0.f, dWself, d);
+  rc = gemm_any(h, split_ws, true, false, d, d, g->V_dst, 1.f, H, d, dS, d, 0.f, dWself, d);
   if (rc) return rc;
   MARK("gemm_dWself");
   // dH[0:V_dst] = dS W_self^T ; halo rows start at zero
-  rc = gemm_rm(h, false, true, g->V_dst, d, d, 1.f, dS, d, Wself, d, 0.f, dH, d);
+  rc = gemm_any(h, split_ws, false, true, g->V_dst, d, d, 1.f, dS, d, Wself, d, 0.f, dH, d);
   if (rc) return rc;
   if (g->V_src > g->V_dst) {
     rc = rgcn_check_cuda(cudaMemsetAsync(dH + (size_t)g->V_dst * d, 0,
@@ -411,6 +455,7 @@ extern "C" int64_t rgcn_basis_workspace_bytes(const rgcn_graph_t* g, int32_t d, 
     return RGCN_ERR_INVALID;
   }
   int64_t bytes = align_up((int64_t)g->n_relw * B * 4);  // concatenated coefficient table
+  bytes += align_up((int64_t)2 * d * d * B * 4);           // hi/lo split of the GEMM B operands
   if (backward) {
     bytes += align_up((int64_t)g->n_relw * B * 4);           // dC (concatenated)
     bytes += 2 * align_up((int64_t)g->V_dst * d * 4);        // G, dS
@@ -442,6 +487,7 @@ extern "C" int rgcn_basis_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
   const int64_t dB = (int64_t)d * B;
   Carver ws(workspace, workspace_bytes);
   float* Ccat = ws.take<float>((int64_t)g->n_relw * B);
+  float* split_ws = ws.take<float>((int64_t)2 * d * d * B);
   rc = rgcn_check_cuda(cudaMemcpyAsync(Ccat, Cf, (size_t)R * B * 4, cudaMemcpyDeviceToDevice, st), "copy Cf");
   if (!rc) rc = rgcn_check_cuda(cudaMemcpyAsync(Ccat + (size_t)R * B, Cb, (size_t)R * B * 4, cudaMemcpyDeviceToDevice, st), "copy Cb");
   if (rc) return rc;
@@ -454,14 +500,14 @@ extern "C" int rgcn_basis_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
   cublasHandle_t h;
   rc = get_cublas(g->device, st, &h);
   if (rc) return rc;
-  rc = gemm_rm(h, false, false, g->V_dst, d, d, 1.f, H, d, Wself, d, 0.f, out, d);
+  rc = gemm_any(h, split_ws, false, false, g->V_dst, d, d, 1.f, H, d, Wself, d, 0.f, out, d);
   if (rc) return rc;
   rc = launch_mask_relu(out, drop_mask, 1.0f / keep, 0, (int64_t)g->V_dst * d, st);
   if (rc) return rc;
   // out += Agg_f @ Vf.reshape(d*B, d) + Agg_b @ Vb.reshape(d*B, d)    (gcn_basis.py:60-68 re-associated)
-  rc = gemm_rm(h, false, false, g->V_dst, d, dB, 1.f, saved, 2 * dB, Vf, d, 1.f, out, d);
+  rc = gemm_any(h, split_ws, false, false, g->V_dst, d, dB, 1.f, saved, 2 * dB, Vf, d, 1.f, out, d);
   if (rc) return rc;
-  rc = gemm_rm(h, false, false, g->V_dst, d, dB, 1.f, saved + dB, 2 * dB, Vb, d, 1.f, out, d);
+  rc = gemm_any(h, split_ws, false, false, g->V_dst, d, dB, 1.f, saved + dB, 2 * dB, Vb, d, 1.f, out, d);
   if (rc) return rc;
   return launch_mask_relu(out, nullptr, 1.f, relu, (int64_t)g->V_dst * d, st);
 }
@@ -491,6 +537,7 @@ extern "C" int rgcn_basis_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   const int64_t dB = (int64_t)d * B;
   Carver ws(workspace, workspace_bytes);
   float* Ccat = ws.take<float>((int64_t)g->n_relw * B);
+  float* split_ws = ws.take<float>((int64_t)2 * d * d * B);
   float* dCcat = ws.take<float>((int64_t)g->n_relw * B);
   float* G = ws.take<float>((int64_t)g->V_dst * d);
   float* dS = ws.take<float>((int64_t)g->V_dst * d);
@@ -506,9 +553,9 @@ extern "C" int rgcn_basis_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   cublasHandle_t h;
   rc = get_cublas(g->device, st, &h);
   if (rc) return rc;
-  rc = gemm_rm(h, true, false, d, d, g->V_dst, 1.f, H, d, dS, d, 0.f, dWself, d);
+  rc = gemm_any(h, split_ws, true, false, d, d, g->V_dst, 1.f, H, d, dS, d, 0.f, dWself, d);
   if (rc) return rc;
-  rc = gemm_rm(h, false, true, g->V_dst, d, d, 1.f, dS, d, Wself, d, 0.f, dH, d);
+  rc = gemm_any(h, split_ws, false, true, g->V_dst, d, d, 1.f, dS, d, Wself, d, 0.f, dH, d);
   if (rc) return rc;
   if (g->V_src > g->V_dst) {
     rc = rgcn_check_cuda(cudaMemsetAsync(dH + (size_t)g->V_dst * d, 0,
@@ -517,14 +564,14 @@ extern "C" int rgcn_basis_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
     if (rc) return rc;
   }
   // dV_dir.reshape(d*B, d) = Agg_dir^T G
-  rc = gemm_rm(h, true, false, dB, d, g->V_dst, 1.f, saved, 2 * dB, G, d, 0.f, dVf, d);
+  rc = gemm_any(h, split_ws, true, false, dB, d, g->V_dst, 1.f, saved, 2 * dB, G, d, 0.f, dVf, d);
   if (rc) return rc;
-  rc = gemm_rm(h, true, false, dB, d, g->V_dst, 1.f, saved + dB, 2 * dB, G, d, 0.f, dVb, d);
+  rc = gemm_any(h, split_ws, true, false, dB, d, g->V_dst, 1.f, saved + dB, 2 * dB, G, d, 0.f, dVb, d);
   if (rc) return rc;
   // dAgg_dir = G V_dir.reshape(d*B, d)^T
-  rc = gemm_rm(h, false, true, g->V_dst, dB, d, 1.f, G, d, Vf, d, 0.f, dAgg, 2 * dB);
+  rc = gemm_any(h, split_ws, false, true, g->V_dst, dB, d, 1.f, G, d, Vf, d, 0.f, dAgg, 2 * dB);
   if (rc) return rc;
-  rc = gemm_rm(h, false, true, g->V_dst, dB, d, 1.f, G, d, Vb, d, 0.f, dAgg + dB, 2 * dB);
+  rc = gemm_any(h, split_ws, false, true, g->V_dst, dB, d, 1.f, G, d, Vb, d, 0.f, dAgg + dB, 2 * dB);
   if (rc) return rc;
   // dC[w,b] = sum_m norm_m < H[src_m], dAgg[dst_m][dir][:,b] >
   rc = rgcn_check_cuda(cudaMemsetAsync(dCcat, 0, (size_t)g->n_relw * B * 4, st), "memset(dC)");
@@ -541,9 +588,9 @@ extern "C" int rgcn_basis_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   AggLaunch as = make_agg(g->by_src, G, d, d, nullptr, nullptr);
   rc = launch_basis_agg(as, Ccat, B, g->n_relw, /*layout=*/1, P, st);
   if (rc) return rc;
-  rc = gemm_rm(h, false, true, g->V_src, d, dB, 1.f, P, 2 * dB, Vf, dB, 1.f, dH, d);
+  rc = gemm_any(h, split_ws, false, true, g->V_src, d, dB, 1.f, P, 2 * dB, Vf, dB, 1.f, dH, d);
   if (rc) return rc;
-  return gemm_rm(h, false, true, g->V_src, d, dB, 1.f, P + dB, 2 * dB, Vb, dB, 1.f, dH, d);
+  return gemm_any(h, split_ws, false, true, g->V_src, d, dB, 1.f, P + dB, 2 * dB, Vb, dB, 1.f, dH, d);
 }
 
 // ------------------------------------------------------------------------------------------------

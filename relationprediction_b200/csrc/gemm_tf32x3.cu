@@ -1,0 +1,302 @@
+// gemm_tf32x3.cu -- fp32-accurate dense GEMM on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+//
+//   C[M,N] (+)= A[M,K] * B^T      A row-major (K contiguous), B given K-major as Bt[N,K]
+//
+// Used for the self-loop terms of the R-GCN layer (H @ W_self, dS @ W_self^T; reference:
+// gcn_basis.py:70-71 / gcn_basis_concat.py:65-66 `tf.matmul`).  The 1e-4 parity bar rules out a
+// single TF32 pass (10-bit mantissa), so every fp32 operand is split a = a_hi + a_lo with a_hi
+// exactly representable in TF32 (low 13 mantissa bits cleared) and three MMAs are issued per
+// K-step:  a_hi*b_hi + a_hi*b_lo + a_lo*b_hi   (the a_lo*b_lo term is below fp32 rounding).
+//
+// Structure (one CTA per 128x128 output tile, 160 threads, 1 CTA/SM):
+//   warps 0-3  producers: global fp32 -> registers -> (hi, lo) -> st.shared in the UMMA canonical
+//              K-major SWIZZLE_128B layout for A; cp.async of the pre-split Bt_hi / Bt_lo tiles;
+//              fence.proxy.async + mbarrier arrive.  After the main loop they become the epilogue:
+//              tcgen05.ld of the accumulator rows -> global stores.
+//   warp 4     one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=128, K=8), 12 per
+//              32-wide K block, and frees smem stages / publishes the accumulator with tcgen05.commit.
+//   3-stage smem ring (64 KB per stage), accumulator 128 lanes x 128 columns of TMEM.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;  // BK floats = 128 bytes = one swizzle row
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;     // 16 KB (A_hi, A_lo, B_hi, B_lo each)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES; // 64 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
+constexpr int N_PRODUCERS = 128;
+constexpr int TMEM_COLS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B) | [46,48) version = 1 (sm_100)
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (bits 4-5 = 1), A=B=TF32 (bits 7-9,
+// 10-12 = 2), both K-major (bits 15, 16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ uint32_t swz(int r, int c) {  // byte offset of 16 B chunk c of tile row r
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+
+__global__ void __launch_bounds__(160, 1)
+    k_gemm_tf32x3(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bhi,
+                  const float* __restrict__ Blo, int64_t ldb, float* __restrict__ C, int64_t ldc,
+                  int M, int N, int K, int accumulate) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B: 1024 B aligned
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], N_PRODUCERS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {  // TMEM allocation by one full warp; the same warp frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_smem)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp < 4) {
+    // ================= producers =================
+    const int c = tid & 7;        // 16 B chunk within the 128 B K-row
+    const int rbase = tid >> 3;   // 0..15
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES;
+      const uint32_t b_hi = a_lo + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
+      const int col = kb * BK + c * 4;
+      const bool col_ok = col < K;  // K % 4 == 0: a 16 B chunk is entirely valid or entirely padding
+      // B tiles: pre-split, K-major -> straight async copies (zero-filled outside the matrix)
+#pragma unroll
+      for (int i = 0; i < BN / 16; ++i) {
+        const int r = rbase + 16 * i;
+        const bool ok = col_ok && (n0 + r < N);
+        const size_t off = ok ? ((size_t)(n0 + r) * ldb + col) : 0;
+        cp_async16(b_hi + swz(r, c), Bhi + off, ok ? 16u : 0u);
+        cp_async16(b_lo + swz(r, c), Blo + off, ok ? 16u : 0u);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      // A tile: fp32 -> (hi, lo) in registers
+      float4 v[BM / 16];
+#pragma unroll
+      for (int i = 0; i < BM / 16; ++i) {
+        const int r = rbase + 16 * i;
+        v[i] = (col_ok && (m0 + r < M))
+                   ? __ldg(reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + col))
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < BM / 16; ++i) {
+        const int r = rbase + 16 * i;
+        float4 hi, lo;
+        hi.x = __uint_as_float(__float_as_uint(v[i].x) & 0xffffe000u);
+        hi.y = __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u);
+        hi.z = __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u);
+        hi.w = __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u);
+        lo.x = v[i].x - hi.x;
+        lo.y = v[i].y - hi.y;
+        lo.z = v[i].z - hi.z;
+        lo.w = v[i].w - hi.w;
+        const uint32_t o = swz(r, c);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + o), "f"(hi.x), "f"(hi.y),
+                     "f"(hi.z), "f"(hi.w)
+                     : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + o), "f"(lo.x), "f"(lo.y),
+                     "f"(lo.z), "f"(lo.w)
+                     : "memory");
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core
+      mbar_arrive(&full_bar[s]);
+    }
+    // ================= epilogue =================
+    mbar_wait(&accum_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m0 + warp * 32 + lane;  // TMEM lane == accumulator row
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int cb = 0; cb < BN; cb += 32) {
+      uint32_t r[32];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+            "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+            "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+            "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+            "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr + (uint32_t)cb));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < M) {
+        float* crow = C + (size_t)row * ldc + n0 + cb;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int ncol = n0 + cb + 4 * q;
+          if (ncol < N) {  // N % 4 == 0
+            float4 o = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            if (accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(crow + 4 * q);
+              o.x += old.x;
+              o.y += old.y;
+              o.z += old.z;
+              o.w += old.w;
+            }
+            *reinterpret_cast<float4*>(crow + 4 * q) = o;
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else {
+    // ================= MMA issuer (warp 4, one elected lane) =================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES;
+        const uint32_t b_hi = a_lo + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BK / 8; ++kk) {  // UMMA K = 8 tf32 = 32 bytes along the swizzled row
+          const uint64_t dah = make_desc(a_hi + kk * 32), dal = make_desc(a_lo + kk * 32);
+          const uint64_t dbh = make_desc(b_hi + kk * 32), dbl = make_desc(b_lo + kk * 32);
+          umma_tf32(tmem_base, dal, dbh, (kb | kk) != 0);  // small terms first
+          umma_tf32(tmem_base, dah, dbl, 1);
+          umma_tf32(tmem_base, dah, dbh, 1);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs have read it
+      }
+      umma_commit(&accum_bar);  // accumulator complete
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "n"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// Bt_hi/Bt_lo[n][k] from B: transposed = 0: B is [N,K] row-major already (K-major);
+//                                  transposed = 1: B is [K,N] row-major -> transpose while splitting
+__global__ void k_split_b(const float* __restrict__ B, int64_t ldb, int N, int K, int transposed,
+                          float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t total = (int64_t)N * K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / K), k = (int)(i % K);
+    const float v = transposed ? __ldg(B + (size_t)k * ldb + n) : __ldg(B + (size_t)n * ldb + k);
+    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
+}  // namespace
+
+int launch_gemm_split_b(const float* B, int64_t ldb, int N, int K, int transposed, float* hi, float* lo,
+                        cudaStream_t st) {
+  const int64_t total = (int64_t)N * K;
+  if (total == 0) return RGCN_OK;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_split_b<<<blocks, 256, 0, st>>>(B, ldb, N, K, transposed, hi, lo);
+  ++g_rgcn_launches;
+  return rgcn_check_cuda(cudaGetLastError(), "k_split_b");
+}
+
+int launch_gemm_tf32x3(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, int64_t ldb,
+                       float* C, int64_t ldc, int M, int N, int K, int accumulate, cudaStream_t st) {
+  if (M == 0 || N == 0) return RGCN_OK;
+  if (K % 4 != 0 || N % 4 != 0 || lda % 4 != 0 || ldb % 4 != 0 || ldc % 4 != 0) {
+    rgcn_set_error("gemm_tf32x3: K, N and leading dimensions must be multiples of 4");
+    return RGCN_ERR_INVALID;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = rgcn_check_cuda(cudaFuncSetAttribute(k_gemm_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  SMEM_BYTES),
+                             "cudaFuncSetAttribute(gemm smem)");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
+  k_gemm_tf32x3<<<grid, 160, SMEM_BYTES, st>>>(A, lda, Bt_hi, Bt_lo, ldb, C, ldc, M, N, K, accumulate);
+  ++g_rgcn_launches;
+  return rgcn_check_cuda(cudaGetLastError(), "k_gemm_tf32x3");
+}

@@ -74,6 +74,12 @@ int launch_mask_relu(float* x, const uint8_t* mask, float inv_keep, int relu, in
 // zero rows listed in `rows` of a [*, width] matrix
 int launch_zero_rows(float* A, int64_t width, const int32_t* rows, int n_rows, cudaStream_t st);
 
+// fp32-accurate tensor-core GEMM (gemm_tf32x3.cu): C[M,N] (+)= A[M,K] * Bt[N,K]^T with Bt pre-split
+int launch_gemm_split_b(const float* B, int64_t ldb, int N, int K, int transposed, float* hi, float* lo,
+                        cudaStream_t st);
+int launch_gemm_tf32x3(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, int64_t ldb,
+                       float* C, int64_t ldc, int M, int N, int K, int accumulate, cudaStream_t st);
+
 // DistMult
 int launch_distmult_forward(const float* codes, const float* rel, int d, const int32_t* X, int64_t N,
                             const float* Y, float* energies, float* loss_out, cudaStream_t st);

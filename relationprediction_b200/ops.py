@@ -291,3 +291,21 @@ class _DistMultFn(torch.autograd.Function):
 def distmult(codes, rel, X, Y=None):
     """DistMult energies + sigmoid cross-entropy + L2 term (bilinear_diag.py:14-34,63-69)."""
     return _DistMultFn.apply(codes, rel, X, Y)
+
+
+def gemm_tf32x3(A, B, b_is_nk=False, out=None, accumulate=False):
+    """C = A @ B (B [K,N]) or A @ B.T (B [N,K], b_is_nk=True) on the tcgen05 tensor cores with the
+    3xTF32 split (fp32-level accuracy).  Thin wrapper over rgcn_gemm_tf32x3 (include/rgcn_b200.h)."""
+    lib = _lib.load()
+    _check_cuda_f32("A", A)
+    _check_cuda_f32("B", B)
+    M, K = A.shape
+    N = B.shape[0] if b_is_nk else B.shape[1]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    ws = torch.empty(2 * N * K, dtype=torch.float32, device=A.device)
+    rc = lib.rgcn_gemm_tf32x3(_ptr(A), A.stride(0), _ptr(B), B.stride(0), int(b_is_nk), _ptr(out),
+                              out.stride(0), M, N, K, int(accumulate), _ptr(ws), ws.numel() * 4,
+                              _stream(A.device))
+    _lib.check(rc, "rgcn_gemm_tf32x3")
+    return out

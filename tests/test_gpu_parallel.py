@@ -1,0 +1,83 @@
+"""GPU (>= 2 devices): the 1-D node-sharded layer (halo all-to-all over NCCL) reproduces the single-GPU
+forward output, input gradient and (after the all-reduce) weight gradients."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import synthetic_kg
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, V, R, E, d, B, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from relationprediction_b200 import parallel
+        tr = synthetic_kg(V, R, E, seed=5, skewed=True)
+        sg = parallel.ShardedGraph(tr, V, R, rank, world, dev)
+        p = sg.plan
+        g = torch.Generator().manual_seed(0)
+        s = d // B
+        H = torch.randn(V, d, generator=g)
+        dOut = torch.randn(V, d, generator=g)
+        Wf = (torch.randn(R, B, s, s, generator=g) * 0.3).to(dev).requires_grad_(True)
+        Wb = (torch.randn(R, B, s, s, generator=g) * 0.3).to(dev).requires_grad_(True)
+        Ws = (torch.randn(d, d, generator=g) * 0.05).to(dev).requires_grad_(True)
+        Hl = H[p.lo:p.hi].to(dev).requires_grad_(True)
+        out = sg.block_layer(Hl, Wf, Wb, Ws, B, None, 1.0, True)
+        out.backward(dOut[p.lo:p.hi].to(dev))
+        sg.allreduce_weight_grads([Wf, Wb, Ws])
+        torch.cuda.synchronize()
+        np.savez(os.path.join(out_dir, "r%d.npz" % rank), out=out.detach().cpu().numpy(), dH=Hl.grad.cpu().numpy(),
+                 dWf=Wf.grad.cpu().numpy(), dWb=Wb.grad.cpu().numpy(), dWs=Ws.grad.cpu().numpy(), lo=p.lo, hi=p.hi)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sharded_block_layer_equals_single_gpu(tmp_path, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    from relationprediction_b200 import ops
+    V, R, E, d, B = 3000, 11, 40000, 500, 100
+    mp.spawn(_worker, args=(world, _free_port(), V, R, E, d, B, str(tmp_path)), nprocs=world, join=True)
+    tr = synthetic_kg(V, R, E, seed=5, skewed=True)
+    g = torch.Generator().manual_seed(0)
+    s = d // B
+    H = torch.randn(V, d, generator=g)
+    dOut = torch.randn(V, d, generator=g)
+    Wf = (torch.randn(R, B, s, s, generator=g) * 0.3).cuda().requires_grad_(True)
+    Wb = (torch.randn(R, B, s, s, generator=g) * 0.3).cuda().requires_grad_(True)
+    Ws = (torch.randn(d, d, generator=g) * 0.05).cuda().requires_grad_(True)
+    Hc = H.cuda().requires_grad_(True)
+    graph = ops.Graph(tr, V, R, device=0)
+    out = ops.block_layer(Hc, Wf, Wb, Ws, graph, B, None, 1.0, True)
+    out.backward(dOut.cuda())
+
+    def rel(a, b):
+        return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+    for rank in range(world):
+        z = np.load(tmp_path / ("r%d.npz" % rank))
+        lo, hi = int(z["lo"]), int(z["hi"])
+        assert rel(z["out"], out.detach().cpu().numpy()[lo:hi]) < 1e-5
+        assert rel(z["dH"], Hc.grad.cpu().numpy()[lo:hi]) < 1e-5
+        assert rel(z["dWf"], Wf.grad.cpu().numpy()) < 1e-5
+        assert rel(z["dWb"], Wb.grad.cpu().numpy()) < 1e-5
+        assert rel(z["dWs"], Ws.grad.cpu().numpy()) < 1e-5
