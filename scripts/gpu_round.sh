@@ -1,8 +1,11 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_gemm.py -q -m gpu -x > gpurun_out/pytest_gemm.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gemm.log
-tail -30 gpurun_out/pytest_gemm.log
-timeout 300 python scripts/gemm_perf.py > gpurun_out/gemm_perf.txt 2>&1; cat gpurun_out/gemm_perf.txt
-timeout 1500 python -m pytest tests -q -m gpu -x --deselect tests/test_gpu_gemm.py > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -15 gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py > gpurun_out/bench_fb.json 2> gpurun_out/bench_fb.err; echo "bench rc=$?"
+tail -3 gpurun_out/bench_fb.err; python scripts/show_bench.py gpurun_out/bench_fb.json
+timeout 600 python bench.py --workload synthetic --scale 0.02 --no-cpu-baseline --steps 5 > gpurun_out/bench_syn.json 2> gpurun_out/bench_syn.err; echo "bench syn rc=$?"
+tail -3 gpurun_out/bench_syn.err; python scripts/show_bench.py gpurun_out/bench_syn.json
+timeout 600 python bench.py --workload synthetic --scale 0.1 --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/bench_syn01.json 2> gpurun_out/bench_syn01.err; echo "bench syn rc=$?"
+tail -3 gpurun_out/bench_syn01.err; python scripts/show_bench.py gpurun_out/bench_syn01.json
