@@ -340,7 +340,8 @@ extern "C" int rgcn_block_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
     rc = launch_mask_relu(out, drop_mask, 1.0f / keep, 0, (int64_t)g->V_dst * d, st);
     if (rc) return rc;
     rc = launch_block_rel(g->by_rel.d_items, (int)g->by_rel.n_items, g->by_rel.d_row,
-                          g->by_rel.d_nbr, g->by_rel.d_norm, H, d, d, s, Wt, out, st);
+                          g->by_rel.d_nbr, g->by_rel.d_norm, H, d, d, s, Wt, out, nullptr, 0, nullptr,
+                          st);
     if (rc) return rc;
     MARK("block_agg_fwd");
     rc = launch_mask_relu(out, nullptr, 1.f, relu, (int64_t)g->V_dst * d, st);
@@ -423,10 +424,16 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
         "memset(scratch)");
     if (rc) return rc;
   }
-  if (use_rel_major(d, s)) {
-    rc = launch_block_rel(g->by_rel_src.d_items, (int)g->by_rel_src.n_items,
-                          g->by_rel_src.d_row, g->by_rel_src.d_nbr, g->by_rel_src.d_norm, G, d, d, s,
-                          Wtt, dH, st);
+  // dW accumulates in the j-major layout (zeroed first); when the block size allows, the dH pass
+  // produces it in the same walk (one round of gathers for the whole backward of the messages)
+  rc = rgcn_check_cuda(cudaMemsetAsync(dWt, 0, wt * sizeof(float), st), "memset(dWt)");
+  if (rc) return rc;
+  const bool rel = use_rel_major(d, s);
+  const bool fused = rel && block_rel_fuse_dw_supported(d, s) && !std::getenv("RGCN_NO_FUSE_DW");
+  if (rel) {
+    rc = launch_block_rel(g->by_rel_src.d_items, (int)g->by_rel_src.n_items, g->by_rel_src.d_row,
+                          g->by_rel_src.d_nbr, g->by_rel_src.d_norm, G, d, d, s, Wtt, dH,
+                          fused ? H : nullptr, d, fused ? dWt : nullptr, st);
   } else {
     AggLaunch a = make_agg(g->by_src, G, d, d, scratch, counters);
     rc = launch_block_agg(a, s, Wtt, dH, nullptr, 1.f, 0, st);
@@ -434,11 +441,11 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   if (rc) return rc;
   MARK("block_agg_dH");
   // dW[w] = sum_{m: relw_m = w} norm_m G[dst_m] (x)_block H[src_m]
-  rc = rgcn_check_cuda(cudaMemsetAsync(dWt, 0, wt * sizeof(float), st), "memset(dWt)");
-  if (rc) return rc;
-  rc = launch_block_dw(g->by_rel.d_items, (int)g->by_rel.n_items, g->by_rel.d_row,
-                       g->by_rel.d_nbr, g->by_rel.d_norm, H, d, G, d, d, s, dWt, st);
-  if (rc) return rc;
+  if (!fused) {
+    rc = launch_block_dw(g->by_rel.d_items, (int)g->by_rel.n_items, g->by_rel.d_row,
+                         g->by_rel.d_nbr, g->by_rel.d_norm, H, d, G, d, d, s, dWt, st);
+    if (rc) return rc;
+  }
   MARK("block_dW");
   rc = launch_block_unlayout(dWt, R, B, s, dWf, dWb, st);
   MARK("block_unlayout");

@@ -5,7 +5,7 @@
 // Used for the self-loop terms of the R-GCN layer (H @ W_self, dS @ W_self^T; reference:
 // gcn_basis.py:70-71 / gcn_basis_concat.py:65-66 `tf.matmul`).  The 1e-4 parity bar rules out a
 // single TF32 pass (10-bit mantissa), so every fp32 operand is split a = a_hi + a_lo with a_hi
-// exactly representable in TF32 (low 13 mantissa bits cleared) and three MMAs are issued per
+// exactly representable in TF32 (round-to-nearest, cvt.rna.tf32.f32) and three MMAs are issued per
 // K-step:  a_hi*b_hi + a_hi*b_lo + a_lo*b_hi   (the a_lo*b_lo term is below fp32 rounding).
 //
 // Structure (one CTA per 128x128 output tile, 160 threads, 1 CTA/SM):
@@ -29,7 +29,12 @@ constexpr int TILE_BYTES = BM * BK * 4;     // 16 KB (A_hi, A_lo, B_hi, B_lo eac
 constexpr int STAGE_BYTES = 4 * TILE_BYTES; // 64 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
 constexpr int N_PRODUCERS = 128;
-constexpr int TMEM_COLS = 128;
+// Four accumulators in TMEM (4 x 128 columns): the big hi*hi products and the small cross terms are
+// accumulated separately, each alternating between two accumulators per K block, and summed in fp32
+// registers in the epilogue.  The tensor core adds into its accumulator with truncation, so fewer,
+// same-magnitude additions per accumulator keep the result at SGEMM-level accuracy.
+constexpr int N_ACC = 4;
+constexpr int TMEM_COLS = N_ACC * BN;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -85,6 +90,16 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
                : "memory");
+}
+
+// a = hi + lo with hi = RN_tf32(a) and lo = RN_tf32(a - hi): both exactly representable in TF32, so
+// the tensor core's own fp32->tf32 conversion is exact and the split error is <= 2^-22 |a|, unbiased.
+__device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(a));
+  hi = __uint_as_float(h);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(a - hi));
+  lo = __uint_as_float(l);
 }
 
 __device__ __forceinline__ uint32_t swz(int r, int c) {  // byte offset of 16 B chunk c of tile row r
@@ -159,14 +174,10 @@ __global__ void __launch_bounds__(160, 1)
       for (int i = 0; i < BM / 16; ++i) {
         const int r = rbase + 16 * i;
         float4 hi, lo;
-        hi.x = __uint_as_float(__float_as_uint(v[i].x) & 0xffffe000u);
-        hi.y = __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u);
-        hi.z = __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u);
-        hi.w = __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u);
-        lo.x = v[i].x - hi.x;
-        lo.y = v[i].y - hi.y;
-        lo.z = v[i].z - hi.z;
-        lo.w = v[i].w - hi.w;
+        split_tf32(v[i].x, hi.x, lo.x);
+        split_tf32(v[i].y, hi.y, lo.y);
+        split_tf32(v[i].z, hi.z, lo.z);
+        split_tf32(v[i].w, hi.w, lo.w);
         const uint32_t o = swz(r, c);
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + o), "f"(hi.x), "f"(hi.y),
                      "f"(hi.z), "f"(hi.w)
@@ -184,20 +195,32 @@ __global__ void __launch_bounds__(160, 1)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int row = m0 + warp * 32 + lane;  // TMEM lane == accumulator row
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int n_pair = num_kb > 1 ? 2 : 1;  // accumulators actually written: {0,2} or {0,1,2,3}
 #pragma unroll
     for (int cb = 0; cb < BN; cb += 32) {
       uint32_t r[32];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-            "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-            "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
-            "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
-            "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr + (uint32_t)cb));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float sum[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) sum[q] = 0.f;
+      // small (cross-term) accumulators first, then the big ones
+      for (int a = N_ACC - 1; a >= 0; --a) {
+        if ((a & 1) >= n_pair) continue;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+              "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+              "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+              "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+              "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr + (uint32_t)(a * BN + cb)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 32; ++q) sum[q] += __uint_as_float(r[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 32; ++q) r[q] = __float_as_uint(sum[q]);
       if (row < M) {
         float* crow = C + (size_t)row * ldc + n0 + cb;
 #pragma unroll
@@ -233,9 +256,12 @@ __global__ void __launch_bounds__(160, 1)
         for (int kk = 0; kk < BK / 8; ++kk) {  // UMMA K = 8 tf32 = 32 bytes along the swizzled row
           const uint64_t dah = make_desc(a_hi + kk * 32), dal = make_desc(a_lo + kk * 32);
           const uint64_t dbh = make_desc(b_hi + kk * 32), dbl = make_desc(b_lo + kk * 32);
-          umma_tf32(tmem_base, dal, dbh, (kb | kk) != 0);  // small terms first
-          umma_tf32(tmem_base, dah, dbl, 1);
-          umma_tf32(tmem_base, dah, dbh, 1);
+          const uint32_t acc_big = tmem_base + (uint32_t)((kb & 1) * BN);
+          const uint32_t acc_small = tmem_base + (uint32_t)((2 + (kb & 1)) * BN);
+          const uint32_t first = (kb < 2 && kk == 0) ? 0u : 1u;  // first touch overwrites
+          umma_tf32(acc_small, dal, dbh, first);
+          umma_tf32(acc_small, dah, dbl, 1);
+          umma_tf32(acc_big, dah, dbh, first);
         }
         umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs have read it
       }
@@ -261,9 +287,10 @@ __global__ void k_split_b(const float* __restrict__ B, int64_t ldb, int N, int K
        i += (int64_t)gridDim.x * blockDim.x) {
     const int n = (int)(i / K), k = (int)(i % K);
     const float v = transposed ? __ldg(B + (size_t)k * ldb + n) : __ldg(B + (size_t)n * ldb + k);
-    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    float h, l;
+    split_tf32(v, h, l);
     hi[i] = h;
-    lo[i] = v - h;
+    lo[i] = l;
   }
 }
 

@@ -33,9 +33,12 @@ int launch_block_agg(const AggLaunch& a, int s, const float* Wt, float* out, con
 // Weight-id major variant of the above (weights in registers, vector reductions into `out`, which
 // must already hold the self-loop term).  Supported block sizes: block_rel_supported().
 bool block_rel_supported(int d, int s);
+bool block_rel_fuse_dw_supported(int d, int s);
+// dWt != nullptr (backward pass, X = G, rows = sources, Hrow = layer input): additionally accumulates
+// the block weight gradient in the j-major layout (dWt zeroed by the caller) in the same walk.
 int launch_block_rel(const WorkItem* items, int n_items, const int32_t* r_row, const int32_t* r_nbr,
                      const float* r_norm, const float* X, int ldx, int d, int s, const float* Wt,
-                     float* out, cudaStream_t st);
+                     float* out, const float* Hrow, int ldh, float* dWt, cudaStream_t st);
 
 // Block-diagonal weight gradient, weight-id major:
 //   dWt[w][j][b*s+i] += sum_{m: relw_m = w} norm_m * G[dst_m, b*s+i] * H[src_m, b*s+j]

@@ -374,24 +374,30 @@ __global__ void __launch_bounds__(RGCN_THREADS, 1)
 // by L2-sized supertiles of rows, graph.cu).  Weight traffic drops from d*s*4 bytes per run to
 // d*s*4 bytes per item; the price is a non-deterministic fp32 summation order across items.
 // ------------------------------------------------------------------------------------------------
-template <int S, int NV>
+template <int S, int NV, bool FUSE_DW>
 __global__ void __launch_bounds__(RGCN_THREADS, 1)
     k_block_rel(const WorkItem* __restrict__ items, int n_items, const int32_t* __restrict__ r_row,
                 const int32_t* __restrict__ r_nbr, const float* __restrict__ r_norm,
                 const float* __restrict__ X, int ldx, int d, const float* __restrict__ Wt,
-                float* __restrict__ out) {
+                float* __restrict__ out, const float* __restrict__ Hrow, int ldh,
+                float* __restrict__ dWt) {
+  // FUSE_DW (backward pass only: X = G, rows = sources): the same walk also produces the block
+  // weight gradient  dWt[w][j][col] += (sum_run norm*G[dst])[col] * H[row][block(col)+j],
+  // so the separate dW pass (and its second round of gathers) disappears.
   static_assert(S > 0, "rel-major kernel needs a compile-time block size");
-  __shared__ __align__(16) float xbuf_all[RGCN_WARPS_PER_BLOCK][NV * 128];
+  __shared__ __align__(16) float xbuf_all[RGCN_WARPS_PER_BLOCK][(FUSE_DW ? 2 : 1) * NV * 128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * RGCN_WARPS_PER_BLOCK + warp;
   if (item >= n_items) return;
   const int c0 = blockIdx.y * (NV * 128);
   float* xbuf = xbuf_all[warp];
+  float* hbuf = xbuf + NV * 128;
   const int4 itv = __ldg(reinterpret_cast<const int4*>(items) + item);
   const int beg = itv.x, end = itv.y, w = itv.z;
 
   // weights of this (weight id, slab) -> registers; x offsets of the lane's outputs -> registers
   float4 wreg[S][NV];
+  float4 acc[FUSE_DW ? S : 1][NV];
   int xo[NV][4];
   const float* wr = Wt + (size_t)w * S * d;
 #pragma unroll
@@ -400,12 +406,14 @@ __global__ void __launch_bounds__(RGCN_THREADS, 1)
 #pragma unroll
     for (int j = 0; j < S; ++j) wreg[j][k] = (col < d) ? ldg4(wr + (size_t)j * d + col) : zero4();
 #pragma unroll
+    for (int j = 0; j < (FUSE_DW ? S : 1); ++j) acc[j][k] = zero4();
+#pragma unroll
     for (int c = 0; c < 4; ++c) xo[k][c] = ((col + c) / S) * S - c0;
   }
 
-  float4 xs[NV];
+  float4 xs[NV], hcur[NV];
 #pragma unroll
-  for (int k = 0; k < NV; ++k) xs[k] = zero4();
+  for (int k = 0; k < NV; ++k) xs[k] = hcur[k] = zero4();
   int cur = -1;
 
   auto flush = [&](int row) {
@@ -413,7 +421,10 @@ __global__ void __launch_bounds__(RGCN_THREADS, 1)
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int lc = 4 * (lane + 32 * k);
-      if (c0 + lc < d) *reinterpret_cast<float4*>(xbuf + lc) = xs[k];
+      if (c0 + lc < d) {
+        *reinterpret_cast<float4*>(xbuf + lc) = xs[k];
+        if (FUSE_DW) *reinterpret_cast<float4*>(hbuf + lc) = hcur[k];
+      }
     }
     __syncwarp();
     float* po = out + (size_t)row * d + c0;
@@ -425,13 +436,20 @@ __global__ void __launch_bounds__(RGCN_THREADS, 1)
 #pragma unroll
         for (int j = 0; j < S; ++j) {
           if (S % 4 == 0) {
-            const float x = xbuf[xo[k][0] + j];
-            fma4(y, x, wreg[j][k]);
+            fma4(y, xbuf[xo[k][0] + j], wreg[j][k]);
+            if (FUSE_DW) fma4(acc[FUSE_DW ? j : 0][k], hbuf[xo[k][0] + j], xs[k]);
           } else {
             y.x = fmaf(wreg[j][k].x, xbuf[xo[k][0] + j], y.x);
             y.y = fmaf(wreg[j][k].y, xbuf[xo[k][1] + j], y.y);
             y.z = fmaf(wreg[j][k].z, xbuf[xo[k][2] + j], y.z);
             y.w = fmaf(wreg[j][k].w, xbuf[xo[k][3] + j], y.w);
+            if (FUSE_DW) {
+              float4& a = acc[FUSE_DW ? j : 0][k];
+              a.x = fmaf(xs[k].x, hbuf[xo[k][0] + j], a.x);
+              a.y = fmaf(xs[k].y, hbuf[xo[k][1] + j], a.y);
+              a.z = fmaf(xs[k].z, hbuf[xo[k][2] + j], a.z);
+              a.w = fmaf(xs[k].w, hbuf[xo[k][3] + j], a.w);
+            }
           }
         }
         red4(po + lc, y);
@@ -450,30 +468,40 @@ __global__ void __launch_bounds__(RGCN_THREADS, 1)
       my_nm = __ldg(r_norm + base + lane);
     }
     for (int t = 0; t < n; t += U) {
-      float4 x[U][NV];
+      float4 x[U][NV], hx[FUSE_DW ? U : 1][NV];
       int rv[U];
       float nm[U];
+      bool starts[U];
+      int prev = cur;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int tt = min(t + u, n - 1);
         const int src = __shfl_sync(FULL, my_nbr, tt);
         rv[u] = __shfl_sync(FULL, my_row, tt);
         nm[u] = __shfl_sync(FULL, my_nm, tt);
+        starts[u] = (t + u < n) && (rv[u] != prev);  // warp-uniform
+        prev = rv[u];
         const float* xr = X + (size_t)src * ldx + c0;
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
           const int lc = 4 * (lane + 32 * k);
-          x[u][k] = (c0 + lc < d) ? ldg4(xr + lc) : zero4();
+          const bool ok = c0 + lc < d;
+          x[u][k] = ok ? ldg4(xr + lc) : zero4();
+          if (FUSE_DW)  // the run's own H row travels with the run's first gathered row
+            hx[FUSE_DW ? u : 0][k] = (ok && starts[u]) ? ldg4(Hrow + (size_t)rv[u] * ldh + c0 + lc) : zero4();
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (t + u < n) {
-          if (rv[u] != cur) {
+          if (starts[u]) {
             if (cur >= 0) flush(cur);
             cur = rv[u];
 #pragma unroll
-            for (int k = 0; k < NV; ++k) xs[k] = zero4();
+            for (int k = 0; k < NV; ++k) {
+              xs[k] = zero4();
+              if (FUSE_DW) hcur[k] = hx[FUSE_DW ? u : 0][k];
+            }
           }
 #pragma unroll
           for (int k = 0; k < NV; ++k) fma4(xs[k], nm[u], x[u][k]);
@@ -482,6 +510,17 @@ __global__ void __launch_bounds__(RGCN_THREADS, 1)
     }
   }
   if (cur >= 0) flush(cur);
+  if (FUSE_DW) {
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      float* pw = dWt + ((size_t)w * S + j) * d + c0;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int lc = 4 * (lane + 32 * k);
+        if (c0 + lc < d) red4(pw + lc, acc[FUSE_DW ? j : 0][k]);
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -917,14 +956,15 @@ int launch_block_dw(const WorkItem* items, int n_items, const int32_t* r_dst, co
 }
 
 
-template <int S, int NV>
+template <int S, int NV, bool FUSE>
 static int launch_block_rel_t(const WorkItem* items, int n_items, const int32_t* r_row,
                               const int32_t* r_nbr, const float* r_norm, const float* X, int ldx,
-                              int d, const float* Wt, float* out, cudaStream_t st) {
+                              int d, const float* Wt, float* out, const float* Hrow, int ldh,
+                              float* dWt, cudaStream_t st) {
   const int slabs = (d + NV * 128 - 1) / (NV * 128);
   dim3 grid((n_items + RGCN_WARPS_PER_BLOCK - 1) / RGCN_WARPS_PER_BLOCK, slabs);
-  k_block_rel<S, NV><<<grid, RGCN_THREADS, 0, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d,
-                                                     Wt, out);
+  k_block_rel<S, NV, FUSE><<<grid, RGCN_THREADS, 0, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx,
+                                                           d, Wt, out, Hrow, ldh, dWt);
   return check_launch("k_block_rel");
 }
 
@@ -934,15 +974,28 @@ bool block_rel_supported(int d, int s) {
   return false;
 }
 
+// the dW-fused variant keeps 2*s*NV float4 of weights + gradient accumulators in registers
+bool block_rel_fuse_dw_supported(int d, int s) { return s == 4 || s == 8 || s == 16; }
+
 int launch_block_rel(const WorkItem* items, int n_items, const int32_t* r_row, const int32_t* r_nbr,
                      const float* r_norm, const float* X, int ldx, int d, int s, const float* Wt,
-                     float* out, cudaStream_t st) {
+                     float* out, const float* Hrow, int ldh, float* dWt, cudaStream_t st) {
   if (n_items == 0) return RGCN_OK;
-#define RL(S_, NV_) \
-  return launch_block_rel_t<S_, NV_>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, st)
+  const bool fuse = dWt != nullptr;
+  if (fuse && !block_rel_fuse_dw_supported(d, s)) {
+    rgcn_set_error("rel-major block kernel: dW fusion unsupported for this block size");
+    return RGCN_ERR_INVALID;
+  }
+#define RL(S_, NV_)                                                                                  \
+  return fuse ? launch_block_rel_t<S_, NV_, true>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, \
+                                                  out, Hrow, ldh, dWt, st)                             \
+              : launch_block_rel_t<S_, NV_, false>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d,   \
+                                                   Wt, out, Hrow, ldh, dWt, st)
+#define RLN(S_, NV_) \
+  return launch_block_rel_t<S_, NV_, false>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt, st)
   const int nv = pick_nv(d);
   if (s == 5) {
-    switch (nv) { case 1: RL(5, 1); case 2: RL(5, 2); case 3: RL(5, 3); default: RL(5, 4); }
+    switch (nv) { case 1: RLN(5, 1); case 2: RLN(5, 2); case 3: RLN(5, 3); default: RLN(5, 4); }
   } else if (s == 4) {
     switch (nv) { case 1: RL(4, 1); case 2: RL(4, 2); case 3: RL(4, 3); default: RL(4, 4); }
   } else if (s == 8) {
@@ -952,6 +1005,7 @@ int launch_block_rel(const WorkItem* items, int n_items, const int32_t* r_row, c
     RL(16, 1);
   }
 #undef RL
+#undef RLN
   rgcn_set_error("rel-major block kernel: unsupported block size");
   return RGCN_ERR_INVALID;
 }
