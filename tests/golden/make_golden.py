@@ -111,3 +111,42 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def make_eval_golden():
+    """Ranking golden from the REFERENCE's own numpy-only evaluation.py (importable): a fake model with
+    tied scores, raw + filtered MRR / Hits@n over both corruption directions."""
+    from common import evaluation as ref_eval
+    rng = np.random.RandomState(0)
+    V = 50
+    train = np.stack([rng.randint(0, V, 300), rng.randint(0, 4, 300), rng.randint(0, V, 300)], 1)
+    T = np.round(rng.rand(4, V, V).astype(np.float32), 2)
+
+    class FakeModel:
+        def score_all_subjects(self, tr):
+            return np.stack([T[r, :, o] for s, r, o in tr])
+
+        def score_all_objects(self, tr):
+            return np.stack([T[r, s, :] for s, r, o in tr])
+    sc = ref_eval.Scorer({'Metric': 'MRR'})
+    sc.register_data(train)
+    sc.register_degrees(train)
+    sc.register_model(FakeModel())
+    sc.finalize_frequency_computation(train)
+    summ = sc.compute_scores(train[:40]).get_summary()
+    res = {k: {m: float(v) for m, v in summ.results[k].items() if m in ('MRR', 'H@1', 'H@3', 'H@10')}
+           for k in ('Raw', 'Filtered')}
+    np.savez_compressed(os.path.join(HERE, "eval_golden.npz"), train=train, T=T,
+                        raw=np.array([res['Raw'][m] for m in ('MRR', 'H@1', 'H@3', 'H@10')]),
+                        filtered=np.array([res['Filtered'][m] for m in ('MRR', 'H@1', 'H@3', 'H@10')]))
+    # negative sampler golden (reference auxilliaries.NegativeSampler, numpy-only, seeded)
+    from common import auxilliaries as ref_aux
+    np.random.seed(123)
+    ns = ref_aux.NegativeSampler(3, V)
+    idx, lab = ns.transform(train[:20])
+    np.savez_compressed(os.path.join(HERE, "negsample_golden.npz"), batch=train[:20], idx=idx, labels=lab)
+
+
+if __name__ == "__main__":
+    make_eval_golden()
+    print("wrote eval_golden.npz, negsample_golden.npz")
