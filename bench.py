@@ -378,8 +378,13 @@ def main():
             top = max(mine, key=mine.get)
             peak, peak_src = peaks()
             achieved = alg[top] / (mine[top] * 1e-3) / 1e9
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+            if os.path.exists(tp):
+                with open(tp) as fh:
+                    traffic = json.load(fh).get(args.workload, {}).get(top)
             roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": None, "algorithmic_bytes": int(alg[top]),
+                        "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": int(alg[top]),
                         "kernel_ms": mine[top], "peak_source": peak_src,
                         "note": "algorithmic bytes count every row gather as HBM bytes; with H resident in "
                                 "the 126 MB L2 (H = %.0f MB here) frac can exceed 1" % (V * d * 4 / 1e6),

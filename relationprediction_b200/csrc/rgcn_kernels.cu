@@ -17,6 +17,9 @@
 // (gcn_basis_concat.py:38-39) is never materialised.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 int64_t g_rgcn_launches = 0;
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(RGCN_THREADS, 1)
 // d*s*4 bytes per item; the price is a non-deterministic fp32 summation order across items.
 // ------------------------------------------------------------------------------------------------
 template <int S, int NV, bool FUSE_DW>
-__global__ void __launch_bounds__(RGCN_THREADS, 1)
+__global__ void __launch_bounds__(RGCN_THREADS, FUSE_DW ? 1 : (S * NV > 8 ? 2 : 3))
     k_block_rel(const WorkItem* __restrict__ items, int n_items, const int32_t* __restrict__ r_row,
                 const int32_t* __restrict__ r_nbr, const float* __restrict__ r_norm,
                 const float* __restrict__ X, int ldx, int d, const float* __restrict__ Wt,
@@ -457,7 +460,9 @@ __global__ void __launch_bounds__(RGCN_THREADS, 1)
     }
   };
 
-  constexpr int U = 2;
+  // heavy register configurations (s*NV > 16 float4 of weights) keep one row in flight per lane so that
+  // two blocks (16 warps) fit an SM: more warps hide the transform phases better than deeper unrolling
+  constexpr int U = (S * NV > 16) ? 1 : 2;
   for (int base = beg; base < end; base += 32) {
     const int n = min(32, end - base);
     int my_row = 0, my_nbr = 0;
@@ -993,7 +998,14 @@ int launch_block_rel(const WorkItem* items, int n_items, const int32_t* r_row, c
                                                    Wt, out, Hrow, ldh, dWt, st)
 #define RLN(S_, NV_) \
   return launch_block_rel_t<S_, NV_, false>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt, st)
-  const int nv = pick_nv(d);
+  int nv = pick_nv(d);
+  // the dW-fused variant doubles the per-lane register state: one quad per lane (4 column slabs at
+  // d = 512) keeps two blocks per SM resident and measured fastest (11.4 vs 12.6 ms/step, synthetic)
+  if (fuse && s != 5) nv = 1;
+  if (const char* e = std::getenv("RGCN_REL_NV")) {  // tuning knob: quads per lane (column slabs = d/(128 nv))
+    const int v = std::atoi(e);
+    if (v >= 1 && v <= 4 && s != 5 && (v * 128) % s == 0) nv = std::min(nv, v);
+  }
   if (s == 5) {
     switch (nv) { case 1: RLN(5, 1); case 2: RLN(5, 2); case 3: RLN(5, 3); default: RLN(5, 4); }
   } else if (s == 4) {
