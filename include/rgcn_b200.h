@@ -63,6 +63,13 @@ int rgcn_gemm_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, i
                      int64_t ldc, int32_t M, int32_t N, int32_t K, int accumulate, void* workspace,
                      int64_t workspace_bytes, void* stream);
 
+/* C[M,N] = (accumulate ? C : 0) + A^T B with A [K,M], B [K,N] row-major (the V-long reductions of
+ * the backward pass: dW_self = H^T dS).  Same tensor-core path, both operands MN-major, split-K with
+ * vector reductions into C (fp32 summation order across splits not reproducible run to run).
+ * M, N and the leading dimensions must be multiples of 4. */
+int rgcn_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                        int32_t M, int32_t N, int32_t K, int accumulate, void* stream);
+
 /* Optional per-kernel timing (bench.py roofline): when enabled, every layer entry point records a
  * CUDA event on its stream after each internal stage.  rgcn_profile_read() synchronises, writes
  * the stage durations (ms) and their '\n'-separated names, clears the log and returns the count. */

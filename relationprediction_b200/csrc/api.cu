@@ -93,6 +93,13 @@ int gemm_any(cublasHandle_t h, float* split_ws, bool ta, bool tb, int64_t m, int
   const bool ok = mode == 2 && !ta && alpha == 1.f && (beta == 0.f || beta == 1.f) && k > 0 && m > 0 &&
                   k % 4 == 0 && n % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 && split_ws &&
                   m < 0x7fffffffLL;
+  if (mode == 2 && ta && !tb && alpha == 1.f && (beta == 0.f || beta == 1.f) && m % 4 == 0 &&
+      n % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 && k < 0x7fffffffLL &&
+      !std::getenv("RGCN_NO_TN_GEMM")) {
+    cudaStream_t st;
+    cublasGetStream(h, &st);
+    return launch_gemm_tn_tf32x3(A, lda, B, ldb, C, ldc, (int)m, (int)n, (int)k, beta != 0.f, st);
+  }
   if (!ok) return gemm_rm(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
   cudaStream_t st;
   cublasGetStream(h, &st);
@@ -228,6 +235,16 @@ extern "C" int rgcn_gemm_tf32x3(const float* A, int64_t lda, const float* B, int
   int rc = launch_gemm_split_b(B, ldb, N, K, b_is_nk ? 0 : 1, hi, lo, st);
   if (rc) return rc;
   return launch_gemm_tf32x3(A, lda, hi, lo, K, C, ldc, M, N, K, accumulate, st);
+}
+
+extern "C" int rgcn_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                                   int64_t ldc, int32_t M, int32_t N, int32_t K, int accumulate,
+                                   void* stream) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K < 0) {
+    rgcn_set_error("rgcn_gemm_tn_tf32x3: bad arguments");
+    return RGCN_ERR_INVALID;
+  }
+  return launch_gemm_tn_tf32x3(A, lda, B, ldb, C, ldc, M, N, K, accumulate, (cudaStream_t)stream);
 }
 
 extern "C" int64_t rgcn_launch_count(void) { return g_rgcn_launches; }

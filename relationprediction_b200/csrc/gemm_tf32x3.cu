@@ -278,6 +278,194 @@ __global__ void __launch_bounds__(160, 1)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// C[M,N] += A^T B with A [K,M] and B [K,N] row-major: the V-long reductions of the backward pass
+// (dW_self = H^T dS, basis dV = Agg^T G).  Both operands are "MN-major" for the tensor core (the
+// contraction index is the slow one in memory).  For 32-bit MN-major operands the only shared-memory
+// layout the tensor core accepts is SWIZZLE_128B_BASE32B (cutlass sm100_common.inl:92): a 128-byte row
+// holds 32 consecutive M (or N) values of one k, FOUR k-rows form a 512-byte atom in which the 32-byte
+// chunk index is XORed with (k & 3) (Swizzle<2,5,2> on byte addresses); SBO = 512 B between k-atoms
+// (two per K = 8 MMA step), LBO = 4 KB between 32-wide MN blocks.  Both operands are split hi/lo in
+// registers by the producers.  Split-K over gridDim.z; partial tiles are added with red.global.add.v4.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t IDESC_TN = IDESC | (1u << 15) | (1u << 16);  // a_major = b_major = MN
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(4096 >> 4) << 16) |
+         ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);  // layout type 1 = SWIZZLE_128B_BASE32B
+}
+__device__ __forceinline__ void umma_tf32_tn(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(IDESC_TN), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(160, 1)
+    k_gemm_tn_tf32x3(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
+                     float* __restrict__ C, int64_t ldc, int M, int N, int K, int kb_per_split) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_smem;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int kb_total = (K + BK - 1) / BK;
+  const int kb_begin = blockIdx.z * kb_per_split;
+  const int num_kb = min(kb_per_split, kb_total - kb_begin);
+  if (num_kb <= 0) return;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], N_PRODUCERS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_smem)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp < 4) {
+    // producers: chunk id = tid + 128 i -> tile row kr = id / 32 (0..31), 16 B chunk cm = id % 32 of the
+    // 512-byte (128 floats) MN extent
+    for (int kbi = 0; kbi < num_kb; ++kbi) {
+      const int s = kbi % STAGES;
+      const uint32_t ph = (uint32_t)(kbi / STAGES) & 1u;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES;
+      const uint32_t b_hi = a_lo + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
+      const int k0 = (kb_begin + kbi) * BK;
+      float4 va[8], vb[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int id = tid + 128 * i;
+        const int kr = id >> 5, cm = id & 31;
+        const int krow = k0 + kr;
+        const bool kok = krow < K;
+        va[i] = (kok && (m0 + 4 * cm < M))
+                    ? __ldg(reinterpret_cast<const float4*>(A + (size_t)krow * lda + m0 + 4 * cm))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[i] = (kok && (n0 + 4 * cm < N))
+                    ? __ldg(reinterpret_cast<const float4*>(B + (size_t)krow * ldb + n0 + 4 * cm))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int id = tid + 128 * i;
+        const int kr = id >> 5, cm = id & 31;
+        const int c8 = cm & 7;  // 16 B chunk within the 128 B row: 32 B chunk (c8 >> 1) is swizzled with k & 3
+        const uint32_t off = (uint32_t)((cm >> 3) * 4096 + (kr >> 2) * 512 + (kr & 3) * 128 +
+                                        ((((c8 >> 1) ^ (kr & 3)) << 5) | ((c8 & 1) << 4)));
+        float4 hi, lo;
+        split_tf32(va[i].x, hi.x, lo.x);
+        split_tf32(va[i].y, hi.y, lo.y);
+        split_tf32(va[i].z, hi.z, lo.z);
+        split_tf32(va[i].w, hi.w, lo.w);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "f"(hi.x), "f"(hi.y),
+                     "f"(hi.z), "f"(hi.w) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "f"(lo.x), "f"(lo.y),
+                     "f"(lo.z), "f"(lo.w) : "memory");
+        split_tf32(vb[i].x, hi.x, lo.x);
+        split_tf32(vb[i].y, hi.y, lo.y);
+        split_tf32(vb[i].z, hi.z, lo.z);
+        split_tf32(vb[i].w, hi.w, lo.w);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(b_hi + off), "f"(hi.x), "f"(hi.y),
+                     "f"(hi.z), "f"(hi.w) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(b_lo + off), "f"(lo.x), "f"(lo.y),
+                     "f"(lo.z), "f"(lo.w) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&full_bar[s]);
+    }
+    // epilogue: add this split's tile into C
+    mbar_wait(&accum_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m0 + warp * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int n_pair = num_kb > 1 ? 2 : 1;
+#pragma unroll
+    for (int cb = 0; cb < BN; cb += 32) {
+      uint32_t r[32];
+      float sum[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) sum[q] = 0.f;
+      for (int a = N_ACC - 1; a >= 0; --a) {
+        if ((a & 1) >= n_pair) continue;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+              "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+              "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+              "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+              "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr + (uint32_t)(a * BN + cb)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 32; ++q) sum[q] += __uint_as_float(r[q]);
+      }
+      if (row < M) {
+        float* crow = C + (size_t)row * ldc + n0 + cb;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (n0 + cb + 4 * q < N)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + 4 * q),
+                         "f"(sum[4 * q]), "f"(sum[4 * q + 1]), "f"(sum[4 * q + 2]), "f"(sum[4 * q + 3])
+                         : "memory");
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else {
+    if (lane == 0) {
+      for (int kbi = 0; kbi < num_kb; ++kbi) {
+        const int s = kbi % STAGES;
+        const uint32_t ph = (uint32_t)(kbi / STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES;
+        const uint32_t b_hi = a_lo + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BK / 8; ++kk) {  // two 512 B k-atoms (8 k-rows) per MMA K-step
+          const uint64_t dah = make_desc_mn(a_hi + kk * 1024), dal = make_desc_mn(a_lo + kk * 1024);
+          const uint64_t dbh = make_desc_mn(b_hi + kk * 1024), dbl = make_desc_mn(b_lo + kk * 1024);
+          const uint32_t acc_big = tmem_base + (uint32_t)((kbi & 1) * BN);
+          const uint32_t acc_small = tmem_base + (uint32_t)((2 + (kbi & 1)) * BN);
+          const uint32_t first = (kbi < 2 && kk == 0) ? 0u : 1u;
+          umma_tf32_tn(acc_small, dal, dbh, first);
+          umma_tf32_tn(acc_small, dah, dbl, 1);
+          umma_tf32_tn(acc_big, dah, dbh, first);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&accum_bar);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "n"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
 // Bt_hi/Bt_lo[n][k] from B: transposed = 0: B is [N,K] row-major already (K-major);
 //                                  transposed = 1: B is [K,N] row-major -> transpose while splitting
 __global__ void k_split_b(const float* __restrict__ B, int64_t ldb, int N, int K, int transposed,
@@ -326,4 +514,39 @@ int launch_gemm_tf32x3(const float* A, int64_t lda, const float* Bt_hi, const fl
   k_gemm_tf32x3<<<grid, 160, SMEM_BYTES, st>>>(A, lda, Bt_hi, Bt_lo, ldb, C, ldc, M, N, K, accumulate);
   ++g_rgcn_launches;
   return rgcn_check_cuda(cudaGetLastError(), "k_gemm_tf32x3");
+}
+
+// C[M,N] (+)= A^T B, A [K,M] row-major, B [K,N] row-major (see k_gemm_tn_tf32x3)
+int launch_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                          int M, int N, int K, int accumulate, cudaStream_t st) {
+  if (M == 0 || N == 0) return RGCN_OK;
+  if (M % 4 != 0 || N % 4 != 0 || lda % 4 != 0 || ldb % 4 != 0 || ldc % 4 != 0) {
+    rgcn_set_error("gemm_tn_tf32x3: M, N and leading dimensions must be multiples of 4");
+    return RGCN_ERR_INVALID;
+  }
+  if (!accumulate) {
+    int rc = rgcn_check_cuda(cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st),
+                             "memset(C)");
+    if (rc) return rc;
+  }
+  if (K == 0) return RGCN_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = rgcn_check_cuda(cudaFuncSetAttribute(k_gemm_tn_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  SMEM_BYTES),
+                             "cudaFuncSetAttribute(gemm tn smem)");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  const int tm = (M + BM - 1) / BM, tn = (N + BN - 1) / BN;
+  const int kb_total = (K + BK - 1) / BK;
+  int splits = (2 * 148 + tm * tn - 1) / (tm * tn);  // about two waves of CTAs
+  if (splits > kb_total / 4) splits = kb_total / 4;  // at least 4 K blocks per split
+  if (splits < 1) splits = 1;
+  const int kb_per_split = (kb_total + splits - 1) / splits;
+  splits = (kb_total + kb_per_split - 1) / kb_per_split;
+  dim3 grid(tm, tn, splits);
+  k_gemm_tn_tf32x3<<<grid, 160, SMEM_BYTES, st>>>(A, lda, B, ldb, C, ldc, M, N, K, kb_per_split);
+  ++g_rgcn_launches;
+  return rgcn_check_cuda(cudaGetLastError(), "k_gemm_tn_tf32x3");
 }

@@ -83,6 +83,9 @@ int launch_gemm_split_b(const float* B, int64_t ldb, int N, int K, int transpose
 int launch_gemm_tf32x3(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, int64_t ldb,
                        float* C, int64_t ldc, int M, int N, int K, int accumulate, cudaStream_t st);
 
+int launch_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                          int M, int N, int K, int accumulate, cudaStream_t st);
+
 // DistMult
 int launch_distmult_forward(const float* codes, const float* rel, int d, const int32_t* X, int64_t N,
                             const float* Y, float* energies, float* loss_out, cudaStream_t st);

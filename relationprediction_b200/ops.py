@@ -309,3 +309,18 @@ def gemm_tf32x3(A, B, b_is_nk=False, out=None, accumulate=False):
                               _stream(A.device))
     _lib.check(rc, "rgcn_gemm_tf32x3")
     return out
+
+
+def gemm_tn_tf32x3(A, B, out=None, accumulate=False):
+    """C = A.T @ B with A [K,M], B [K,N] (contraction over the slow dimension), tcgen05 3xTF32, split-K."""
+    lib = _lib.load()
+    _check_cuda_f32("A", A)
+    _check_cuda_f32("B", B)
+    K, M = A.shape
+    N = B.shape[1]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    rc = lib.rgcn_gemm_tn_tf32x3(_ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(out), out.stride(0), M, N, K,
+                                 int(accumulate), _stream(A.device))
+    _lib.check(rc, "rgcn_gemm_tn_tf32x3")
+    return out

@@ -43,3 +43,18 @@ def test_gemm_tf32x3_is_tighter_than_single_tf32_and_handles_scales():
     Bm = torch.randn(500, 500, device="cuda", generator=g)
     lib_out = ops.gemm_tf32x3(Av.contiguous(), Bm)
     assert rel(lib_out, Av.double() @ Bm.double()) < 1e-5
+
+
+@pytest.mark.parametrize("K,M,N", [(128, 128, 128), (1000, 128, 128), (14541, 500, 500), (50000, 512, 512),
+                                   (33, 8, 8), (4097, 132, 36), (3000, 2500, 500), (100, 200, 24)])
+def test_gemm_tn_tf32x3_matches_float64(K, M, N):
+    g = torch.Generator(device="cuda").manual_seed(K + M)
+    A = torch.randn(K, M, device="cuda", generator=g)
+    B = torch.randn(K, N, device="cuda", generator=g)
+    ref = A.double().T @ B.double()
+    C = ops.gemm_tn_tf32x3(A, B)
+    assert torch.isfinite(C).all()
+    assert rel(C, ref) < 1e-5, rel(C, ref)
+    C0 = torch.randn(M, N, device="cuda", generator=g)
+    C1 = ops.gemm_tn_tf32x3(A, B, out=C0.clone(), accumulate=True)
+    assert rel(C1, ref + C0.double()) < 1e-5
