@@ -8,12 +8,12 @@
 // exactly representable in TF32 (round-to-nearest, cvt.rna.tf32.f32) and three MMAs are issued per
 // K-step:  a_hi*b_hi + a_hi*b_lo + a_lo*b_hi   (the a_lo*b_lo term is below fp32 rounding).
 //
-// Structure (one CTA per 128x128 output tile, 160 threads, 1 CTA/SM):
-//   warps 0-3  producers: global fp32 -> registers -> (hi, lo) -> st.shared in the UMMA canonical
+// Structure (one CTA per 128x128 output tile, 288 threads, 1 CTA/SM):
+//   warps 0-7  producers: global fp32 -> registers -> (hi, lo) -> st.shared in the UMMA canonical
 //              K-major SWIZZLE_128B layout for A; cp.async of the pre-split Bt_hi / Bt_lo tiles;
 //              fence.proxy.async + mbarrier arrive.  After the main loop they become the epilogue:
 //              tcgen05.ld of the accumulator rows -> global stores.
-//   warp 4     one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=128, K=8), 12 per
+//   warp 8     one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=128, K=8), 12 per
 //              32-wide K block, and frees smem stages / publishes the accumulator with tcgen05.commit.
 //   3-stage smem ring (64 KB per stage), accumulator 128 lanes x 128 columns of TMEM.
 #include <cuda_runtime.h>
@@ -28,7 +28,9 @@ constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;     // 16 KB (A_hi, A_lo, B_hi, B_lo each)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES; // 64 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
-constexpr int N_PRODUCERS = 128;
+constexpr int N_PRODUCERS = 256;  // 8 producer/epilogue warps + 1 MMA warp
+constexpr int N_THREADS = N_PRODUCERS + 32;
+constexpr int MMA_WARP = N_PRODUCERS / 32;
 // Four accumulators in TMEM (4 x 128 columns): the big hi*hi products and the small cross terms are
 // accumulated separately, each alternating between two accumulators per K block, and summed in fp32
 // registers in the epilogue.  The tensor core adds into its accumulator with truncation, so fewer,
@@ -106,7 +108,7 @@ __device__ __forceinline__ uint32_t swz(int r, int c) {  // byte offset of 16 B 
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(N_THREADS, 1)
     k_gemm_tf32x3(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bhi,
                   const float* __restrict__ Blo, int64_t ldb, float* __restrict__ C, int64_t ldc,
                   int M, int N, int K, int accumulate) {
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(160, 1)
     mbar_init(&accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {  // TMEM allocation by one full warp; the same warp frees it
+  if (warp == MMA_WARP) {  // TMEM allocation by one full warp; the same warp frees it
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&tmem_base_smem)),
                  "n"(TMEM_COLS)
@@ -139,10 +141,10 @@ __global__ void __launch_bounds__(160, 1)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
 
-  if (warp < 4) {
+  if (warp < MMA_WARP) {
     // ================= producers =================
     const int c = tid & 7;        // 16 B chunk within the 128 B K-row
-    const int rbase = tid >> 3;   // 0..15
+    const int rbase = tid >> 3;   // 0..31
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
@@ -153,8 +155,8 @@ __global__ void __launch_bounds__(160, 1)
       const bool col_ok = col < K;  // K % 4 == 0: a 16 B chunk is entirely valid or entirely padding
       // B tiles: pre-split, K-major -> straight async copies (zero-filled outside the matrix)
 #pragma unroll
-      for (int i = 0; i < BN / 16; ++i) {
-        const int r = rbase + 16 * i;
+      for (int i = 0; i < BN / 32; ++i) {
+        const int r = rbase + 32 * i;
         const bool ok = col_ok && (n0 + r < N);
         const size_t off = ok ? ((size_t)(n0 + r) * ldb + col) : 0;
         cp_async16(b_hi + swz(r, c), Bhi + off, ok ? 16u : 0u);
@@ -162,17 +164,17 @@ __global__ void __launch_bounds__(160, 1)
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
       // A tile: fp32 -> (hi, lo) in registers
-      float4 v[BM / 16];
+      float4 v[BM / 32];
 #pragma unroll
-      for (int i = 0; i < BM / 16; ++i) {
-        const int r = rbase + 16 * i;
+      for (int i = 0; i < BM / 32; ++i) {
+        const int r = rbase + 32 * i;
         v[i] = (col_ok && (m0 + r < M))
                    ? __ldg(reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + col))
                    : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int i = 0; i < BM / 16; ++i) {
-        const int r = rbase + 16 * i;
+      for (int i = 0; i < BM / 32; ++i) {
+        const int r = rbase + 32 * i;
         float4 hi, lo;
         split_tf32(v[i].x, hi.x, lo.x);
         split_tf32(v[i].y, hi.y, lo.y);
@@ -193,11 +195,13 @@ __global__ void __launch_bounds__(160, 1)
     // ================= epilogue =================
     mbar_wait(&accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = m0 + warp * 32 + lane;  // TMEM lane == accumulator row
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // a warp may only touch TMEM lanes 32*(warp % 4)..+31; warps 0-3 take columns 0-63, warps 4-7 64-127
+    const int row = m0 + (warp & 3) * 32 + lane;  // TMEM lane == accumulator row
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int cb_begin = (warp >> 2) * (BN / 2);
     const int n_pair = num_kb > 1 ? 2 : 1;  // accumulators actually written: {0,2} or {0,1,2,3}
 #pragma unroll
-    for (int cb = 0; cb < BN; cb += 32) {
+    for (int cb = cb_begin; cb < cb_begin + BN / 2; cb += 32) {
       uint32_t r[32];
       float sum[32];
 #pragma unroll
@@ -270,7 +274,7 @@ __global__ void __launch_bounds__(160, 1)
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "n"(TMEM_COLS)
@@ -305,7 +309,7 @@ __device__ __forceinline__ void umma_tf32_tn(uint32_t tmem_d, uint64_t da, uint6
       : "memory");
 }
 
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(N_THREADS, 1)
     k_gemm_tn_tf32x3(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
                      float* __restrict__ C, int64_t ldc, int M, int N, int K, int kb_per_split) {
   extern __shared__ uint8_t smem_raw[];
@@ -327,7 +331,7 @@ __global__ void __launch_bounds__(160, 1)
     mbar_init(&accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&tmem_base_smem)),
                  "n"(TMEM_COLS)
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(160, 1)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
 
-  if (warp < 4) {
+  if (warp < MMA_WARP) {
     // producers: chunk id = tid + 128 i -> tile row kr = id / 32 (0..31), 16 B chunk cm = id % 32 of the
     // 512-byte (128 floats) MN extent
     for (int kbi = 0; kbi < num_kb; ++kbi) {
@@ -349,10 +353,10 @@ __global__ void __launch_bounds__(160, 1)
       const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES;
       const uint32_t b_hi = a_lo + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
       const int k0 = (kb_begin + kbi) * BK;
-      float4 va[8], vb[8];
+      float4 va[4], vb[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int id = tid + 128 * i;
+      for (int i = 0; i < 4; ++i) {
+        const int id = tid + N_PRODUCERS * i;
         const int kr = id >> 5, cm = id & 31;
         const int krow = k0 + kr;
         const bool kok = krow < K;
@@ -364,8 +368,8 @@ __global__ void __launch_bounds__(160, 1)
                     : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int id = tid + 128 * i;
+      for (int i = 0; i < 4; ++i) {
+        const int id = tid + N_PRODUCERS * i;
         const int kr = id >> 5, cm = id & 31;
         const int c8 = cm & 7;  // 16 B chunk within the 128 B row: 32 B chunk (c8 >> 1) is swizzled with k & 3
         const uint32_t off = (uint32_t)((cm >> 3) * 4096 + (kr >> 2) * 512 + (kr & 3) * 128 +
@@ -394,11 +398,12 @@ __global__ void __launch_bounds__(160, 1)
     // epilogue: add this split's tile into C
     mbar_wait(&accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = m0 + warp * 32 + lane;
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int row = m0 + (warp & 3) * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int cb_begin = (warp >> 2) * (BN / 2);
     const int n_pair = num_kb > 1 ? 2 : 1;
 #pragma unroll
-    for (int cb = 0; cb < BN; cb += 32) {
+    for (int cb = cb_begin; cb < cb_begin + BN / 2; cb += 32) {
       uint32_t r[32];
       float sum[32];
 #pragma unroll
@@ -458,7 +463,7 @@ __global__ void __launch_bounds__(160, 1)
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "n"(TMEM_COLS)
@@ -511,7 +516,7 @@ int launch_gemm_tf32x3(const float* A, int64_t lda, const float* Bt_hi, const fl
     attr_set = true;
   }
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
-  k_gemm_tf32x3<<<grid, 160, SMEM_BYTES, st>>>(A, lda, Bt_hi, Bt_lo, ldb, C, ldc, M, N, K, accumulate);
+  k_gemm_tf32x3<<<grid, N_THREADS, SMEM_BYTES, st>>>(A, lda, Bt_hi, Bt_lo, ldb, C, ldc, M, N, K, accumulate);
   ++g_rgcn_launches;
   return rgcn_check_cuda(cudaGetLastError(), "k_gemm_tf32x3");
 }
@@ -546,7 +551,7 @@ int launch_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t l
   const int kb_per_split = (kb_total + splits - 1) / splits;
   splits = (kb_total + kb_per_split - 1) / kb_per_split;
   dim3 grid(tm, tn, splits);
-  k_gemm_tn_tf32x3<<<grid, 160, SMEM_BYTES, st>>>(A, lda, B, ldb, C, ldc, M, N, K, kb_per_split);
+  k_gemm_tn_tf32x3<<<grid, N_THREADS, SMEM_BYTES, st>>>(A, lda, B, ldb, C, ldc, M, N, K, kb_per_split);
   ++g_rgcn_launches;
   return rgcn_check_cuda(cudaGetLastError(), "k_gemm_tn_tf32x3");
 }
