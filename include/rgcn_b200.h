@@ -168,6 +168,21 @@ int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, const float
                         const float* dOut, float* dH, float* dWf, float* dWb, float* dWself,
                         void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Messages-only parts of the block layer, for graphs whose sources live in a separate row space
+ * (the halo rows of the node-sharded path: V_src may be smaller than V_dst):
+ *   aggregate          : out[dst,:] += sum_m norm_m * blockdiag(W[relw_m]) . X[src_m,:]      (no self loop)
+ *   aggregate_backward : dX [V_src,d] (overwritten) = sum_m norm_m W^T G[dst_m];
+ *                        dWf, dWb (overwritten, or += when accumulate_dW) = block outer products.
+ * Same per-message arithmetic as gcn_basis_concat.py:35-52 + the SpMMs of :69-75. */
+int64_t rgcn_block_aggregate_workspace_bytes(const rgcn_graph_t* g, int32_t d, int32_t B, int backward);
+int rgcn_block_aggregate(const rgcn_graph_t* g, int32_t d, int32_t B, const float* X, const float* Wf,
+                         const float* Wb, float* out, void* workspace, int64_t workspace_bytes,
+                         void* stream);
+int rgcn_block_aggregate_backward(const rgcn_graph_t* g, int32_t d, int32_t B, const float* X,
+                                  const float* Wf, const float* Wb, const float* G, float* dX,
+                                  float* dWf, float* dWb, int accumulate_dW, void* workspace,
+                                  int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Basis-decomposition R-GCN layer ("BasisGcn", encoders/message_gcns/gcn_basis.py:39-88).
  *

@@ -17,6 +17,7 @@ EXPORTED_SYMBOLS = [
     "rgcn_graph_create", "rgcn_graph_create_messages", "rgcn_graph_destroy", "rgcn_graph_info",
     "rgcn_graph_export_bytes", "rgcn_graph_export",
     "rgcn_block_workspace_bytes", "rgcn_block_forward", "rgcn_block_backward",
+    "rgcn_block_aggregate_workspace_bytes", "rgcn_block_aggregate", "rgcn_block_aggregate_backward",
     "rgcn_basis_workspace_bytes", "rgcn_basis_forward", "rgcn_basis_backward",
     "distmult_forward", "distmult_backward",
 ]
@@ -72,6 +73,13 @@ def _declare(lib):
     lib.rgcn_block_backward.restype = c_int
     lib.rgcn_block_backward.argtypes = [vp, c_int32, c_int32, vp, vp, vp, vp, vp, c_float, c_int, vp,
                                         vp, vp, vp, vp, vp, vp, c_int64, vp]
+    lib.rgcn_block_aggregate_workspace_bytes.restype = c_int64
+    lib.rgcn_block_aggregate_workspace_bytes.argtypes = [vp, c_int32, c_int32, c_int]
+    lib.rgcn_block_aggregate.restype = c_int
+    lib.rgcn_block_aggregate.argtypes = [vp, c_int32, c_int32, vp, vp, vp, vp, vp, c_int64, vp]
+    lib.rgcn_block_aggregate_backward.restype = c_int
+    lib.rgcn_block_aggregate_backward.argtypes = [vp, c_int32, c_int32, vp, vp, vp, vp, vp, vp, vp, c_int, vp,
+                                                  c_int64, vp]
     lib.rgcn_basis_workspace_bytes.restype = c_int64
     lib.rgcn_basis_workspace_bytes.argtypes = [vp, c_int32, c_int32, c_int]
     lib.rgcn_basis_forward.restype = c_int

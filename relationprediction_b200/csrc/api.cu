@@ -174,6 +174,16 @@ int common_checks(const rgcn_graph_t* g, int32_t d, int32_t B, const char* who) 
   return RGCN_OK;
 }
 
+int layer_checks(const rgcn_graph_t* g, int32_t d, int32_t B, const char* who) {
+  int rc = common_checks(g, d, B, who);
+  if (rc) return rc;
+  if (g->V_src < g->V_dst) {  // the self-loop term reads H rows [0, V_dst)
+    rgcn_set_error(std::string(who) + ": layer entry points need V_src >= V_dst (messages-only graphs go through rgcn_block_aggregate)");
+    return RGCN_ERR_INVALID;
+  }
+  return RGCN_OK;
+}
+
 AggLaunch make_agg(const CsrSide& side, const float* X, int ldx, int d, float* scratch,
                    int* counters) {
   AggLaunch a;
@@ -309,7 +319,7 @@ extern "C" int rgcn_block_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
                                   const float* Wf, const float* Wb, const float* Wself,
                                   const uint8_t* drop_mask, float keep, int relu, float* out,
                                   void* workspace, int64_t workspace_bytes, void* stream) {
-  int rc = common_checks(g, d, B, "rgcn_block_forward");
+  int rc = layer_checks(g, d, B, "rgcn_block_forward");
   if (rc) return rc;
   if (d % B != 0) {
     rgcn_set_error("rgcn_block_forward: d must be a multiple of B (gcn_basis_concat.py:15)");
@@ -377,7 +387,7 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
                                    const float* dOut, float* dH, float* dWf, float* dWb,
                                    float* dWself, void* workspace, int64_t workspace_bytes,
                                    void* stream) {
-  int rc = common_checks(g, d, B, "rgcn_block_backward");
+  int rc = layer_checks(g, d, B, "rgcn_block_backward");
   if (rc) return rc;
   if (d % B != 0) {
     rgcn_set_error("rgcn_block_backward: d must be a multiple of B");
@@ -464,9 +474,129 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
     if (rc) return rc;
   }
   MARK("block_dW");
-  rc = launch_block_unlayout(dWt, R, B, s, dWf, dWb, st);
+  rc = launch_block_unlayout(dWt, R, B, s, dWf, dWb, 0, st);
   MARK("block_unlayout");
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Messages-only parts of the block layer (used by the node-sharded path to overlap the halo exchange:
+// the local-source messages go through rgcn_block_forward/backward, the halo-source messages here)
+// ------------------------------------------------------------------------------------------------
+extern "C" int64_t rgcn_block_aggregate_workspace_bytes(const rgcn_graph_t* g, int32_t d, int32_t B,
+                                                        int backward) {
+  if (!g || d <= 0 || B <= 0 || d % B != 0) {
+    rgcn_set_error("rgcn_block_aggregate_workspace_bytes: bad arguments");
+    return RGCN_ERR_INVALID;
+  }
+  const int64_t s = d / B;
+  const int64_t wt = (int64_t)g->n_relw * s * d;
+  const int slabs = slabs_for(d);
+  const int64_t n_split = backward ? g->by_src.n_split : g->by_dst.n_split;
+  return (backward ? 2 : 1) * align_up(wt * 4) + align_up(n_split * d * 4) + align_up(n_split * slabs * 4) + 256;
+}
+
+extern "C" int rgcn_block_aggregate(const rgcn_graph_t* g, int32_t d, int32_t B, const float* X,
+                                    const float* Wf, const float* Wb, float* out, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
+  int rc = common_checks(g, d, B, "rgcn_block_aggregate");
+  if (rc) return rc;
+  if (d % B != 0 || !X || !Wf || !Wb || !out || !workspace) {
+    rgcn_set_error("rgcn_block_aggregate: bad arguments");
+    return RGCN_ERR_INVALID;
+  }
+  if (workspace_bytes < rgcn_block_aggregate_workspace_bytes(g, d, B, 0)) {
+    rgcn_set_error("rgcn_block_aggregate: workspace too small");
+    return RGCN_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = rgcn_check_cuda(cudaSetDevice(g->device), "cudaSetDevice");
+  if (rc) return rc;
+  const int s = d / B, R = g->n_relw / 2;
+  const int slabs = slabs_for(d);
+  const int64_t n_split = g->by_dst.n_split;
+  Carver ws(workspace, workspace_bytes);
+  float* Wt = ws.take<float>((int64_t)g->n_relw * s * d);
+  float* scratch = ws.take<float>(n_split * d);
+  int* counters = ws.take<int>(n_split * slabs);
+  MARK("start");
+  rc = launch_block_relayout(Wf, Wb, R, B, s, 0, Wt, st);
+  if (rc) return rc;
+  if (use_rel_major(d, s)) {
+    rc = launch_block_rel(g->by_rel.d_items, (int)g->by_rel.n_items, g->by_rel.d_row, g->by_rel.d_nbr,
+                          g->by_rel.d_norm, X, d, d, s, Wt, out, nullptr, 0, nullptr, st);
+  } else {
+    if (n_split > 0) {
+      rc = rgcn_check_cuda(
+          cudaMemsetAsync(scratch, 0, (char*)(counters + n_split * slabs) - (char*)scratch, st),
+          "memset(scratch)");
+      if (rc) return rc;
+    }
+    AggLaunch a = make_agg(g->by_dst, X, d, d, scratch, counters);
+    rc = launch_block_agg(a, s, Wt, out, nullptr, 1.f, 0, st);  // out = out + sum (in-place epilogue)
+  }
+  MARK("block_aggregate");
+  return rc;
+}
+
+extern "C" int rgcn_block_aggregate_backward(const rgcn_graph_t* g, int32_t d, int32_t B,
+                                             const float* X, const float* Wf, const float* Wb,
+                                             const float* G, float* dX, float* dWf, float* dWb,
+                                             int accumulate_dW, void* workspace,
+                                             int64_t workspace_bytes, void* stream) {
+  int rc = common_checks(g, d, B, "rgcn_block_aggregate_backward");
+  if (rc) return rc;
+  if (d % B != 0 || !X || !Wf || !Wb || !G || !dX || !dWf || !dWb || !workspace) {
+    rgcn_set_error("rgcn_block_aggregate_backward: bad arguments");
+    return RGCN_ERR_INVALID;
+  }
+  if (workspace_bytes < rgcn_block_aggregate_workspace_bytes(g, d, B, 1)) {
+    rgcn_set_error("rgcn_block_aggregate_backward: workspace too small");
+    return RGCN_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = rgcn_check_cuda(cudaSetDevice(g->device), "cudaSetDevice");
+  if (rc) return rc;
+  const int s = d / B, R = g->n_relw / 2;
+  const int slabs = slabs_for(d);
+  const int64_t n_split = g->by_src.n_split;
+  const int64_t wt = (int64_t)g->n_relw * s * d;
+  Carver ws(workspace, workspace_bytes);
+  float* Wtt = ws.take<float>(wt);
+  float* dWt = ws.take<float>(wt);
+  float* scratch = ws.take<float>(n_split * d);
+  int* counters = ws.take<int>(n_split * slabs);
+  MARK("start");
+  rc = launch_block_relayout(Wf, Wb, R, B, s, 1, Wtt, st);
+  if (rc) return rc;
+  rc = rgcn_check_cuda(cudaMemsetAsync(dX, 0, (size_t)g->V_src * d * sizeof(float), st), "memset(dX)");
+  if (rc) return rc;
+  rc = rgcn_check_cuda(cudaMemsetAsync(dWt, 0, wt * sizeof(float), st), "memset(dWt)");
+  if (rc) return rc;
+  const bool rel = use_rel_major(d, s);
+  const bool fused = rel && block_rel_fuse_dw_supported(d, s) && !std::getenv("RGCN_NO_FUSE_DW");
+  if (rel) {
+    rc = launch_block_rel(g->by_rel_src.d_items, (int)g->by_rel_src.n_items, g->by_rel_src.d_row,
+                          g->by_rel_src.d_nbr, g->by_rel_src.d_norm, G, d, d, s, Wtt, dX,
+                          fused ? X : nullptr, d, fused ? dWt : nullptr, st);
+  } else {
+    if (n_split > 0) {
+      rc = rgcn_check_cuda(
+          cudaMemsetAsync(scratch, 0, (char*)(counters + n_split * slabs) - (char*)scratch, st),
+          "memset(scratch)");
+      if (rc) return rc;
+    }
+    AggLaunch a = make_agg(g->by_src, G, d, d, scratch, counters);
+    rc = launch_block_agg(a, s, Wtt, dX, nullptr, 1.f, 0, st);
+  }
+  if (rc) return rc;
+  if (!fused) {
+    rc = launch_block_dw(g->by_rel.d_items, (int)g->by_rel.n_items, g->by_rel.d_row, g->by_rel.d_nbr,
+                         g->by_rel.d_norm, X, d, G, d, d, s, dWt, st);
+    if (rc) return rc;
+  }
+  MARK("block_aggregate_bwd");
+  return launch_block_unlayout(dWt, R, B, s, dWf, dWb, accumulate_dW, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -494,7 +624,7 @@ extern "C" int rgcn_basis_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
                                   const float* Cb, const float* Wself, const uint8_t* drop_mask,
                                   float keep, int relu, float* out, float* saved, void* workspace,
                                   int64_t workspace_bytes, void* stream) {
-  int rc = common_checks(g, d, B, "rgcn_basis_forward");
+  int rc = layer_checks(g, d, B, "rgcn_basis_forward");
   if (rc) return rc;
   if (!H || !Vf || !Vb || !Cf || !Cb || !Wself || !out || !saved || !workspace || keep <= 0.f) {
     rgcn_set_error("rgcn_basis_forward: null pointer or keep <= 0");
@@ -543,7 +673,7 @@ extern "C" int rgcn_basis_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
                                    const float* dOut, float* dH, float* dVf, float* dVb, float* dCf,
                                    float* dCb, float* dWself, void* workspace,
                                    int64_t workspace_bytes, void* stream) {
-  int rc = common_checks(g, d, B, "rgcn_basis_backward");
+  int rc = layer_checks(g, d, B, "rgcn_basis_backward");
   if (rc) return rc;
   if (!H || !Vf || !Vb || !Cf || !Cb || !Wself || !saved || !dOut || !dH || !dVf || !dVb || !dCf ||
       !dCb || !dWself || !workspace || (relu && !out) || keep <= 0.f) {

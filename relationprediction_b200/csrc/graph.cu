@@ -192,8 +192,8 @@ int build(const int32_t* dst, const int32_t* src, const int32_t* relw, const flo
     return RGCN_ERR_INVALID;
   }
   *out = nullptr;
-  if (M < 0 || M > 0x7fffffffLL || V_dst < 0 || V_src < V_dst || n_relw <= 0) {
-    rgcn_set_error("rgcn_graph_create: bad sizes (need 0<=M<2^31, 0<=V_dst<=V_src, n_relw>0)");
+  if (M < 0 || M > 0x7fffffffLL || V_dst < 0 || V_src < 0 || n_relw <= 0) {
+    rgcn_set_error("rgcn_graph_create: bad sizes (need 0<=M<2^31, V_dst>=0, V_src>=0, n_relw>0)");
     return RGCN_ERR_INVALID;
   }
   rgcn_graph* g = new_graph(M, V_dst, V_src, n_relw, device);

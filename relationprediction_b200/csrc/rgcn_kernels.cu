@@ -699,7 +699,7 @@ __global__ void k_block_relayout(const float* __restrict__ Wf, const float* __re
 }
 
 __global__ void k_block_unlayout(const float* __restrict__ dWt, int R, int B, int s,
-                                 float* __restrict__ dWf, float* __restrict__ dWb) {
+                                 float* __restrict__ dWf, float* __restrict__ dWb, int accumulate) {
   const int d = B * s;
   const int64_t per = (int64_t)d * s;
   const int64_t total = 2 * (int64_t)R * per;
@@ -712,10 +712,8 @@ __global__ void k_block_unlayout(const float* __restrict__ dWt, int R, int B, in
     const int i = (rem / s) % s;
     const int j = rem % s;
     const float v = __ldg(dWt + ((size_t)w * s + j) * d + b * s + i);
-    if (w < R)
-      dWf[(size_t)w * per + rem] = v;
-    else
-      dWb[(size_t)(w - R) * per + rem] = v;
+    float* p = (w < R) ? dWf + (size_t)w * per + rem : dWb + (size_t)(w - R) * per + rem;
+    *p = accumulate ? *p + v : v;
   }
 }
 
@@ -1199,9 +1197,9 @@ int launch_block_relayout(const float* Wf, const float* Wb, int R, int B, int s,
 }
 
 int launch_block_unlayout(const float* dWt, int R, int B, int s, float* dWf, float* dWb,
-                          cudaStream_t st) {
+                          int accumulate, cudaStream_t st) {
   const int64_t total = 2 * (int64_t)R * B * s * s;
-  k_block_unlayout<<<grid_for(total, 256), 256, 0, st>>>(dWt, R, B, s, dWf, dWb);
+  k_block_unlayout<<<grid_for(total, 256), 256, 0, st>>>(dWt, R, B, s, dWf, dWb, accumulate);
   return check_launch("k_block_unlayout");
 }
 

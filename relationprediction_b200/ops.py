@@ -324,3 +324,36 @@ def gemm_tn_tf32x3(A, B, out=None, accumulate=False):
                                  int(accumulate), _stream(A.device))
     _lib.check(rc, "rgcn_gemm_tn_tf32x3")
     return out
+
+
+def block_aggregate_(out, X, W_forward, W_backward, graph, n_blocks):
+    """out[dst] += sum_m norm_m W[relw_m] . X[src_m] (messages only, in place; rgcn_block_aggregate)."""
+    lib = _lib.load()
+    d = X.shape[1]
+    _check_cuda_f32("X", X, (graph.V_src, d))
+    _check_cuda_f32("out", out, (graph.V_dst, d))
+    nb = lib.rgcn_block_aggregate_workspace_bytes(graph.handle, d, n_blocks, 0)
+    ws = _workspace(nb, X.device)
+    rc = lib.rgcn_block_aggregate(graph.handle, d, n_blocks, _ptr(X), _ptr(W_forward), _ptr(W_backward),
+                                  _ptr(out), _ptr(ws), ws.numel(), _stream(X.device))
+    _lib.check(rc, "rgcn_block_aggregate")
+    return out
+
+
+def block_aggregate_backward(X, W_forward, W_backward, G, graph, n_blocks, dWf=None, dWb=None):
+    """Returns (dX, dWf, dWb) of block_aggregate_; when dWf/dWb are given they are accumulated into."""
+    lib = _lib.load()
+    d = X.shape[1]
+    _check_cuda_f32("X", X, (graph.V_src, d))
+    _check_cuda_f32("G", G, (graph.V_dst, d))
+    acc = dWf is not None
+    if not acc:
+        dWf, dWb = torch.empty_like(W_forward), torch.empty_like(W_backward)
+    dX = torch.empty_like(X)
+    nb = lib.rgcn_block_aggregate_workspace_bytes(graph.handle, d, n_blocks, 1)
+    ws = _workspace(nb, X.device)
+    rc = lib.rgcn_block_aggregate_backward(graph.handle, d, n_blocks, _ptr(X), _ptr(W_forward), _ptr(W_backward),
+                                           _ptr(G), _ptr(dX), _ptr(dWf), _ptr(dWb), int(acc), _ptr(ws),
+                                           ws.numel(), _stream(X.device))
+    _lib.check(rc, "rgcn_block_aggregate_backward")
+    return dX, dWf, dWb

@@ -109,9 +109,66 @@ class _HaloExchange(torch.autograd.Function):
         return dH, None, None, None
 
 
+class _OverlappedBlockLayer(torch.autograd.Function):
+    """Sharded block layer with the halo all-to-all hidden behind the local work.
+
+    forward : start all-to-all(halo rows) || self-loop GEMM + LOCAL-source messages (rgcn_block_forward on
+              the local graph, ReLU deferred) -> wait -> HALO-source messages (rgcn_block_aggregate) -> ReLU
+    backward: G = dOut * relu'(out) -> halo-source backward first (rgcn_block_aggregate_backward) -> start
+              all-to-all(halo gradients) || local backward (rgcn_block_backward) -> wait -> scatter-add."""
+
+    @staticmethod
+    def forward(ctx, H_local, Wf, Wb, Ws, sg, n_blocks, drop_mask, keep, relu):
+        p = sg.plan
+        d = H_local.shape[1]
+        dev = H_local.device
+        H_local = H_local.contiguous()
+        send = H_local.index_select(0, sg.send_rows)
+        H_halo = torch.empty(p.n_halo, d, dtype=H_local.dtype, device=dev)
+        work = dist.all_to_all_single(H_halo, send, output_split_sizes=p.recv_counts.tolist(),
+                                      input_split_sizes=p.send_counts.tolist(), group=sg.group, async_op=True)
+        with torch.no_grad():
+            out = ops._BlockLayerFn.apply(H_local, Wf, Wb, Ws, sg.graph_local, n_blocks, drop_mask, keep, False)
+        work.wait()
+        ops.block_aggregate_(out, H_halo, Wf, Wb, sg.graph_halo, n_blocks)
+        if relu:
+            out.relu_()
+        ctx.sg, ctx.n_blocks, ctx.keep, ctx.relu, ctx.mask = sg, n_blocks, keep, relu, drop_mask
+        ctx.save_for_backward(H_local, Wf, Wb, Ws, H_halo, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        H_local, Wf, Wb, Ws, H_halo, out = ctx.saved_tensors
+        sg, B = ctx.sg, ctx.n_blocks
+        p = sg.plan
+        G = (dOut * (out > 0)) if ctx.relu else dOut
+        G = G.contiguous()
+        dHalo, dWf, dWb = ops.block_aggregate_backward(H_halo, Wf, Wb, G, sg.graph_halo, B)
+        back = torch.empty(int(p.send_counts.sum()), G.shape[1], dtype=G.dtype, device=G.device)
+        work = dist.all_to_all_single(back, dHalo, output_split_sizes=p.send_counts.tolist(),
+                                      input_split_sizes=p.recv_counts.tolist(), group=sg.group, async_op=True)
+        lib = ops._lib.load()
+        d = H_local.shape[1]
+        dH = torch.empty_like(H_local)
+        dWf_l, dWb_l, dWs = torch.empty_like(Wf), torch.empty_like(Wb), torch.empty_like(Ws)
+        nb = lib.rgcn_block_workspace_bytes(sg.graph_local.handle, d, B, 1)
+        ws = ops._workspace(nb, G.device)
+        rc = lib.rgcn_block_backward(sg.graph_local.handle, d, B, ops._ptr(H_local), ops._ptr(Wf), ops._ptr(Wb),
+                                     ops._ptr(Ws), ops._ptr(ctx.mask), float(ctx.keep), 0, ops._ptr(out),
+                                     ops._ptr(G), ops._ptr(dH), ops._ptr(dWf_l), ops._ptr(dWb_l), ops._ptr(dWs),
+                                     ops._ptr(ws), ws.numel(), ops._stream(G.device))
+        ops._lib.check(rc, "rgcn_block_backward")
+        dWf += dWf_l
+        dWb += dWb_l
+        work.wait()
+        dH.index_add_(0, sg.send_rows, back)
+        return dH, dWf, dWb, dWs, None, None, None, None, None
+
+
 class ShardedGraph(object):
     def __init__(self, triples, n_nodes, n_relations, rank, world, device, norm_mode="canonical",
-                 norm_f=None, norm_b=None, group=None):
+                 norm_f=None, norm_b=None, group=None, overlap=True):
         self.plan = ShardPlan(triples, n_nodes, n_relations, rank, world, norm_mode, norm_f, norm_b)
         self.device = torch.device(device)
         self.group = group
@@ -123,12 +180,26 @@ class ShardedGraph(object):
         self.graph = ops.Graph.from_messages(p.msg_dst, p.msg_src, p.msg_relw, p.msg_norm, p.n_local,
                                              p.n_local + p.n_halo, 2 * n_relations, device=index)
         self.send_rows = torch.as_tensor(p.send_rows, device=self.device)
+        # split by source locality so the halo exchange can overlap the local-source work
+        self.overlap = overlap and world > 1
+        if self.overlap:
+            loc = p.msg_src < p.n_local
+            self.graph_local = ops.Graph.from_messages(p.msg_dst[loc], p.msg_src[loc], p.msg_relw[loc],
+                                                       p.msg_norm[loc], p.n_local, p.n_local,
+                                                       2 * n_relations, device=index)
+            rem = ~loc
+            self.graph_halo = ops.Graph.from_messages(p.msg_dst[rem], p.msg_src[rem] - p.n_local, p.msg_relw[rem],
+                                                      p.msg_norm[rem], p.n_local, max(p.n_halo, 0),
+                                                      2 * n_relations, device=index)
 
     def halo_exchange(self, H_local):
         return _HaloExchange.apply(H_local, self.plan, self.send_rows, self.group)
 
     def block_layer(self, H_local, W_forward, W_backward, W_self, n_blocks, drop_mask=None, keep=1.0,
                     relu=True):
+        if self.overlap and self.device.type == "cuda":
+            return _OverlappedBlockLayer.apply(H_local, W_forward, W_backward, W_self, self, int(n_blocks),
+                                               drop_mask, keep, relu)
         return ops.block_layer(self.halo_exchange(H_local), W_forward, W_backward, W_self, self.graph,
                                n_blocks, drop_mask, keep, relu)
 
