@@ -35,7 +35,12 @@ __global__ void k_tri2msg(const int32_t* __restrict__ tri, int64_t E, int32_t R,
        k += (int64_t)gridDim.x * blockDim.x) {
     const int32_t s = tri[3 * k], r = tri[3 * k + 1], o = tri[3 * k + 2];
     if (s < 0 || s >= V || o < 0 || o >= V || r < 0 || r >= R) {
+      // flag it (checked by the host at the single synchronisation) and write memory-safe values so
+      // the kernels already queued behind this one cannot index out of range
       atomicExch(bad, 1);
+      dst[k] = src[k] = relw[k] = 0;
+      dst[E + k] = src[E + k] = 0;
+      relw[E + k] = R;
       continue;
     }
     dst[k] = o;
@@ -253,10 +258,24 @@ int scan_i32(Scratch& sc, const int32_t* in, int32_t* out, int64_t n, cudaStream
   return RGCN_OK;
 }
 
-int build_csr_view(rgcn_graph* g, CsrSide& side, const int32_t* row, int32_t n_rows,
-                   const int32_t* nbr, const int32_t* relw, const float* norm, int64_t M,
-                   bool count_runs, unsigned long long* d_runs, cudaStream_t st, int64_t& bytes) {
-  Scratch sc(st);
+// Each view is built in two phases so the whole preparation needs ONE host synchronisation:
+//   phase A (all asynchronous): sort, gather, CSR pointer, per-row item counts + exclusive scans, the
+//                               totals copied into a pinned host slot;
+//   -- one cudaStreamSynchronize for all four views --
+//   phase B: allocate the work-item arrays (sizes now known on the host) and fill them.
+struct ViewTmp {
+  Scratch sc;
+  int32_t* item_off = nullptr;
+  int32_t* split_off = nullptr;
+  int32_t n_keys = 0;
+  explicit ViewTmp(cudaStream_t st) : sc(st) {}
+};
+
+int csr_phase_a(rgcn_graph* g, CsrSide& side, ViewTmp& t, const int32_t* row, int32_t n_rows,
+                const int32_t* nbr, const int32_t* relw, const float* norm, int64_t M,
+                bool count_runs, unsigned long long* d_runs, int32_t* h_totals /* pinned [2] */,
+                cudaStream_t st, int64_t& bytes) {
+  Scratch& sc = t.sc;
   int rc;
   if ((rc = dalloc(&side.d_rowptr, (int64_t)n_rows + 1, st, &bytes))) return rc;
   int32_t* perm;
@@ -280,12 +299,11 @@ int build_csr_view(rgcn_graph* g, CsrSide& side, const int32_t* row, int32_t n_r
     if ((rc = dalloc(&side.d_mid, M, st, &bytes))) return rc;
     DCK(cudaMemcpyAsync(side.d_mid, perm, (size_t)M * 4, cudaMemcpyDeviceToDevice, st));
   }
-  // work items
-  int32_t *nitems, *issplit, *item_off, *split_off;
+  int32_t *nitems, *issplit;
   if ((rc = sc.get(&nitems, (int64_t)n_rows + 1))) return rc;
   if ((rc = sc.get(&issplit, (int64_t)n_rows + 1))) return rc;
-  if ((rc = sc.get(&item_off, (int64_t)n_rows + 1))) return rc;
-  if ((rc = sc.get(&split_off, (int64_t)n_rows + 1))) return rc;
+  if ((rc = sc.get(&t.item_off, (int64_t)n_rows + 1))) return rc;
+  if ((rc = sc.get(&t.split_off, (int64_t)n_rows + 1))) return rc;
   DCK(cudaMemsetAsync(nitems, 0, ((size_t)n_rows + 1) * 4, st));
   DCK(cudaMemsetAsync(issplit, 0, ((size_t)n_rows + 1) * 4, st));
   if (n_rows > 0) {
@@ -293,34 +311,39 @@ int build_csr_view(rgcn_graph* g, CsrSide& side, const int32_t* row, int32_t n_r
                                                          issplit);
     ++g_rgcn_launches;
   }
-  if ((rc = scan_i32(sc, nitems, item_off, (int64_t)n_rows + 1, st))) return rc;
-  if ((rc = scan_i32(sc, issplit, split_off, (int64_t)n_rows + 1, st))) return rc;
-  int32_t totals[2] = {0, 0};
-  DCK(cudaMemcpyAsync(&totals[0], item_off + n_rows, 4, cudaMemcpyDeviceToHost, st));
-  DCK(cudaMemcpyAsync(&totals[1], split_off + n_rows, 4, cudaMemcpyDeviceToHost, st));
-  DCK(cudaStreamSynchronize(st));
-  side.n_items = totals[0];
-  side.n_split = totals[1];
+  if ((rc = scan_i32(sc, nitems, t.item_off, (int64_t)n_rows + 1, st))) return rc;
+  if ((rc = scan_i32(sc, issplit, t.split_off, (int64_t)n_rows + 1, st))) return rc;
+  DCK(cudaMemcpyAsync(&h_totals[0], t.item_off + n_rows, 4, cudaMemcpyDeviceToHost, st));
+  DCK(cudaMemcpyAsync(&h_totals[1], t.split_off + n_rows, 4, cudaMemcpyDeviceToHost, st));
+  return RGCN_OK;
+}
+
+int csr_phase_b(rgcn_graph* g, CsrSide& side, ViewTmp& t, int32_t n_rows, const int32_t* h_totals,
+                cudaStream_t st, int64_t& bytes) {
+  int rc;
+  side.n_items = h_totals[0];
+  side.n_split = h_totals[1];
   if ((rc = dalloc(&side.d_items, side.n_items, st, &bytes))) return rc;
   if ((rc = dalloc(&side.d_split_nitems, side.n_split, st, &bytes))) return rc;
   if ((rc = dalloc(&side.d_split_rows, side.n_split, st, &bytes))) return rc;
   if (n_rows > 0) {
-    k_csr_fill_items<<<grid_for(n_rows), 256, 0, st>>>(side.d_rowptr, n_rows, g->item_max, item_off,
-                                                        split_off, side.d_items, side.d_split_nitems,
+    k_csr_fill_items<<<grid_for(n_rows), 256, 0, st>>>(side.d_rowptr, n_rows, g->item_max, t.item_off,
+                                                        t.split_off, side.d_items, side.d_split_nitems,
                                                         side.d_split_rows);
     ++g_rgcn_launches;
   }
   return rgcn_check_cuda(cudaGetLastError(), "graph prep (csr view)");
 }
 
-int build_rel_view(rgcn_graph* g, RelSide& side, const int32_t* row, int32_t n_rows,
-                   const int32_t* nbr, const int32_t* relw, const float* norm, int64_t M,
-                   cudaStream_t st, int64_t& bytes) {
-  Scratch sc(st);
+int rel_phase_a(rgcn_graph* g, RelSide& side, ViewTmp& t, const int32_t* row, int32_t n_rows,
+                const int32_t* nbr, const int32_t* relw, const float* norm, int64_t M,
+                int32_t* h_total /* pinned [1] */, cudaStream_t st, int64_t& bytes) {
+  Scratch& sc = t.sc;
   int rc;
   const int32_t n_super = std::max(1, (n_rows + g->supertile_rows - 1) / g->supertile_rows);
   side.n_super = n_super;
   const int64_t nkeys = (int64_t)n_super * g->n_relw;
+  t.n_keys = (int32_t)nkeys;
   if ((rc = dalloc(&side.d_ptr, nkeys + 1, st, &bytes))) return rc;
   int32_t* perm;
   uint64_t* keys;
@@ -339,29 +362,64 @@ int build_rel_view(rgcn_graph* g, RelSide& side, const int32_t* row, int32_t n_r
     if ((rc = dalloc(&side.d_mid, M, st, &bytes))) return rc;
     DCK(cudaMemcpyAsync(side.d_mid, perm, (size_t)M * 4, cudaMemcpyDeviceToDevice, st));
   }
-  int32_t *nitems, *item_off;
+  int32_t* nitems;
   if ((rc = sc.get(&nitems, nkeys + 1))) return rc;
-  if ((rc = sc.get(&item_off, nkeys + 1))) return rc;
+  if ((rc = sc.get(&t.item_off, nkeys + 1))) return rc;
   DCK(cudaMemsetAsync(nitems, 0, ((size_t)nkeys + 1) * 4, st));
   k_rel_item_counts<<<grid_for(nkeys), 256, 0, st>>>(side.d_ptr, (int32_t)nkeys, g->item_max, nitems);
   ++g_rgcn_launches;
-  if ((rc = scan_i32(sc, nitems, item_off, nkeys + 1, st))) return rc;
-  int32_t total = 0;
-  DCK(cudaMemcpyAsync(&total, item_off + nkeys, 4, cudaMemcpyDeviceToHost, st));
-  DCK(cudaStreamSynchronize(st));
-  side.n_items = total;
+  if ((rc = scan_i32(sc, nitems, t.item_off, nkeys + 1, st))) return rc;
+  DCK(cudaMemcpyAsync(h_total, t.item_off + nkeys, 4, cudaMemcpyDeviceToHost, st));
+  return RGCN_OK;
+}
+
+int rel_phase_b(rgcn_graph* g, RelSide& side, ViewTmp& t, const int32_t* h_total, cudaStream_t st,
+                int64_t& bytes) {
+  int rc;
+  side.n_items = h_total[0];
   if ((rc = dalloc(&side.d_items, side.n_items, st, &bytes))) return rc;
-  k_rel_fill_items<<<grid_for(nkeys), 256, 0, st>>>(side.d_ptr, (int32_t)nkeys, g->item_max,
-                                                     g->n_relw, item_off, side.d_items);
+  k_rel_fill_items<<<grid_for(t.n_keys), 256, 0, st>>>(side.d_ptr, t.n_keys, g->item_max, g->n_relw,
+                                                        t.item_off, side.d_items);
   ++g_rgcn_launches;
   return rgcn_check_cuda(cudaGetLastError(), "graph prep (rel view)");
+}
+
+// pinned host slots for the few integers the host needs back (one set per thread)
+struct HostSlots {
+  int32_t* p = nullptr;  // [0..1] by_dst, [2..3] by_src, [4] by_rel, [5] by_rel_src, [6] bad flag
+  unsigned long long* runs = nullptr;
+  HostSlots() {
+    cudaHostAlloc((void**)&p, 8 * sizeof(int32_t), cudaHostAllocDefault);
+    cudaHostAlloc((void**)&runs, sizeof(unsigned long long), cudaHostAllocDefault);
+  }
+};
+
+void tune_mempool_once(int device) {
+  // keep freed blocks in the stream-ordered pool instead of returning them to the OS at every
+  // synchronisation (the default release threshold is 0: every graph build would re-map memory)
+  static bool done[64] = {false};
+  if (device < 0 || device >= 64 || done[device]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done[device] = true;
 }
 
 }  // namespace
 
 // Builds every device-side structure of `g` from DEVICE message arrays (length M).
-int rgcn_build_on_device(rgcn_graph* g, const int32_t* d_dst, const int32_t* d_src,
-                         const int32_t* d_relw, const float* d_norm, cudaStream_t st) {
+// d_bad (optional): device flag set by the caller's validation kernel; checked at the single sync.
+int rgcn_build_on_device_checked(rgcn_graph* g, const int32_t* d_dst, const int32_t* d_src,
+                                 const int32_t* d_relw, const float* d_norm, const int* d_bad,
+                                 cudaStream_t st) {
+  static thread_local HostSlots hs;
+  if (!hs.p || !hs.runs) {
+    rgcn_set_error("cudaHostAlloc failed in graph prep");
+    return RGCN_ERR_NOMEM;
+  }
+  tune_mempool_once(g->device);
   int64_t bytes = 0;
   const int64_t M = g->M;
   int rc;
@@ -372,20 +430,33 @@ int rgcn_build_on_device(rgcn_graph* g, const int32_t* d_dst, const int32_t* d_s
     if ((rc = dalloc(&g->d_msg_norm, M, st, &bytes))) return rc;
     DCK(cudaMemcpyAsync(g->d_msg_norm, d_norm, (size_t)M * 4, cudaMemcpyDeviceToDevice, st));
   }
-  rc = build_csr_view(g, g->by_dst, d_dst, g->V_dst, d_src, d_relw, d_norm, M, true, d_runs, st, bytes);
-  if (!rc) rc = build_csr_view(g, g->by_src, d_src, g->V_src, d_dst, d_relw, d_norm, M, false, nullptr, st, bytes);
-  if (!rc) rc = build_rel_view(g, g->by_rel, d_dst, g->V_dst, d_src, d_relw, d_norm, M, st, bytes);
-  if (!rc) rc = build_rel_view(g, g->by_rel_src, d_src, g->V_src, d_dst, d_relw, d_norm, M, st, bytes);
-  unsigned long long runs = 0;
-  if (!rc) {
-    rc = rgcn_check_cuda(cudaMemcpyAsync(&runs, d_runs, sizeof(runs), cudaMemcpyDeviceToHost, st), "copy runs");
-    if (!rc) rc = rgcn_check_cuda(cudaStreamSynchronize(st), "sync(graph prep)");
-  }
+  ViewTmp t0(st), t1(st), t2(st), t3(st);
+  hs.p[6] = 0;
+  rc = csr_phase_a(g, g->by_dst, t0, d_dst, g->V_dst, d_src, d_relw, d_norm, M, true, d_runs, hs.p + 0, st, bytes);
+  if (!rc) rc = csr_phase_a(g, g->by_src, t1, d_src, g->V_src, d_dst, d_relw, d_norm, M, false, nullptr, hs.p + 2, st, bytes);
+  if (!rc) rc = rel_phase_a(g, g->by_rel, t2, d_dst, g->V_dst, d_src, d_relw, d_norm, M, hs.p + 4, st, bytes);
+  if (!rc) rc = rel_phase_a(g, g->by_rel_src, t3, d_src, g->V_src, d_dst, d_relw, d_norm, M, hs.p + 5, st, bytes);
+  if (!rc) rc = rgcn_check_cuda(cudaMemcpyAsync(hs.runs, d_runs, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "copy runs");
+  if (!rc && d_bad) rc = rgcn_check_cuda(cudaMemcpyAsync(hs.p + 6, d_bad, 4, cudaMemcpyDeviceToHost, st), "copy flag");
+  if (!rc) rc = rgcn_check_cuda(cudaStreamSynchronize(st), "sync(graph prep)");
   cudaFreeAsync(d_runs, st);
-  g->n_groups = (int64_t)runs;
+  if (!rc && hs.p[6]) {
+    rgcn_set_error("rgcn_graph_create: index out of range");
+    rc = RGCN_ERR_INVALID;
+  }
+  if (!rc) rc = csr_phase_b(g, g->by_dst, t0, g->V_dst, hs.p + 0, st, bytes);
+  if (!rc) rc = csr_phase_b(g, g->by_src, t1, g->V_src, hs.p + 2, st, bytes);
+  if (!rc) rc = rel_phase_b(g, g->by_rel, t2, hs.p + 4, st, bytes);
+  if (!rc) rc = rel_phase_b(g, g->by_rel_src, t3, hs.p + 5, st, bytes);
+  g->n_groups = (int64_t)*hs.runs;
   g->device_bytes = bytes;
   g->built_on_device = true;
   return rc;
+}
+
+int rgcn_build_on_device(rgcn_graph* g, const int32_t* d_dst, const int32_t* d_src,
+                         const int32_t* d_relw, const float* d_norm, cudaStream_t st) {
+  return rgcn_build_on_device_checked(g, d_dst, d_src, d_relw, d_norm, nullptr, st);
 }
 
 // triples (DEVICE, int32 [E,3]) -> messages + norm -> rgcn_build_on_device
@@ -421,14 +492,7 @@ int rgcn_build_from_triples_device(rgcn_graph* g, const int32_t* d_triples, int6
     }
     ++g_rgcn_launches;
   }
-  int h_bad = 0;
-  DCK(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st));
-  DCK(cudaStreamSynchronize(st));
-  if (h_bad) {
-    rgcn_set_error("rgcn_graph_create: a triple is out of range");
-    return RGCN_ERR_INVALID;
-  }
-  return rgcn_build_on_device(g, dst, src, relw, norm, st);
+  return rgcn_build_on_device_checked(g, dst, src, relw, norm, bad, st);
 }
 
 int rgcn_check_messages_device(const int32_t* d_dst, const int32_t* d_src, const int32_t* d_relw,

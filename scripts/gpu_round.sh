@@ -1,11 +1,10 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_gemm.py -q -m gpu -x -k tn > gpurun_out/pytest_gemm.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gemm.log
-tail -12 gpurun_out/pytest_gemm.log
-timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests/test_gpu_graph_prep.py tests/test_gpu_model.py -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_fb.json 2> gpurun_out/bench_fb.err; echo "bench rc=$?"
-tail -3 gpurun_out/bench_fb.err; python scripts/show_bench.py gpurun_out/bench_fb.json
-timeout 600 python bench.py --workload synthetic --scale 0.02 --no-cpu-baseline --steps 5 > gpurun_out/bench_syn.json 2> gpurun_out/bench_syn.err; echo "bench syn rc=$?"
-tail -3 gpurun_out/bench_syn.err; python scripts/show_bench.py gpurun_out/bench_syn.json
+timeout 300 python scripts/e2e_probe.py 2>&1 | tail -8
+timeout 600 python bench.py > gpurun_out/bench_fb.json 2> gpurun_out/bench_fb.err; tail -3 gpurun_out/bench_fb.err; python scripts/show_bench.py gpurun_out/bench_fb.json
+python - <<'PY'
+import json; j=json.loads(open('gpurun_out/bench_fb.json').read().strip().splitlines()[-1]); print(j['e2e']); print(j['roofline']); print(j['clocks'], j['wall_s_timed_region'])
+PY
