@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--skewed", action="store_true", help="synthetic workload: skewed endpoints")
     ap.add_argument("--cpu-sample-edges", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (needs 4 pinned V*d buffers)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -311,7 +312,7 @@ def main():
 
     # ---- e2e: same layer fwd+bwd through the public API with HOST buffers (single GPU path) ----
     e2e = None
-    if world == 1:
+    if world == 1 and not args.no_e2e and V * d * 4 <= (4 << 30):
         tri_pin = torch.from_numpy(triples).pin_memory()
         H_pin = H.cpu().pin_memory()
         dOut_pin = dOut.cpu().pin_memory()

@@ -645,12 +645,14 @@ extern "C" int rgcn_basis_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
   rc = rgcn_check_cuda(cudaMemcpyAsync(Ccat, Cf, (size_t)R * B * 4, cudaMemcpyDeviceToDevice, st), "copy Cf");
   if (!rc) rc = rgcn_check_cuda(cudaMemcpyAsync(Ccat + (size_t)R * B, Cb, (size_t)R * B * 4, cudaMemcpyDeviceToDevice, st), "copy Cb");
   if (rc) return rc;
+  MARK("start");
   // Agg[v][dir][k*B+b] = sum_m norm_m C[relw_m,b] H[src_m,k]
   rc = launch_zero_rows(saved, 2 * dB, g->by_dst.d_split_rows, (int)g->by_dst.n_split, st);
   if (rc) return rc;
   AggLaunch a = make_agg(g->by_dst, H, d, d, nullptr, nullptr);
   rc = launch_basis_agg(a, Ccat, B, g->n_relw, /*layout=*/0, saved, st);
   if (rc) return rc;
+  MARK("basis_agg_fwd");
   cublasHandle_t h;
   rc = get_cublas(g->device, st, &h);
   if (rc) return rc;
@@ -663,7 +665,10 @@ extern "C" int rgcn_basis_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
   if (rc) return rc;
   rc = gemm_any(h, split_ws, false, false, g->V_dst, d, dB, 1.f, saved + dB, 2 * dB, Vb, d, 1.f, out, d);
   if (rc) return rc;
-  return launch_mask_relu(out, nullptr, 1.f, relu, (int64_t)g->V_dst * d, st);
+  MARK("basis_gemms_fwd");
+  rc = launch_mask_relu(out, nullptr, 1.f, relu, (int64_t)g->V_dst * d, st);
+  MARK("relu_epilogue");
+  return rc;
 }
 
 extern "C" int rgcn_basis_backward(const rgcn_graph_t* g, int32_t d, int32_t B, const float* H,
@@ -702,6 +707,7 @@ extern "C" int rgcn_basis_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   if (!rc) rc = rgcn_check_cuda(cudaMemcpyAsync(Ccat + (size_t)R * B, Cb, (size_t)R * B * 4, cudaMemcpyDeviceToDevice, st), "copy Cb");
   if (rc) return rc;
 
+  MARK("start");
   rc = launch_grad_prologue(dOut, out, drop_mask, 1.0f / keep, relu, (int64_t)g->V_dst * d, G, dS, st);
   if (rc) return rc;
   cublasHandle_t h;
@@ -717,6 +723,7 @@ extern "C" int rgcn_basis_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
                          "memset(dH halo)");
     if (rc) return rc;
   }
+  MARK("basis_self_loop_bwd");
   // dV_dir.reshape(d*B, d) = Agg_dir^T G
   rc = gemm_any(h, split_ws, true, false, dB, d, g->V_dst, 1.f, saved, 2 * dB, G, d, 0.f, dVf, d);
   if (rc) return rc;
@@ -727,12 +734,14 @@ extern "C" int rgcn_basis_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   if (rc) return rc;
   rc = gemm_any(h, split_ws, false, true, g->V_dst, dB, d, 1.f, G, d, Vb, d, 0.f, dAgg + dB, 2 * dB);
   if (rc) return rc;
+  MARK("basis_gemms_dV_dAgg");
   // dC[w,b] = sum_m norm_m < H[src_m], dAgg[dst_m][dir][:,b] >
   rc = rgcn_check_cuda(cudaMemsetAsync(dCcat, 0, (size_t)g->n_relw * B * 4, st), "memset(dC)");
   if (rc) return rc;
   AggLaunch a = make_agg(g->by_dst, H, d, d, nullptr, nullptr);
   rc = launch_basis_dc(a, dAgg, B, g->n_relw, dCcat, st);
   if (rc) return rc;
+  MARK("basis_dC");
   rc = rgcn_check_cuda(cudaMemcpyAsync(dCf, dCcat, (size_t)R * B * 4, cudaMemcpyDeviceToDevice, st), "copy dCf");
   if (!rc) rc = rgcn_check_cuda(cudaMemcpyAsync(dCb, dCcat + (size_t)R * B, (size_t)R * B * 4, cudaMemcpyDeviceToDevice, st), "copy dCb");
   if (rc) return rc;
@@ -742,9 +751,12 @@ extern "C" int rgcn_basis_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   AggLaunch as = make_agg(g->by_src, G, d, d, nullptr, nullptr);
   rc = launch_basis_agg(as, Ccat, B, g->n_relw, /*layout=*/1, P, st);
   if (rc) return rc;
+  MARK("basis_agg_dH");
   rc = gemm_any(h, split_ws, false, true, g->V_src, d, dB, 1.f, P, 2 * dB, Vf, dB, 1.f, dH, d);
   if (rc) return rc;
-  return gemm_any(h, split_ws, false, true, g->V_src, d, dB, 1.f, P + dB, 2 * dB, Vb, dB, 1.f, dH, d);
+  rc = gemm_any(h, split_ws, false, true, g->V_src, d, dB, 1.f, P + dB, 2 * dB, Vb, dB, 1.f, dH, d);
+  MARK("basis_gemms_dH");
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

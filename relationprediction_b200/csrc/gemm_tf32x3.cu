@@ -143,17 +143,15 @@ __global__ void __launch_bounds__(N_THREADS, 1)
 
   if (warp < MMA_WARP) {
     // ================= producers =================
+    // Software-pipelined: while block kb is converted and stored, the global loads of A(kb+1) are
+    // already in flight in registers and the async copies of B(kb+1) in the next smem stage.
     const int c = tid & 7;        // 16 B chunk within the 128 B K-row
     const int rbase = tid >> 3;   // 0..31
-    for (int kb = 0; kb < num_kb; ++kb) {
+    auto issue_b = [&](int kb) {
       const int s = kb % STAGES;
-      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-      mbar_wait(&empty_bar[s], ph ^ 1u);
-      const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES;
-      const uint32_t b_hi = a_lo + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
+      const uint32_t b_hi = smem_base + s * STAGE_BYTES + 2 * TILE_BYTES, b_lo = b_hi + TILE_BYTES;
       const int col = kb * BK + c * 4;
       const bool col_ok = col < K;  // K % 4 == 0: a 16 B chunk is entirely valid or entirely padding
-      // B tiles: pre-split, K-major -> straight async copies (zero-filled outside the matrix)
 #pragma unroll
       for (int i = 0; i < BN / 32; ++i) {
         const int r = rbase + 32 * i;
@@ -163,8 +161,10 @@ __global__ void __launch_bounds__(N_THREADS, 1)
         cp_async16(b_lo + swz(r, c), Blo + off, ok ? 16u : 0u);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      // A tile: fp32 -> (hi, lo) in registers
-      float4 v[BM / 32];
+    };
+    auto load_a = [&](int kb, float4 (&v)[BM / 32]) {
+      const int col = kb * BK + c * 4;
+      const bool col_ok = col < K;
 #pragma unroll
       for (int i = 0; i < BM / 32; ++i) {
         const int r = rbase + 32 * i;
@@ -172,14 +172,30 @@ __global__ void __launch_bounds__(N_THREADS, 1)
                    ? __ldg(reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + col))
                    : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    };
+    float4 vcur[BM / 32], vnext[BM / 32];
+    mbar_wait(&empty_bar[0], 1u);
+    issue_b(0);
+    load_a(0, vcur);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      const bool more = kb + 1 < num_kb;
+      if (more) {
+        const int s1 = (kb + 1) % STAGES;
+        const uint32_t ph1 = (uint32_t)((kb + 1) / STAGES) & 1u;
+        mbar_wait(&empty_bar[s1], ph1 ^ 1u);
+        issue_b(kb + 1);
+        load_a(kb + 1, vnext);
+      }
+      const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES;
 #pragma unroll
       for (int i = 0; i < BM / 32; ++i) {
         const int r = rbase + 32 * i;
         float4 hi, lo;
-        split_tf32(v[i].x, hi.x, lo.x);
-        split_tf32(v[i].y, hi.y, lo.y);
-        split_tf32(v[i].z, hi.z, lo.z);
-        split_tf32(v[i].w, hi.w, lo.w);
+        split_tf32(vcur[i].x, hi.x, lo.x);
+        split_tf32(vcur[i].y, hi.y, lo.y);
+        split_tf32(vcur[i].z, hi.z, lo.z);
+        split_tf32(vcur[i].w, hi.w, lo.w);
         const uint32_t o = swz(r, c);
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + o), "f"(hi.x), "f"(hi.y),
                      "f"(hi.z), "f"(hi.w)
@@ -188,9 +204,14 @@ __global__ void __launch_bounds__(N_THREADS, 1)
                      "f"(lo.z), "f"(lo.w)
                      : "memory");
       }
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (more)
+        asm volatile("cp.async.wait_group 1;" ::: "memory");  // B(kb) has landed, B(kb+1) may still fly
+      else
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core
       mbar_arrive(&full_bar[s]);
+#pragma unroll
+      for (int i = 0; i < BM / 32; ++i) vcur[i] = vnext[i];
     }
     // ================= epilogue =================
     mbar_wait(&accum_bar, 0);
@@ -344,16 +365,11 @@ __global__ void __launch_bounds__(N_THREADS, 1)
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp < MMA_WARP) {
-    // producers: chunk id = tid + 128 i -> tile row kr = id / 32 (0..31), 16 B chunk cm = id % 32 of the
-    // 512-byte (128 floats) MN extent
-    for (int kbi = 0; kbi < num_kb; ++kbi) {
-      const int s = kbi % STAGES;
-      const uint32_t ph = (uint32_t)(kbi / STAGES) & 1u;
-      mbar_wait(&empty_bar[s], ph ^ 1u);
-      const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES;
-      const uint32_t b_hi = a_lo + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
+    // producers: chunk id = tid + 256 i -> tile row kr = id / 32 (0..31), 16 B chunk cm = id % 32 of the
+    // 512-byte (128 floats) MN extent.  Software-pipelined like the NT kernel: the loads of block kb+1
+    // are in flight while block kb is split and stored.
+    auto load_ab = [&](int kbi, float4 (&va)[4], float4 (&vb)[4]) {
       const int k0 = (kb_begin + kbi) * BK;
-      float4 va[4], vb[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int id = tid + N_PRODUCERS * i;
@@ -367,6 +383,16 @@ __global__ void __launch_bounds__(N_THREADS, 1)
                     ? __ldg(reinterpret_cast<const float4*>(B + (size_t)krow * ldb + n0 + 4 * cm))
                     : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    };
+    float4 va[4], vb[4], van[4], vbn[4];
+    load_ab(0, va, vb);
+    for (int kbi = 0; kbi < num_kb; ++kbi) {
+      const int s = kbi % STAGES;
+      const uint32_t ph = (uint32_t)(kbi / STAGES) & 1u;
+      if (kbi + 1 < num_kb) load_ab(kbi + 1, van, vbn);
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES;
+      const uint32_t b_hi = a_lo + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int id = tid + N_PRODUCERS * i;
@@ -394,6 +420,11 @@ __global__ void __launch_bounds__(N_THREADS, 1)
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(&full_bar[s]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        va[i] = van[i];
+        vb[i] = vbn[i];
+      }
     }
     // epilogue: add this split's tile into C
     mbar_wait(&accum_bar, 0);

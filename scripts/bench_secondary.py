@@ -102,8 +102,17 @@ def layer_case(name, V, R, E, d, B, variant, skewed):
     ms = timeit(step, n=10)
     with torch.no_grad():
         ms_f = timeit(lambda: f(), n=10)
+    _lib.profile_enable(True)
+    acc = {}
+    for _ in range(5):
+        flush.zero_()
+        step()
+        torch.cuda.synchronize()
+        for nm, v in _lib.profile_read():
+            acc[nm] = acc.get(nm, 0.0) + v / 5
+    _lib.profile_enable(False)
     out[name] = {"V": V, "R": R, "E": E, "d": d, "B": B, "variant": variant, "fwd_ms": ms_f, "fwd_bwd_ms": ms,
-                 "M_edges_per_s": E / ms / 1e3}
+                 "M_edges_per_s": E / ms / 1e3, "stages_ms": {k: round(v, 4) for k, v in acc.items()}}
 
 
 layer_case("wn18_basis_B2_d200 (BASELINE configs[2])", 40943, 18, 141442, 200, 2, "basis", True)
