@@ -474,7 +474,7 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
     if (rc) return rc;
   }
   MARK("block_dW");
-  rc = launch_block_unlayout(dWt, R, B, s, dWf, dWb, 0, st);
+  rc = launch_block_unlayout(dWt, R, B, s, dWf, dWb, 0, fused ? 1 : 0, st);
   MARK("block_unlayout");
   return rc;
 }
@@ -596,7 +596,7 @@ extern "C" int rgcn_block_aggregate_backward(const rgcn_graph_t* g, int32_t d, i
     if (rc) return rc;
   }
   MARK("block_aggregate_bwd");
-  return launch_block_unlayout(dWt, R, B, s, dWf, dWb, accumulate_dW, st);
+  return launch_block_unlayout(dWt, R, B, s, dWf, dWb, accumulate_dW, fused ? 1 : 0, st);
 }
 
 // ------------------------------------------------------------------------------------------------

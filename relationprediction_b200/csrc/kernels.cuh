@@ -53,7 +53,7 @@ int launch_block_relayout(const float* Wf, const float* Wb, int R, int B, int s,
                           float* Wt, cudaStream_t st);
 // inverse of transpose=0 layout: dW[w][b][i][j] = dWt[w][j][b*s+i]
 int launch_block_unlayout(const float* dWt, int R, int B, int s, float* dWf, float* dWb,
-                          int accumulate, cudaStream_t st);
+                          int accumulate, int table_t, cudaStream_t st);
 
 // Basis aggregation: Agg[row][dir][...] = sum_m norm_m * C[relw_m, b] * X[nbr_m, k]
 //   layout 0 (interleaved): index k*B + b      (matches V.reshape(d_in*B, d_out) rows)

@@ -384,17 +384,19 @@ __global__ void __launch_bounds__(RGCN_THREADS, (FUSE_DW || S * NV > 16) ? 1 : (
                 const float* __restrict__ X, int ldx, int d, const float* __restrict__ Wt,
                 float* __restrict__ out, const float* __restrict__ Hrow, int ldh,
                 float* __restrict__ dWt) {
-  // FUSE_DW (backward pass only: X = G, rows = sources): the same walk also produces the block
-  // weight gradient  dWt[w][j][col] += (sum_run norm*G[dst])[col] * H[row][block(col)+j],
-  // so the separate dW pass (and its second round of gathers) disappears.
+  // FUSE_DW (backward pass only: X = G, rows = sources, Wt = the TRANSPOSED table): the same walk also
+  // produces the block weight gradient.  With g = sum_run norm*G[dst] and h = H[row]:
+  //   dH[row][b*s+j] += sum_i W[b][i][j] g[b*s+i]     (the transform: lane owns column b*s+j, reads g from smem)
+  //   dW[b][i][j]    += g[b*s+i] * h[b*s+j]           (same g values from smem, h quad in registers)
+  // so the gradient accumulates in the transposed-table layout dWt[w][i][b*s+j] with NO extra shared
+  // memory traffic, and the separate dW pass (a second round of gathers) disappears.
   static_assert(S > 0, "rel-major kernel needs a compile-time block size");
-  __shared__ __align__(16) float xbuf_all[RGCN_WARPS_PER_BLOCK][(FUSE_DW ? 2 : 1) * NV * 128];
+  __shared__ __align__(16) float xbuf_all[RGCN_WARPS_PER_BLOCK][NV * 128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * RGCN_WARPS_PER_BLOCK + warp;
   if (item >= n_items) return;
   const int c0 = blockIdx.y * (NV * 128);
   float* xbuf = xbuf_all[warp];
-  float* hbuf = xbuf + NV * 128;
   const int4 itv = __ldg(reinterpret_cast<const int4*>(items) + item);
   const int beg = itv.x, end = itv.y, w = itv.z;
 
@@ -424,10 +426,7 @@ __global__ void __launch_bounds__(RGCN_THREADS, (FUSE_DW || S * NV > 16) ? 1 : (
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int lc = 4 * (lane + 32 * k);
-      if (c0 + lc < d) {
-        *reinterpret_cast<float4*>(xbuf + lc) = xs[k];
-        if (FUSE_DW) *reinterpret_cast<float4*>(hbuf + lc) = hcur[k];
-      }
+      if (c0 + lc < d) *reinterpret_cast<float4*>(xbuf + lc) = xs[k];
     }
     __syncwarp();
     float* po = out + (size_t)row * d + c0;
@@ -439,19 +438,22 @@ __global__ void __launch_bounds__(RGCN_THREADS, (FUSE_DW || S * NV > 16) ? 1 : (
 #pragma unroll
         for (int j = 0; j < S; ++j) {
           if (S % 4 == 0) {
-            fma4(y, xbuf[xo[k][0] + j], wreg[j][k]);
-            if (FUSE_DW) fma4(acc[FUSE_DW ? j : 0][k], hbuf[xo[k][0] + j], xs[k]);
+            const float xv = xbuf[xo[k][0] + j];
+            fma4(y, xv, wreg[j][k]);
+            if (FUSE_DW) fma4(acc[FUSE_DW ? j : 0][k], xv, hcur[k]);
           } else {
-            y.x = fmaf(wreg[j][k].x, xbuf[xo[k][0] + j], y.x);
-            y.y = fmaf(wreg[j][k].y, xbuf[xo[k][1] + j], y.y);
-            y.z = fmaf(wreg[j][k].z, xbuf[xo[k][2] + j], y.z);
-            y.w = fmaf(wreg[j][k].w, xbuf[xo[k][3] + j], y.w);
+            const float x0 = xbuf[xo[k][0] + j], x1 = xbuf[xo[k][1] + j];
+            const float x2 = xbuf[xo[k][2] + j], x3 = xbuf[xo[k][3] + j];
+            y.x = fmaf(wreg[j][k].x, x0, y.x);
+            y.y = fmaf(wreg[j][k].y, x1, y.y);
+            y.z = fmaf(wreg[j][k].z, x2, y.z);
+            y.w = fmaf(wreg[j][k].w, x3, y.w);
             if (FUSE_DW) {
               float4& a = acc[FUSE_DW ? j : 0][k];
-              a.x = fmaf(xs[k].x, hbuf[xo[k][0] + j], a.x);
-              a.y = fmaf(xs[k].y, hbuf[xo[k][1] + j], a.y);
-              a.z = fmaf(xs[k].z, hbuf[xo[k][2] + j], a.z);
-              a.w = fmaf(xs[k].w, hbuf[xo[k][3] + j], a.w);
+              a.x = fmaf(x0, hcur[k].x, a.x);
+              a.y = fmaf(x1, hcur[k].y, a.y);
+              a.z = fmaf(x2, hcur[k].z, a.z);
+              a.w = fmaf(x3, hcur[k].w, a.w);
             }
           }
         }
@@ -546,7 +548,6 @@ __global__ void __launch_bounds__(RGCN_THREADS, FUSE_DW ? 2 : 3)
   constexpr int GROUPS = RGCN_WARPS_PER_BLOCK / G;
   constexpr int U = FUSE_DW ? 2 : 4;              // rows in flight per lane
   __shared__ __align__(16) float xbuf_all[GROUPS][2][512];
-  __shared__ __align__(16) float hbuf_all[FUSE_DW ? GROUPS : 1][2][512];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gi = warp / G, g = warp % G;
   const int item = blockIdx.x * GROUPS + gi;
@@ -577,13 +578,9 @@ __global__ void __launch_bounds__(RGCN_THREADS, FUSE_DW ? 2 : 3)
 
   auto flush = [&](int row) {
     float* xb = xbuf_all[gi][par];
-    float* hb = hbuf_all[FUSE_DW ? gi : 0][par];
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      if (colq[k] < d) {
-        *reinterpret_cast<float4*>(xb + colq[k]) = xs[k];
-        if (FUSE_DW) *reinterpret_cast<float4*>(hb + colq[k]) = hcur[k];
-      }
+      if (colq[k] < d) *reinterpret_cast<float4*>(xb + colq[k]) = xs[k];
     }
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * G) : "memory");
     float* po = out + (size_t)row * d;
@@ -593,16 +590,18 @@ __global__ void __launch_bounds__(RGCN_THREADS, FUSE_DW ? 2 : 3)
         float4 y = zero4();
 #pragma unroll
         for (int j = 0; j < S; ++j) {
-          y.x = fmaf(wreg[j][k].x, xb[xo[k][0] + j], y.x);
-          y.y = fmaf(wreg[j][k].y, xb[xo[k][1] + j], y.y);
-          y.z = fmaf(wreg[j][k].z, xb[xo[k][2] + j], y.z);
-          y.w = fmaf(wreg[j][k].w, xb[xo[k][3] + j], y.w);
-          if (FUSE_DW) {
+          const float x0 = xb[xo[k][0] + j], x1 = xb[xo[k][1] + j];
+          const float x2 = xb[xo[k][2] + j], x3 = xb[xo[k][3] + j];
+          y.x = fmaf(wreg[j][k].x, x0, y.x);
+          y.y = fmaf(wreg[j][k].y, x1, y.y);
+          y.z = fmaf(wreg[j][k].z, x2, y.z);
+          y.w = fmaf(wreg[j][k].w, x3, y.w);
+          if (FUSE_DW) {  // dW[b][i=j][.] += g[b*s+i] * h[col]: same smem values, h quad in registers
             float4& a = acc[FUSE_DW ? j : 0][k];
-            a.x = fmaf(xs[k].x, hb[xo[k][0] + j], a.x);
-            a.y = fmaf(xs[k].y, hb[xo[k][1] + j], a.y);
-            a.z = fmaf(xs[k].z, hb[xo[k][2] + j], a.z);
-            a.w = fmaf(xs[k].w, hb[xo[k][3] + j], a.w);
+            a.x = fmaf(x0, hcur[k].x, a.x);
+            a.y = fmaf(x1, hcur[k].y, a.y);
+            a.z = fmaf(x2, hcur[k].z, a.z);
+            a.w = fmaf(x3, hcur[k].w, a.w);
           }
         }
         red4(po + colq[k], y);
@@ -698,8 +697,10 @@ __global__ void k_block_relayout(const float* __restrict__ Wf, const float* __re
   }
 }
 
+// table_t = 0: dWt is j-major (dWt[w][j][b*s+i]); table_t = 1: i-major (dWt[w][i][b*s+j], fused kernels)
 __global__ void k_block_unlayout(const float* __restrict__ dWt, int R, int B, int s,
-                                 float* __restrict__ dWf, float* __restrict__ dWb, int accumulate) {
+                                 float* __restrict__ dWf, float* __restrict__ dWb, int accumulate,
+                                 int table_t) {
   const int d = B * s;
   const int64_t per = (int64_t)d * s;
   const int64_t total = 2 * (int64_t)R * per;
@@ -711,7 +712,8 @@ __global__ void k_block_unlayout(const float* __restrict__ dWt, int R, int B, in
     const int b = rem / (s * s);
     const int i = (rem / s) % s;
     const int j = rem % s;
-    const float v = __ldg(dWt + ((size_t)w * s + j) * d + b * s + i);
+    const float v = table_t ? __ldg(dWt + ((size_t)w * s + i) * d + b * s + j)
+                            : __ldg(dWt + ((size_t)w * s + j) * d + b * s + i);
     float* p = (w < R) ? dWf + (size_t)w * per + rem : dWb + (size_t)(w - R) * per + rem;
     *p = accumulate ? *p + v : v;
   }
@@ -1197,9 +1199,9 @@ int launch_block_relayout(const float* Wf, const float* Wb, int R, int B, int s,
 }
 
 int launch_block_unlayout(const float* dWt, int R, int B, int s, float* dWf, float* dWb,
-                          int accumulate, cudaStream_t st) {
+                          int accumulate, int table_t, cudaStream_t st) {
   const int64_t total = 2 * (int64_t)R * B * s * s;
-  k_block_unlayout<<<grid_for(total, 256), 256, 0, st>>>(dWt, R, B, s, dWf, dWb, accumulate);
+  k_block_unlayout<<<grid_for(total, 256), 256, 0, st>>>(dWt, R, B, s, dWf, dWb, accumulate, table_t);
   return check_launch("k_block_unlayout");
 }
 
