@@ -166,9 +166,115 @@ class _OverlappedBlockLayer(torch.autograd.Function):
         return dH, dWf, dWb, dWs, None, None, None, None, None
 
 
+def _post(ops_list):
+    return dist.batch_isend_irecv(ops_list) if ops_list else []
+
+
+def ring_post_forward(sg, send_all, H_halo):
+    """Post the P-1 ring steps of the halo exchange (step k: send my rows to rank me+k, receive the rows
+    of rank me-k).  Returns one list of Work handles per step; step k's rows are usable after waiting
+    on works[k-1], so the consumer can process peer me-1's rows while peer me-2's are still in flight."""
+    p = sg.plan
+    me, P = p.rank, p.world
+    works = []
+    for k in range(1, P):
+        st, rf = (me + k) % P, (me - k) % P
+        ops_k = []
+        if p.send_counts[st]:
+            ops_k.append(dist.P2POp(dist.isend, send_all[sg.send_off[st]:sg.send_off[st + 1]], st, sg.group))
+        if p.recv_counts[rf]:
+            ops_k.append(dist.P2POp(dist.irecv, H_halo[sg.halo_off[rf]:sg.halo_off[rf + 1]], rf, sg.group))
+        works.append(_post(ops_k))
+    return works
+
+
+def ring_post_backward_step(sg, k, dX_from_rf, back):
+    """Backward ring step k: return the gradient of the rows received from rank me-k to their owner and
+    receive, from rank me+k, the gradient of the rows sent to it."""
+    p = sg.plan
+    me, P = p.rank, p.world
+    st, rf = (me + k) % P, (me - k) % P
+    ops_k = []
+    if p.recv_counts[rf]:
+        ops_k.append(dist.P2POp(dist.isend, dX_from_rf, rf, sg.group))
+    if p.send_counts[st]:
+        ops_k.append(dist.P2POp(dist.irecv, back[sg.send_off[st]:sg.send_off[st + 1]], st, sg.group))
+    return _post(ops_k)
+
+
+class _PipelinedBlockLayer(torch.autograd.Function):
+    """Sharded block layer with a PIPELINED ring halo exchange: the rows of every peer are a separate
+    transfer and a separate message sub-graph, so peer q's messages are aggregated while peer q+1's rows
+    are still crossing NVLink (forward), and every peer's halo gradients leave as soon as they are
+    computed while the next peer's are being computed (backward)."""
+
+    @staticmethod
+    def forward(ctx, H_local, Wf, Wb, Ws, sg, n_blocks, drop_mask, keep, relu):
+        p = sg.plan
+        me, P = p.rank, p.world
+        d = H_local.shape[1]
+        H_local = H_local.contiguous()
+        send_all = H_local.index_select(0, sg.send_rows)
+        H_halo = torch.empty(p.n_halo, d, dtype=H_local.dtype, device=H_local.device)
+        works = ring_post_forward(sg, send_all, H_halo)
+        with torch.no_grad():
+            out = ops._BlockLayerFn.apply(H_local, Wf, Wb, Ws, sg.graph_local, n_blocks, drop_mask, keep, False)
+        for k in range(1, P):
+            for w in works[k - 1]:
+                w.wait()
+            rf = (me - k) % P
+            if p.recv_counts[rf]:
+                ops.block_aggregate_(out, H_halo[sg.halo_off[rf]:sg.halo_off[rf + 1]], Wf, Wb,
+                                     sg.graph_halo_peer[rf], n_blocks)
+        if relu:
+            out.relu_()
+        ctx.sg, ctx.n_blocks, ctx.keep, ctx.relu, ctx.mask = sg, n_blocks, keep, relu, drop_mask
+        ctx.keep_alive = send_all
+        ctx.save_for_backward(H_local, Wf, Wb, Ws, H_halo, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        H_local, Wf, Wb, Ws, H_halo, out = ctx.saved_tensors
+        sg, B = ctx.sg, ctx.n_blocks
+        p = sg.plan
+        me, P = p.rank, p.world
+        G = ((dOut * (out > 0)) if ctx.relu else dOut).contiguous()
+        d = G.shape[1]
+        back = torch.empty(int(p.send_counts.sum()), d, dtype=G.dtype, device=G.device)
+        works, alive = [], []
+        dWf = dWb = None
+        for k in range(1, P):
+            rf = (me - k) % P
+            dX = None
+            if p.recv_counts[rf]:
+                dX, dWf, dWb = ops.block_aggregate_backward(H_halo[sg.halo_off[rf]:sg.halo_off[rf + 1]], Wf, Wb, G,
+                                                            sg.graph_halo_peer[rf], B, dWf, dWb)
+                alive.append(dX)
+            works.append(ring_post_backward_step(sg, k, dX, back))
+        lib = ops._lib.load()
+        dH = torch.empty_like(H_local)
+        dWf_l, dWb_l, dWs = torch.empty_like(Wf), torch.empty_like(Wb), torch.empty_like(Ws)
+        nb = lib.rgcn_block_workspace_bytes(sg.graph_local.handle, d, B, 1)
+        ws = ops._workspace(nb, G.device)
+        rc = lib.rgcn_block_backward(sg.graph_local.handle, d, B, ops._ptr(H_local), ops._ptr(Wf), ops._ptr(Wb),
+                                     ops._ptr(Ws), ops._ptr(ctx.mask), float(ctx.keep), 0, ops._ptr(out),
+                                     ops._ptr(G), ops._ptr(dH), ops._ptr(dWf_l), ops._ptr(dWb_l), ops._ptr(dWs),
+                                     ops._ptr(ws), ws.numel(), ops._stream(G.device))
+        ops._lib.check(rc, "rgcn_block_backward")
+        if dWf is not None:
+            dWf_l += dWf
+            dWb_l += dWb
+        for wk in works:
+            for w in wk:
+                w.wait()
+        dH.index_add_(0, sg.send_rows, back)
+        return dH, dWf_l, dWb_l, dWs, None, None, None, None, None
+
+
 class ShardedGraph(object):
     def __init__(self, triples, n_nodes, n_relations, rank, world, device, norm_mode="canonical",
-                 norm_f=None, norm_b=None, group=None, overlap=True):
+                 norm_f=None, norm_b=None, group=None, overlap=True, pipelined=None):
         self.plan = ShardPlan(triples, n_nodes, n_relations, rank, world, norm_mode, norm_f, norm_b)
         self.device = torch.device(device)
         self.group = group
@@ -180,8 +286,12 @@ class ShardedGraph(object):
         self.graph = ops.Graph.from_messages(p.msg_dst, p.msg_src, p.msg_relw, p.msg_norm, p.n_local,
                                              p.n_local + p.n_halo, 2 * n_relations, device=index)
         self.send_rows = torch.as_tensor(p.send_rows, device=self.device)
+        self.send_off = np.concatenate([[0], np.cumsum(p.send_counts)]).astype(np.int64).tolist()
+        self.halo_off = np.concatenate([[0], np.cumsum(p.recv_counts)]).astype(np.int64).tolist()
         # split by source locality so the halo exchange can overlap the local-source work
         self.overlap = overlap and world > 1
+        # per-peer ring pipeline (default from 3 ranks up; with 2 ranks it degenerates to the single exchange)
+        self.pipelined = self.overlap and (world >= 3 if pipelined is None else bool(pipelined))
         if self.overlap:
             loc = p.msg_src < p.n_local
             self.graph_local = ops.Graph.from_messages(p.msg_dst[loc], p.msg_src[loc], p.msg_relw[loc],
@@ -191,12 +301,26 @@ class ShardedGraph(object):
             self.graph_halo = ops.Graph.from_messages(p.msg_dst[rem], p.msg_src[rem] - p.n_local, p.msg_relw[rem],
                                                       p.msg_norm[rem], p.n_local, max(p.n_halo, 0),
                                                       2 * n_relations, device=index)
+            self.graph_halo_peer = {}
+            if self.pipelined:
+                hsrc = p.msg_src - p.n_local  # halo-row index of every remote-source message
+                for q in range(world):
+                    lo_q, hi_q = self.halo_off[q], self.halo_off[q + 1]
+                    if q == rank or hi_q == lo_q:
+                        continue
+                    sel = rem & (hsrc >= lo_q) & (hsrc < hi_q)
+                    self.graph_halo_peer[q] = ops.Graph.from_messages(
+                        p.msg_dst[sel], hsrc[sel] - lo_q, p.msg_relw[sel], p.msg_norm[sel], p.n_local,
+                        hi_q - lo_q, 2 * n_relations, device=index)
 
     def halo_exchange(self, H_local):
         return _HaloExchange.apply(H_local, self.plan, self.send_rows, self.group)
 
     def block_layer(self, H_local, W_forward, W_backward, W_self, n_blocks, drop_mask=None, keep=1.0,
                     relu=True):
+        if self.pipelined and self.device.type == "cuda":
+            return _PipelinedBlockLayer.apply(H_local, W_forward, W_backward, W_self, self, int(n_blocks),
+                                              drop_mask, keep, relu)
         if self.overlap and self.device.type == "cuda":
             return _OverlappedBlockLayer.apply(H_local, W_forward, W_backward, W_self, self, int(n_blocks),
                                                drop_mask, keep, relu)

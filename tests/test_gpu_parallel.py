@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, V, R, E, d, B, out_dir, overlap):
+def _worker(rank, world, port, V, R, E, d, B, out_dir, mode):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -31,7 +31,9 @@ def _worker(rank, world, port, V, R, E, d, B, out_dir, overlap):
     try:
         from relationprediction_b200 import parallel
         tr = synthetic_kg(V, R, E, seed=5, skewed=True)
-        sg = parallel.ShardedGraph(tr, V, R, rank, world, dev, overlap=overlap)
+        sg = parallel.ShardedGraph(tr, V, R, rank, world, dev, overlap=(mode != "plain"),
+                                   pipelined=(mode == "pipelined"))
+        assert sg.pipelined == (mode == "pipelined")
         p = sg.plan
         g = torch.Generator().manual_seed(0)
         s = d // B
@@ -51,14 +53,14 @@ def _worker(rank, world, port, V, R, E, d, B, out_dir, overlap):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("overlap", [True, False], ids=["overlapped-halo", "plain-halo"])
-@pytest.mark.parametrize("world", [2])
-def test_sharded_block_layer_equals_single_gpu(tmp_path, world, overlap):
+@pytest.mark.parametrize("mode", ["pipelined", "overlapped", "plain"])
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_block_layer_equals_single_gpu(tmp_path, world, mode):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     from relationprediction_b200 import ops
     V, R, E, d, B = 3000, 11, 40000, 500, 100
-    mp.spawn(_worker, args=(world, _free_port(), V, R, E, d, B, str(tmp_path), overlap), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), V, R, E, d, B, str(tmp_path), mode), nprocs=world, join=True)
     tr = synthetic_kg(V, R, E, seed=5, skewed=True)
     g = torch.Generator().manual_seed(0)
     s = d // B

@@ -98,3 +98,62 @@ def test_halo_exchange_world2_gloo(tmp_path):
     for rank in range(world):
         got = np.load(tmp_path / ("grad_%d.npy" % rank))
         np.testing.assert_allclose(got, expect[bounds[rank]:bounds[rank + 1]], rtol=1e-6)
+
+
+def _ring_worker(rank, world, port, V, R, E, d, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        tr = synthetic_kg(V, R, E, seed=8, skewed=True)
+        sg = parallel.ShardedGraph(tr, V, R, rank, world, "cpu", pipelined=True)
+        p = sg.plan
+        assert sg.pipelined and set(sg.graph_halo_peer) == {q for q in range(world) if q != rank and p.recv_counts[q]}
+        # per-peer halo sub-graphs partition the remote-source messages
+        assert sum(g.M for g in sg.graph_halo_peer.values()) == sg.graph_halo.M
+        g = torch.Generator().manual_seed(0)
+        H = torch.randn(V, d, generator=g)
+        H_local = H[p.lo:p.hi].contiguous()
+        send_all = H_local.index_select(0, sg.send_rows)
+        H_halo = torch.empty(p.n_halo, d)
+        works = parallel.ring_post_forward(sg, send_all, H_halo)
+        for k in range(1, world):
+            for w in works[k - 1]:
+                w.wait()
+            rf = (rank - k) % world
+            lo, hi = sg.halo_off[rf], sg.halo_off[rf + 1]
+            # after step k exactly the rows of rank me-k are guaranteed to be there
+            assert torch.equal(H_halo[lo:hi], H[torch.as_tensor(p.halo_nodes[lo:hi].astype(np.int64))])
+        # backward ring: gradient of halo row (global id v) coming from rank r is (r+1) * (v+1)
+        back = torch.zeros(int(p.send_counts.sum()), d)
+        wl, alive = [], []
+        for k in range(1, world):
+            rf = (rank - k) % world
+            lo, hi = sg.halo_off[rf], sg.halo_off[rf + 1]
+            dX = None
+            if hi > lo:
+                dX = ((rank + 1) * (torch.as_tensor(p.halo_nodes[lo:hi].astype(np.float32)) + 1))[:, None] * torch.ones(d)
+                alive.append(dX)
+            wl.append(parallel.ring_post_backward_step(sg, k, dX, back))
+        for wk in wl:
+            for w in wk:
+                w.wait()
+        dH = torch.zeros(p.n_local, d)
+        dH.index_add_(0, sg.send_rows, back)
+        np.save(os.path.join(out_dir, "ring_%d.npy" % rank), dH.numpy())
+        np.save(os.path.join(out_dir, "halo_%d.npy" % rank), p.halo_nodes)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pipelined_ring_exchange_world3_gloo(tmp_path):
+    V, R, E, d, world = 300, 5, 2500, 6, 3
+    mp.spawn(_ring_worker, args=(world, _free_port(), V, R, E, d, str(tmp_path)), nprocs=world, join=True)
+    expect = np.zeros((V, d), np.float32)
+    for r in range(world):
+        halo = np.load(tmp_path / ("halo_%d.npy" % r))
+        expect[halo] += ((r + 1) * (halo.astype(np.float32) + 1))[:, None]
+    bounds = parallel.node_bounds(V, world)
+    for r in range(world):
+        got = np.load(tmp_path / ("ring_%d.npy" % r))
+        np.testing.assert_allclose(got, expect[bounds[r]:bounds[r + 1]], rtol=1e-6)
