@@ -290,8 +290,10 @@ class ShardedGraph(object):
         self.halo_off = np.concatenate([[0], np.cumsum(p.recv_counts)]).astype(np.int64).tolist()
         # split by source locality so the halo exchange can overlap the local-source work
         self.overlap = overlap and world > 1
-        # per-peer ring pipeline (default from 3 ranks up; with 2 ranks it degenerates to the single exchange)
-        self.pipelined = self.overlap and (world >= 3 if pipelined is None else bool(pipelined))
+        # per-peer ring pipeline: opt-in.  Measured on 4 / 8 B200 (FB15k-237 shape, weak scaling) it LOSES to
+        # the single overlapped all-to-all (2.15 / 5.69 ms vs 1.84 / 2.40 ms per step): P-1 small sub-graph
+        # launches and NCCL groups per direction cost more than the exposed transfer they hide.
+        self.pipelined = self.overlap and bool(pipelined)
         if self.overlap:
             loc = p.msg_src < p.n_local
             self.graph_local = ops.Graph.from_messages(p.msg_dst[loc], p.msg_src[loc], p.msg_relw[loc],
