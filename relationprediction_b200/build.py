@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
                 return LIB
     cuda_home = os.path.dirname(os.path.dirname(_nvcc()))
     cmd = [
-        _nvcc(), "-shared", "-Xcompiler", "-fPIC", "-O3", "-std=c++17", "-lineinfo",
+        _nvcc(), "-shared", "-Xcompiler", "-fPIC", "-O3", "-std=c++17", "-lineinfo", "--threads", "0",
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-I", os.path.join(HERE, "..", "include"),
     ]
