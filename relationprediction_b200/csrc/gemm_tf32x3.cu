@@ -365,15 +365,15 @@ __global__ void __launch_bounds__(N_THREADS, 1)
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp < MMA_WARP) {
-    // producers: chunk id = tid + 256 i -> tile row kr = id / 32 (0..31), 16 B chunk cm = id % 32 of the
-    // 512-byte (128 floats) MN extent.  Software-pipelined like the NT kernel: the loads of block kb+1
-    // are in flight while block kb is split and stored.
+    // producers: thread -> (k-row tid / 8, 16 B chunk tid % 8) of MN block i (i = 0..3).  Software-
+    // pipelined like the NT kernel: the loads of block kb+1 are in flight while block kb is split and stored.
     auto load_ab = [&](int kbi, float4 (&va)[4], float4 (&vb)[4]) {
       const int k0 = (kb_begin + kbi) * BK;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int id = tid + N_PRODUCERS * i;
-        const int kr = id >> 5, cm = id & 31;
+        // chunk id: MN block (32 floats) = i, k-row = tid / 8, 16 B chunk within the 128 B row = tid % 8:
+        // a warp touches 4 consecutive k-rows x 128 B = one contiguous, conflict-free 512 B of the tile
+        const int kr = tid >> 3, cm = 8 * i + (tid & 7);
         const int krow = k0 + kr;
         const bool kok = krow < K;
         va[i] = (kok && (m0 + 4 * cm < M))
@@ -395,8 +395,7 @@ __global__ void __launch_bounds__(N_THREADS, 1)
       const uint32_t b_hi = a_lo + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int id = tid + N_PRODUCERS * i;
-        const int kr = id >> 5, cm = id & 31;
+        const int kr = tid >> 3, cm = 8 * i + (tid & 7);
         const int c8 = cm & 7;  // 16 B chunk within the 128 B row: 32 B chunk (c8 >> 1) is swizzled with k & 3
         const uint32_t off = (uint32_t)((cm >> 3) * 4096 + (kr >> 2) * 512 + (kr & 3) * 128 +
                                         ((((c8 >> 1) ^ (kr & 3)) << 5) | ((c8 & 1) << 4)));

@@ -34,3 +34,38 @@ def test_negative_sampler_matches_reference_stream():
     np.testing.assert_array_equal(idx, g["idx"])
     np.testing.assert_array_equal(lab, g["labels"])
     assert idx.dtype == np.int32 and lab.dtype == np.float32
+
+
+def test_train_driver_host_helpers(toy, tmp_path):
+    from relationprediction_b200 import train as driver
+    from relationprediction_b200.common import settings_reader
+    ent = {int(k): v for k, v in toy["entities"].items()}
+    rel = {int(k): v for k, v in toy["relations"].items()}
+    (tmp_path / "entities.dict").write_text("".join("%d\t%s\n" % kv for kv in sorted(ent.items())))
+    (tmp_path / "relations.dict").write_text("".join("%d\t%s\n" % kv for kv in sorted(rel.items())))
+    for split in ("train", "valid", "test"):
+        (tmp_path / (split + ".txt")).write_text(
+            "".join("%s\t%s\t%s\n" % (ent[s], rel[r], ent[o]) for s, r, o in toy[split]))
+    splits, entities, relations = driver.load_dataset(str(tmp_path))
+    assert splits["train"].tolist() == toy["train"] and len(entities) == 16 and len(relations) == 9
+    # section merge exactly like train.py:69-86
+    s = driver.merge_settings(settings_reader.read_string(toy["settings_text"]["gcn_block.exp"]), 16, 9, 43)
+    assert s["Encoder"]["EntityCount"] == 16 and s["Encoder"]["CodeDimension"] == "500"
+    assert s["Decoder"]["NegativeSampleRate"] == "10" and s["Optimizer"]["GraphBatchSize"] == "30000"
+    assert s["Evaluation"]["EdgeCount"] == 43
+    # neighbourhood-expansion sampler: distinct edge ids, grows from seen vertices (train.py:161-198)
+    train = splits["train"]
+    adj = [[] for _ in range(16)]
+    for i, (a, _, b) in enumerate(train.tolist()):
+        adj[a].append((i, b))
+        adj[b].append((i, a))
+    deg = np.array([len(a) for a in adj])
+    np.random.seed(1)
+    ids = driver.sample_edge_neighborhood(adj, deg, len(train), 20)
+    assert len(set(ids.tolist())) == 20 and ids.min() >= 0 and ids.max() < 43
+    touched = set()
+    for k, e in enumerate(ids.tolist()):
+        a, _, b = train[e]
+        if k > 0:
+            assert a in touched or b in touched   # every later edge touches an already seen vertex
+        touched.update((int(a), int(b)))
