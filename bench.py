@@ -461,6 +461,44 @@ def main():
                                 "the 126 MB L2 (H = %.0f MB here) frac can exceed 1" % (V * d * 4 / 1e6),
                         "all": {k: {"ms": mine[k], "GB/s": alg[k] / (mine[k] * 1e-3) / 1e9} for k in mine}}
 
+    if world > 1:
+        # per-stage times of rank 0's shard (local-source graph + halo-source graph) and the roofline of its
+        # dominant kernel; guarded: a failure here must never cost the scaling run its bench line
+        try:
+            if rank == 0:
+                _lib.profile_enable(True)
+            acc = {}
+            n_prof = 5
+            for _ in range(n_prof):
+                flush_buf.zero_()
+                step()
+                torch.cuda.synchronize()
+                if rank == 0:
+                    for name, ms in _lib.profile_read():
+                        acc[name] = acc.get(name, 0.0) + ms / n_prof
+            if rank == 0:
+                _lib.profile_enable(False)
+                stages = {k: round(v, 5) for k, v in acc.items()}
+                M_loc = layer.graph_local.M if layer.overlap else layer.graph.M
+                M_halo = layer.graph_halo.M if layer.overlap else 0
+                wt_bytes = 2 * R * s * d * 4
+                alg = {"block_agg_fwd": M_loc * (4 * d + 12) + 8 * V_loc * d + wt_bytes,
+                       "block_aggregate": M_halo * (4 * d + 12) + 4 * V_loc * d + wt_bytes,
+                       "block_agg_dH": M_loc * (8 * d + 12) + 8 * V_loc * d + 2 * wt_bytes,
+                       "block_aggregate_bwd": M_halo * (8 * d + 12) + 4 * layer.n_halo * d + 2 * wt_bytes}
+                mine = {k: v for k, v in acc.items() if k in alg and v > 0}
+                if mine:
+                    top = max(mine, key=mine.get)
+                    peak, peak_src = peaks()
+                    achieved = alg[top] / (mine[top] * 1e-3) / 1e9
+                    roofline = {"kernel": top + " (rank 0 shard)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                                "algorithmic_bytes": int(alg[top]), "kernel_ms": mine[top], "peak_source": peak_src,
+                                "all": {k: {"ms": mine[k], "GB/s": alg[k] / (mine[k] * 1e-3) / 1e9} for k in mine}}
+        except Exception as exc:  # noqa: BLE001
+            roofline, stages = None, {"error": repr(exc)}
+        sync_all()
+
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         spec1 = workload_spec(args, 1)
