@@ -468,15 +468,14 @@ def main():
             if rank == 0:
                 _lib.profile_enable(True)
             acc = {}
-            n_prof = 5
-            for _ in range(n_prof):
+            n_prof = 4  # 17 stage marks per sharded step; the library keeps 96
+            for _ in range(n_prof):  # identical on every rank: the step contains collectives
                 flush_buf.zero_()
                 step()
-                torch.cuda.synchronize()
-                if rank == 0:
-                    for name, ms in _lib.profile_read():
-                        acc[name] = acc.get(name, 0.0) + ms / n_prof
+            torch.cuda.synchronize()
             if rank == 0:
+                for name, ms in _lib.profile_read():
+                    acc[name] = acc.get(name, 0.0) + ms / n_prof
                 _lib.profile_enable(False)
                 stages = {k: round(v, 5) for k, v in acc.items()}
                 M_loc = layer.graph_local.M if layer.overlap else layer.graph.M
