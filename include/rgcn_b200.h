@@ -70,6 +70,12 @@ int rgcn_gemm_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, i
 int rgcn_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                         int32_t M, int32_t N, int32_t K, int accumulate, void* stream);
 
+/* Host-side neighbourhood-expansion edge sampler (next row N2; train.py:161-198): writes sample_size
+ * DISTINCT edge ids.  Same stochastic process as the reference (vertex ~ unpicked-degree x seen, then a
+ * uniform unpicked incident edge), O(log V) per draw instead of O(V); its own random stream (seed). */
+int rgcn_sample_edge_neighborhood(const int32_t* triples_host, int64_t E, int32_t V, int64_t sample_size,
+                                  uint64_t seed, int32_t* out_edges_host);
+
 /* Optional per-kernel timing (bench.py roofline): when enabled, every layer entry point records a
  * CUDA event on its stream after each internal stage.  rgcn_profile_read() synchronises, writes
  * the stage durations (ms) and their '\n'-separated names, clears the log and returns the count. */

@@ -36,8 +36,24 @@ def merge_settings(settings, n_entities, n_relations, n_train):
     return settings
 
 
+def sample_edge_neighborhood_fast(triples, n_entities, sample_size):
+    """The same sampler in the library (csrc/sampler.cu): Fenwick trees instead of an O(V) np.random.choice per
+    draw (~5 s -> ~10 ms for 30 000 edges of FB15k-237); seeded from numpy's global stream."""
+    import ctypes
+
+    from . import _lib
+    tri = np.ascontiguousarray(triples, dtype=np.int32)
+    out = np.empty(sample_size, dtype=np.int32)
+    seed = int(np.random.randint(0, 2 ** 31 - 1))
+    rc = _lib.load().rgcn_sample_edge_neighborhood(ctypes.c_void_p(tri.ctypes.data), tri.shape[0], int(n_entities),
+                                                   int(sample_size), seed, ctypes.c_void_p(out.ctypes.data))
+    _lib.check(rc, "rgcn_sample_edge_neighborhood")
+    return out
+
+
 def sample_edge_neighborhood(adj_list, degrees, n_triplets, sample_size):
-    """Neighbourhood-expansion edge sampler (train.py:161-198), same sequential algorithm."""
+    """Neighbourhood-expansion edge sampler (train.py:161-198), same sequential algorithm (reference
+    restatement; kept as the statistical oracle of sample_edge_neighborhood_fast)."""
     edges = np.zeros(sample_size, dtype=np.int32)
     sample_counts = degrees.copy()
     picked = np.zeros(n_triplets, dtype=bool)
@@ -101,7 +117,7 @@ def main(argv=None):
             X, Y = ns.transform(train)
             return (X, Y)
         if 'GraphBatchSize' in general and int(general['GraphBatchSize']) < len(train):
-            ids = sample_edge_neighborhood(adj_list, degrees, len(train), int(general['GraphBatchSize']))
+            ids = sample_edge_neighborhood_fast(train, len(entities), int(general['GraphBatchSize']))
         else:
             ids = np.arange(len(train))
         graph_batch = train[ids]

@@ -69,3 +69,58 @@ def test_train_driver_host_helpers(toy, tmp_path):
         if k > 0:
             assert a in touched or b in touched   # every later edge touches an already seen vertex
         touched.update((int(a), int(b)))
+
+
+def test_library_edge_sampler_properties_and_distribution(toy):
+    """csrc/sampler.cu against the reference-restated Python sampler: hard invariants on every draw and the
+    first-edge distribution (fallback: uniform vertex with edges, then uniform incident edge) in closed form."""
+    from relationprediction_b200 import train as driver
+    train = np.array(toy["train"], dtype=np.int32)
+    E, V = len(train), 16
+    np.random.seed(5)
+    for size in (1, 10, 43):
+        ids = driver.sample_edge_neighborhood_fast(train, V, size)
+        assert len(ids) == size and len(set(ids.tolist())) == size and ids.min() >= 0 and ids.max() < E
+    # every edge after the first touches an already seen vertex (Toy's graph is connected)
+    for _ in range(50):
+        ids = driver.sample_edge_neighborhood_fast(train, V, 30)
+        touched = set()
+        for k, e in enumerate(ids.tolist()):
+            a, _, b = train[e]
+            if k:
+                assert int(a) in touched or int(b) in touched
+            touched.update((int(a), int(b)))
+    # first-edge law: P(e) = (1/#nonisolated) * (1/deg(s) + 1/deg(o))
+    deg = np.bincount(np.concatenate([train[:, 0], train[:, 2]]), minlength=V)
+    p = (1.0 / deg[train[:, 0]] + 1.0 / deg[train[:, 2]]) / (deg > 0).sum()
+    assert abs(p.sum() - 1) < 1e-12
+    n = 40000
+    firsts = np.array([driver.sample_edge_neighborhood_fast(train, V, 1)[0] for _ in range(n)])
+    freq = np.bincount(firsts, minlength=E) / n
+    assert np.abs(freq - p).max() < 4 * np.sqrt(p.max() / n) + 1e-3
+    # same summary statistic as the Python restatement: mean number of distinct vertices in a 15-edge sample
+    adj = [[] for _ in range(V)]
+    for i, (a, _, b) in enumerate(train.tolist()):
+        adj[a].append((i, b))
+        adj[b].append((i, a))
+    dg = np.array([len(a) for a in adj])
+
+    def n_vertices(ids):
+        return len(set(train[ids][:, 0].tolist()) | set(train[ids][:, 2].tolist()))
+    ref = np.mean([n_vertices(driver.sample_edge_neighborhood(adj, dg, E, 15)) for _ in range(400)])
+    fast = np.mean([n_vertices(driver.sample_edge_neighborhood_fast(train, V, 15)) for _ in range(4000)])
+    assert abs(ref - fast) < 0.35, (ref, fast)
+
+
+def test_library_edge_sampler_scale_and_self_loops():
+    import time
+    from relationprediction_b200 import train as driver
+    from conftest import synthetic_kg
+    tr = synthetic_kg(14541, 237, 272115, seed=3, skewed=True)
+    tr[:50, 2] = tr[:50, 0]   # self loops
+    t0 = time.perf_counter()
+    ids = driver.sample_edge_neighborhood_fast(tr, 14541, 30000)
+    dt = time.perf_counter() - t0
+    assert len(set(ids.tolist())) == 30000 and dt < 2.0   # the reference's numpy loop takes ~5 s
+    ids_all = driver.sample_edge_neighborhood_fast(tr, 14541, len(tr))   # exhausts every edge exactly once
+    assert sorted(ids_all.tolist()) == list(range(len(tr)))
