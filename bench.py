@@ -211,6 +211,9 @@ def main():
     ap.add_argument("--cpu-sample-edges", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (needs 4 pinned V*d buffers)")
+    ap.add_argument("--triples-npz", default=None,
+                    help="use the triples of this .npz (arrays: triples [E,3], V, R) instead of the synthetic generator; "
+                         "diagnostic only (e.g. the real FB15k-237 graph), the default bench stays synthetic")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -236,9 +239,13 @@ def main():
     spec = workload_spec(args, world)
     V, R, E, d, B = spec["V"], spec["R"], spec["E"], spec["d"], spec["B"]
     s = d // B
-    t_gen = time.perf_counter()
-    triples = synthetic_kg(V, R, E, seed=1234, skewed=spec["skewed"])
-    t_gen = time.perf_counter() - t_gen
+    if args.triples_npz:
+        z = np.load(args.triples_npz)
+        triples = np.ascontiguousarray(z["triples"], dtype=np.int32)
+        V, R, E = int(z["V"]), int(z["R"]), int(triples.shape[0])
+        spec = dict(spec, name="triples from " + os.path.basename(args.triples_npz), V=V, R=R, E=E)
+    else:
+        triples = synthetic_kg(V, R, E, seed=1234, skewed=spec["skewed"])
 
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
     if world == 1:
@@ -515,6 +522,7 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
+                "data": "synthetic" if not args.triples_npz else "file",
                 "config": {"workload": spec["name"], "V": V, "R": R, "E": E, "d": d, "B": B, "s": s,
                            "skewed": spec["skewed"], "dropout": "off (keep=1)", "relu": True,
                            "l2": "flushed between timed iterations (256 MB memset outside the event pair)",

@@ -1,10 +1,6 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -4 gpurun_out/pytest_gpu.log
-timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -2
-timeout 600 python bench.py > gpurun_out/bench_fb.json 2> gpurun_out/bench_fb.err; tail -3 gpurun_out/bench_fb.err; python scripts/show_bench.py gpurun_out/bench_fb.json
-timeout 600 python bench.py --workload synthetic --scale 0.02 --no-cpu-baseline --steps 5 > gpurun_out/bench_syn.json 2> gpurun_out/bench_syn.err; tail -3 gpurun_out/bench_syn.err; python scripts/show_bench.py gpurun_out/bench_syn.json
-timeout 600 python scripts/bench_secondary.py > gpurun_out/secondary_r1.json 2> gpurun_out/secondary.err; tail -2 gpurun_out/secondary.err
-python scripts/gemm_perf.py
+timeout 600 python bench.py --triples-npz .scratch/fb15k237_train.npz --no-cpu-baseline > gpurun_out/bench_real_fb15k237.json 2> gpurun_out/bench_real.err; tail -3 gpurun_out/bench_real.err; python scripts/show_bench.py gpurun_out/bench_real_fb15k237.json
+timeout 600 python bench.py --triples-npz .scratch/fb15k_train.npz --no-cpu-baseline --steps 100 > gpurun_out/bench_real_fb15k.json 2> gpurun_out/bench_real.err; tail -3 gpurun_out/bench_real.err; python scripts/show_bench.py gpurun_out/bench_real_fb15k.json
+RGCN_BLOCK_ALGO=0 timeout 600 python bench.py --triples-npz .scratch/fb15k237_train.npz --no-cpu-baseline --no-e2e --steps 100 > gpurun_out/bench_real_fb15k237_dstmajor.json 2> gpurun_out/bench_real.err; tail -3 gpurun_out/bench_real.err; python scripts/show_bench.py gpurun_out/bench_real_fb15k237_dstmajor.json
