@@ -76,6 +76,16 @@ int rgcn_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb
 int rgcn_sample_edge_neighborhood(const int32_t* triples_host, int64_t E, int32_t V, int64_t sample_size,
                                   uint64_t seed, int32_t* out_edges_host);
 
+/* Next row N1: global-norm clipping + Adam with TensorFlow-1.x semantics
+ * (optimization/tensorflow_backend/algorithms.py:65-68 and :36-42).  Call rgcn_sumsq_accumulate on every
+ * gradient tensor into one zeroed device float, then rgcn_adam_update on every (param, grad, m, v) with that
+ * scalar: scale = max_norm * min(1/sqrt(sumsq), 1/max_norm) (skipped when sumsq_dev is NULL or max_norm <= 0);
+ * lr_t = lr*sqrt(1-beta2^step)/(1-beta1^step); p -= lr_t * m / (sqrt(v) + eps).  step is 1-based. */
+int rgcn_sumsq_accumulate(const float* g, int64_t n, float* acc_dev, void* stream);
+int rgcn_adam_update(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                     float beta2, float eps, int64_t step, const float* sumsq_dev, float max_norm,
+                     void* stream);
+
 /* Optional per-kernel timing (bench.py roofline): when enabled, every layer entry point records a
  * CUDA event on its stream after each internal stage.  rgcn_profile_read() synchronises, writes
  * the stage durations (ms) and their '\n'-separated names, clears the log and returns the count. */

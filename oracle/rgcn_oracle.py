@@ -318,3 +318,22 @@ def layer_fwd_bwd(variant, H, triples, weights, norm_f, norm_b, dOut, drop_mask=
     grads = {n: (g if g is not None else torch.zeros_like(t))
              for n, g, t in zip(names, gs, [Ht] + list(wt.values()))}
     return out.detach(), {k: v.detach() for k, v in grads.items()}
+
+
+# --------------------------------------------------------------------------------------------
+# N1: optimizer step           optimization/tensorflow_backend/algorithms.py:36-42 and :65-68
+# (TensorFlow 1.x formulas restated: tf.clip_by_global_norm, tf.train.AdamOptimizer dense update)
+# --------------------------------------------------------------------------------------------
+def tf_clip_by_global_norm(grads, clip_norm):
+    gn = np.sqrt(sum(float((np.asarray(g, dtype=np.float64) ** 2).sum()) for g in grads))
+    scale = clip_norm * min(1.0 / gn if gn > 0 else np.inf, 1.0 / clip_norm)
+    return [np.asarray(g, dtype=np.float64) * scale for g in grads], gn
+
+
+def tf_adam_step(params, grads, ms, vs, t, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8):
+    """In place on float64 numpy arrays; t is the 1-based step count."""
+    lr_t = lr * np.sqrt(1 - beta2 ** t) / (1 - beta1 ** t)
+    for p, g, m, v in zip(params, grads, ms, vs):
+        m[...] = beta1 * m + (1 - beta1) * g
+        v[...] = beta2 * v + (1 - beta2) * g * g
+        p[...] = p - lr_t * m / (np.sqrt(v) + eps)

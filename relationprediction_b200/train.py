@@ -6,13 +6,15 @@ settings/dataset formats, the section merge (train.py:69-86), the per-step sampl
 (graph batch -> GraphSplitSize edge dropout -> negative sampling, :201-245), loss = CE + regularisation
 (:262), global-norm clipping + Adam (optimization/tensorflow_backend/algorithms.py:36-42, :65-68) and
 the periodic validation MRR follow the reference; the "Converge" optimizer stack itself is replaced by
-a plain loop.  Optimizer math runs in torch (Adam, clip): plumbing, not a kernel target."""
+a plain loop.  Clip + Adam run on the library's kernels with the TensorFlow-1.x formulas (optim.py,
+csrc/optimizer.cu)."""
 import argparse
 import os
 
 import numpy as np
 import torch
 
+from .optim import ClippedAdam
 from .common import auxilliaries, evaluation, io, model_builder, settings_reader
 
 
@@ -129,8 +131,8 @@ def main(argv=None):
     weights = [w for w in model.get_weights()]
     algo = opt['Algorithm']
     lr = float(algo['learning_rate'])
-    optimizer = torch.optim.Adam(weights, lr=lr, betas=(0.9, 0.999), eps=1e-8)
     max_norm = float(opt['MaxGradientNorm']) if 'MaxGradientNorm' in opt else None
+    optimizer = ClippedAdam(weights, lr=lr, beta1=0.9, beta2=0.999, eps=1e-8, max_norm=max_norm)
     report_every = int(opt['ReportTrainLossEvery']) if 'ReportTrainLossEvery' in opt else 100
     check_every = int(opt['EarlyStopping']['CheckEvery']) if 'EarlyStopping' in opt else None
     max_it = args.max_iterations if args.max_iterations is not None else 10 ** 9
@@ -138,11 +140,9 @@ def main(argv=None):
     running, it = 0.0, 0
     while it < max_it:
         it += 1
-        optimizer.zero_grad(set_to_none=True)
+        optimizer.zero_grad()
         loss = model.train_loss(*sample())
         loss.backward()
-        if max_norm is not None:
-            torch.nn.utils.clip_grad_norm_([w for w in weights if w.grad is not None], max_norm)
         optimizer.step()
         running += float(loss)
         if it == 1:

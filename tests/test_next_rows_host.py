@@ -124,3 +124,34 @@ def test_library_edge_sampler_scale_and_self_loops():
     assert len(set(ids.tolist())) == 30000 and dt < 2.0   # the reference's numpy loop takes ~5 s
     ids_all = driver.sample_edge_neighborhood_fast(tr, 14541, len(tr))   # exhausts every edge exactly once
     assert sorted(ids_all.tolist()) == list(range(len(tr)))
+
+
+def test_tf_adam_and_clip_restatement_agrees_with_torch():
+    """N1 oracle pin: the TF-1.x Adam / clip_by_global_norm restatement against torch's own implementations
+    (they differ only in where epsilon enters, which vanishes for eps -> 0 / large norms)."""
+    import torch
+    from oracle import rgcn_oracle as oracle
+    rng = np.random.RandomState(3)
+    shapes = [(7, 5), (11,), (3, 4, 2)]
+    ps = [rng.normal(size=s) for s in shapes]
+    tp = [torch.nn.Parameter(torch.tensor(p, dtype=torch.float64)) for p in ps]
+    ms, vs = [np.zeros(s) for s in shapes], [np.zeros(s) for s in shapes]
+    opt = torch.optim.Adam(tp, lr=0.01, betas=(0.9, 0.999), eps=1e-30)
+    for t in range(1, 6):
+        gs = [rng.normal(size=s) * 3 for s in shapes]
+        for p, g in zip(tp, gs):
+            p.grad = torch.tensor(g, dtype=torch.float64)
+        torch.nn.utils.clip_grad_norm_(tp, 1.0)
+        cl, gn = oracle.tf_clip_by_global_norm(gs, 1.0)
+        assert abs(gn - np.sqrt(sum((g ** 2).sum() for g in gs))) < 1e-12
+        for p, c in zip(tp, cl):
+            assert np.abs(p.grad.numpy() - c).max() < 1e-5      # torch divides by (norm + 1e-6)
+            p.grad = torch.tensor(c, dtype=torch.float64)
+        opt.step()
+        oracle.tf_adam_step(ps, cl, ms, vs, t, eps=1e-30)
+        for p, ref in zip(tp, ps):
+            assert np.abs(p.detach().numpy() - ref).max() < 1e-12
+    # below the threshold nothing is scaled; zero gradients stay zero
+    small = [np.full((3,), 1e-3)]
+    assert np.allclose(oracle.tf_clip_by_global_norm(small, 1.0)[0][0], small[0])
+    assert np.all(oracle.tf_clip_by_global_norm([np.zeros(4)], 1.0)[0][0] == 0)
