@@ -3,10 +3,15 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
 this module.  The product path (relationprediction_b200/) never does.
 
-PARITY STATUS: **parity unpinned by the reference.**  The reference's implementation of this path
-needs TensorFlow 1.4 (README.md:9; `import tensorflow` in every hot-path file), which is not
-installable here (no network, no py3.12 wheel), and the reference ships no tests, golden vectors or
-fixtures.  What pins this oracle instead:
+PARITY STATUS: **pinned through the reference's own code executed over a TF-op stand-in; NOT pinned by
+TensorFlow itself.**  The reference's implementation of this path needs TensorFlow 1.4 (README.md:9;
+`import tensorflow` in every hot-path file), which is not installable here (no network, no py3.12 wheel), and
+the reference ships no tests, golden vectors or fixtures.  What pins this oracle:
+  * tests/golden/reference_model_golden.npz -- outputs of the reference's unmodified model classes
+    (model_builder, Representation, AffineTransform, ConcatGcn, BasisGcn, RelationEmbedding, BilinearDiag)
+    run over tests/golden/tf1_shim.py (eager float64 restatement of the ~30 TF ops they call); loss,
+    regularisation, every weight gradient and the test-mode scores agree with this oracle to 1e-10
+    (tests/test_reference_golden.py).  Residual assumption: the shim's per-op TF semantics;
   * the integer goldens derived by hand from data/Toy and listed in SURVEY.md 8(c)
     (tests/golden/toy_golden.json, generated with the reference's own numpy-only loaders
     common/io.py and common/settings_reader.py, which DO import here);
@@ -35,7 +40,7 @@ def process_triples(triples):
 # --------------------------------------------------------------------------------------------
 # F2: incidence normalisation           extras/graph_representations.py:84-93 and :124-133
 # --------------------------------------------------------------------------------------------
-def incidence_norm(rows, n_vertices, mode="canonical"):
+def incidence_norm(rows, n_vertices, mode="canonical", norm_dtype=np.float32):
     """Values of tf.sparse_softmax(SparseTensor([rows, arange(E)], ones, [V,E])).
 
     canonical          : softmax over a row of all-ones = 1 / (#entries in that row)  -- what the
@@ -47,22 +52,22 @@ def incidence_norm(rows, n_vertices, mode="canonical"):
     none               : all ones (:70-82).
     """
     rows = np.asarray(rows, dtype=np.int64)
-    counts = np.bincount(rows, minlength=n_vertices).astype(np.float32)
+    counts = np.bincount(rows, minlength=n_vertices).astype(norm_dtype)   # float32 as TF; float64 for goldens
     if mode == "canonical":
-        return (np.float32(1.0) / counts[rows]).astype(np.float32)
+        return (norm_dtype(1.0) / counts[rows]).astype(norm_dtype)
     if mode == "tf_unsorted_compat":
         order = np.argsort(rows, kind="stable")  # canonical order: by row, then by column (=k)
-        return (np.float32(1.0) / counts[rows[order]]).astype(np.float32)
+        return (norm_dtype(1.0) / counts[rows[order]]).astype(norm_dtype)
     if mode == "none":
-        return np.ones(rows.shape[0], dtype=np.float32)
+        return np.ones(rows.shape[0], dtype=norm_dtype)
     raise ValueError(mode)
 
 
-def graph_norms(triples, n_vertices, mode="canonical"):
+def graph_norms(triples, n_vertices, mode="canonical", norm_dtype=np.float32):
     """(norm_f[E], norm_b[E]): forward matrix rows = receivers (:85-87), backward rows = senders
     (:125-127); normalised per direction, not per relation ('global' branch)."""
     s, _, o = process_triples(triples)
-    return incidence_norm(o, n_vertices, mode), incidence_norm(s, n_vertices, mode)
+    return incidence_norm(o, n_vertices, mode, norm_dtype), incidence_norm(s, n_vertices, mode, norm_dtype)
 
 
 def messages_from_triples(triples, n_relations, n_vertices, mode="canonical"):
@@ -277,9 +282,9 @@ def distmult_predict_all_subjects(codes, rel, X, dtype=torch.float32):
 # train.py:262 (loss = CE + regularisation)
 # --------------------------------------------------------------------------------------------
 def encoder_forward(params, triples, n_vertices, n_relations, variant, mode="train", drop_masks=None,
-                    keep=1.0, norm_mode="canonical", dtype=torch.float32):
+                    keep=1.0, norm_mode="canonical", dtype=torch.float32, norm_dtype=np.float32):
     """params: {'W_in','b_in','layers':[{...}], 'W_relation'}; returns final codes [V,d]."""
-    nf, nb = graph_norms(triples, n_vertices, norm_mode)
+    nf, nb = graph_norms(triples, n_vertices, norm_mode, norm_dtype)
     H = affine_onehot(_t(params["W_in"], dtype), _t(params["b_in"], dtype))  # model_builder.py:140-146
     n_layers = len(params["layers"])
     for li, lp in enumerate(params["layers"]):

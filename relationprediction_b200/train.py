@@ -144,7 +144,7 @@ def main(argv=None):
         loss = model.train_loss(*sample())
         loss.backward()
         optimizer.step()
-        running += float(loss)
+        running += float(loss.detach())
         if it == 1:
             print("Initial loss: %f" % running)
         if it % report_every == 0:

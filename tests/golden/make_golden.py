@@ -6,6 +6,7 @@
                        (common/io.py:27-39), the SURVEY.md 8(c) integer goldens (degrees, norms), the
                        raw text of the shipped .exp settings files and their parse by the REFERENCE's
                        settings_reader (common/settings_reader.py:29-48).
+* (reference-code goldens: see make_reference_golden.py)
 * layer_golden.npz  -- seeded inputs + float64 oracle outputs (forward, all gradients) of one block
                        layer and one basis layer on the Toy graph, plus DistMult loss/grad.  The
                        reference itself cannot run (TensorFlow 1.4 absent): these pin the ORACLE
