@@ -137,6 +137,12 @@ def main():
                  grouping, out)
         run_case("basis_syn_" + grouping, "gcn_basis.exp", widths(20, 3), syn, syn_test, sV, sR, 4,
                  grouping, out)
+    # BASELINE.json configs[0]: one-layer models (the only layer is also the last one => linear, no ReLU)
+    one = [('Encoder', 'NumberOfLayers', '1')]
+    run_case("basis_toy_1layer_canonical", "gcn_basis.exp", widths(24, 2) + one, toy_train, toy_test, tV, tR, 5,
+             "canonical", out)
+    run_case("block_toy_1layer_canonical", "gcn_block.exp", widths(16, 4) + one, toy_train, toy_test, tV, tR, 6,
+             "canonical", out)
     np.savez_compressed(os.path.join(HERE, "reference_model_golden.npz"), **out)
     print("wrote reference_model_golden.npz (%d arrays)" % len(out))
 

@@ -10,12 +10,13 @@ import torch
 from relationprediction_b200.common import model_builder
 from relationprediction_b200.encoders.message_gcns.message_gcn import MessageGcn
 from test_plugin_host import merged_settings
-from test_reference_golden import CASES, GROUPINGS, load_case, split_weights
+from test_reference_golden import ALL, load_case, split_weights
 
 pytestmark = pytest.mark.gpu
 
 WIDTHS = {"block_toy_s5": ("gcn_block.exp", 40, 8), "block_syn_s8": ("gcn_block.exp", 32, 4),
-          "basis_toy": ("gcn_basis.exp", 24, 5), "basis_syn": ("gcn_basis.exp", 20, 3)}
+          "basis_toy": ("gcn_basis.exp", 24, 5), "basis_syn": ("gcn_basis.exp", 20, 3),
+          "basis_toy_1layer": ("gcn_basis.exp", 24, 2), "block_toy_1layer": ("gcn_block.exp", 16, 4)}
 
 
 def rel(a, b):
@@ -32,8 +33,7 @@ def layers_of(model):
     return out[::-1]          # input side first
 
 
-@pytest.mark.parametrize("grouping,norm_mode", GROUPINGS)
-@pytest.mark.parametrize("name,variant", CASES)
+@pytest.mark.parametrize("name,variant,grouping,norm_mode", ALL)
 def test_product_matches_reference_code_outputs(toy, name, variant, grouping, norm_mode):
     c = load_case(name + "_" + grouping)
     settings_file, d, B = WIDTHS[name]
@@ -45,6 +45,8 @@ def test_product_matches_reference_code_outputs(toy, name, variant, grouping, no
         s.put("CodeDimension", str(d))
         s.put("NumberOfBasisFunctions", str(B))
         s.put("NormalizationMode", norm_mode)
+        if name.endswith("_1layer"):
+            s.put("NumberOfLayers", "1")
     model = model_builder.build_decoder(model_builder.build_encoder(enc, c["test_graph"]), dec)
     model.set_device("cuda:0")
     model.initialize_train()

@@ -67,8 +67,11 @@ def rel(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-300))
 
 
-@pytest.mark.parametrize("grouping,norm_mode", GROUPINGS)
-@pytest.mark.parametrize("name,variant", CASES)
+ALL = [(n, v, g, m) for n, v in CASES for g, m in GROUPINGS] + [
+    ("basis_toy_1layer", "basis", "canonical", "canonical"), ("block_toy_1layer", "block", "canonical", "canonical")]
+
+
+@pytest.mark.parametrize("name,variant,grouping,norm_mode", ALL)
 def test_oracle_matches_reference_code_outputs(name, variant, grouping, norm_mode):
     c = load_case(name + "_" + grouping)
     names, leaves, loss, reg, tc = oracle_run(c, variant, norm_mode)
