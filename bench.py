@@ -470,17 +470,24 @@ def main():
 
     if world > 1:
         # per-stage times of rank 0's shard (local-source graph + halo-source graph) and the roofline of its
-        # dominant kernel; guarded: a failure here must never cost the scaling run its bench line
-        try:
-            if rank == 0:
+        # dominant kernel.  The steps (which contain collectives) run identically and unguarded on every
+        # rank; only rank 0's bookkeeping around them is guarded, so a failure there cannot desynchronise
+        # the ranks or cost the scaling run its bench line.
+        prof_ok = False
+        if rank == 0:
+            try:
                 _lib.profile_enable(True)
-            acc = {}
-            n_prof = 4  # 17 stage marks per sharded step; the library keeps 96
-            for _ in range(n_prof):  # identical on every rank: the step contains collectives
-                flush_buf.zero_()
-                step()
-            torch.cuda.synchronize()
-            if rank == 0:
+                prof_ok = True
+            except Exception as exc:  # noqa: BLE001
+                stages = {"error": repr(exc)}
+        n_prof = 4  # 17 stage marks per sharded step; the library keeps 96
+        for _ in range(n_prof):
+            flush_buf.zero_()
+            step()
+        torch.cuda.synchronize()
+        if rank == 0 and prof_ok:
+            try:
+                acc = {}
                 for name, ms in _lib.profile_read():
                     acc[name] = acc.get(name, 0.0) + ms / n_prof
                 _lib.profile_enable(False)
@@ -501,8 +508,8 @@ def main():
                                 "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                                 "algorithmic_bytes": int(alg[top]), "kernel_ms": mine[top], "peak_source": peak_src,
                                 "all": {k: {"ms": mine[k], "GB/s": alg[k] / (mine[k] * 1e-3) / 1e9} for k in mine}}
-        except Exception as exc:  # noqa: BLE001
-            roofline, stages = None, {"error": repr(exc)}
+            except Exception as exc:  # noqa: BLE001
+                roofline, stages = None, {"error": repr(exc)}
         sync_all()
 
     cpu_baseline = None
