@@ -9,7 +9,11 @@ the periodic validation MRR follow the reference; the "Converge" optimizer stack
 a plain loop.  Clip + Adam run on the library's kernels with the TensorFlow-1.x formulas (optim.py,
 csrc/optimizer.cu)."""
 import argparse
+import json
 import os
+import queue
+import threading
+import time
 
 import numpy as np
 import torch
@@ -23,6 +27,42 @@ def load_dataset(dataset):
     splits = {k: io.read_triplets_as_array(os.path.join(dataset, k + '.txt'), ent, rel)
               for k in ('train', 'valid', 'test')}
     return splits, io.read_dictionary(ent), io.read_dictionary(rel)
+
+
+def load_dataset_npz(path):
+    """Packed form of the same data (scripts/pack_dataset.py): arrays train/valid/test [n,3] int32 in the
+    dictionary ids of entities.dict / relations.dict, plus V and R.  The text datasets live in the reference
+    tree, which is not present on a GPU box."""
+    z = np.load(path)
+    splits = {k: np.ascontiguousarray(z[k], dtype=np.int32) for k in ('train', 'valid', 'test')}
+    return splits, list(range(int(z['V']))), list(range(int(z['R'])))
+
+
+def sample_stream(sample, n_threads):
+    """Endless stream of per-step samples; with n_threads > 0 they are produced by background threads
+    (the library sampler and numpy release the GIL), so the GPU never waits for the host transform."""
+    if n_threads <= 0:
+        while True:
+            yield sample()
+    q, stop = queue.Queue(maxsize=2 * n_threads), threading.Event()
+
+    def work():
+        while not stop.is_set():
+            item = sample()
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.1)
+                    break
+                except queue.Full:
+                    pass
+    threads = [threading.Thread(target=work, daemon=True) for _ in range(n_threads)]
+    for t in threads:
+        t.start()
+    try:
+        while True:
+            yield q.get()
+    finally:
+        stop.set()
 
 
 def merge_settings(settings, n_entities, n_relations, n_train):
@@ -83,14 +123,25 @@ def sample_edge_neighborhood(adj_list, degrees, n_triplets, sample_size):
 def main(argv=None):
     ap = argparse.ArgumentParser(description="Train a model on a given dataset.")
     ap.add_argument("--settings", required=True)
-    ap.add_argument("--dataset", required=True)
+    ap.add_argument("--dataset", default=None, help="directory with train/valid/test.txt + the two .dict files")
+    ap.add_argument("--dataset-npz", default=None, help="the same data packed by scripts/pack_dataset.py")
     ap.add_argument("--max-iterations", type=int, default=None)
+    ap.add_argument("--time-budget", type=float, default=None, help="stop training after this many seconds")
+    ap.add_argument("--prefetch", type=int, default=0, help="background threads producing the per-step samples")
+    ap.add_argument("--no-periodic-eval", action="store_true", help="skip the CheckEvery validation passes")
+    ap.add_argument("--final-eval", type=int, default=None, metavar="N",
+                    help="after training rank the first N test triples (0 = all) and print one JSON line")
     ap.add_argument("--device", default="cuda:0")
     args = ap.parse_args(argv)
+    if (args.dataset is None) == (args.dataset_npz is None):
+        ap.error("give exactly one of --dataset / --dataset-npz")
 
     settings = settings_reader.read(args.settings)
     print(settings)
-    splits, entities, relations = load_dataset(args.dataset)
+    if args.dataset_npz is not None:
+        splits, entities, relations = load_dataset_npz(args.dataset_npz)
+    else:
+        splits, entities, relations = load_dataset(args.dataset)
     train, valid, test = splits['train'], splits['valid'], splits['test']
     merge_settings(settings, len(entities), len(relations), len(train))
     general, opt = settings['General'], settings['Optimizer']
@@ -137,23 +188,41 @@ def main(argv=None):
     check_every = int(opt['EarlyStopping']['CheckEvery']) if 'EarlyStopping' in opt else None
     max_it = args.max_iterations if args.max_iterations is not None else 10 ** 9
 
-    running, it = 0.0, 0
+    running, it, last_avg = 0.0, 0, None
+    stream = sample_stream(sample, args.prefetch)
+    t_start = time.time()
     while it < max_it:
+        if args.time_budget is not None and time.time() - t_start > args.time_budget:
+            break
         it += 1
         optimizer.zero_grad()
-        loss = model.train_loss(*sample())
+        loss = model.train_loss(*next(stream))
         loss.backward()
         optimizer.step()
         running += float(loss.detach())
         if it == 1:
             print("Initial loss: %f" % running)
         if it % report_every == 0:
-            print("Average train loss for iteration %d-%d: %f" % (it - report_every + 1, it, running / report_every))
+            last_avg = running / report_every
+            print("Average train loss for iteration %d-%d: %f" % (it - report_every + 1, it, last_avg))
             running = 0.0
-        if check_every and it % check_every == 0:
+        if check_every and it % check_every == 0 and not args.no_periodic_eval:
             summary = scorer.compute_scores(valid).get_summary()
             print("Validation filtered MRR at iteration %d: %f" % (it, summary.results['Filtered']['MRR']))
             scorer.compute_scores(test).get_summary().pretty_print()
+    train_seconds = time.time() - t_start
+    stream.close()
+    if args.final_eval is not None:
+        part = test if args.final_eval == 0 else test[:args.final_eval]
+        t0 = time.time()
+        res = scorer.compute_scores(part).get_summary().results
+        keep = ('MRR', 'H@1', 'H@3', 'H@10')
+        print(json.dumps({"iterations": it, "train_seconds": round(train_seconds, 2),
+                          "ms_per_iteration": round(train_seconds / max(it, 1) * 1e3, 3),
+                          "last_avg_train_loss": last_avg, "test_triples": int(len(part)),
+                          "eval_seconds": round(time.time() - t0, 2),
+                          "raw": {k: float(v) for k, v in res['Raw'].items() if k in keep},
+                          "filtered": {k: float(v) for k, v in res['Filtered'].items() if k in keep}}))
     return model, scorer
 
 

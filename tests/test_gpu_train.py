@@ -78,3 +78,22 @@ def test_toy_training_runs_and_learns(toy, tmp_path, capsys, layers, concat):
     assert len(losses) == 4 and losses[-1] < losses[0]
     summ = scorer.compute_scores(np.array(toy["train"])[:20]).get_summary()
     assert 0.0 < summ.results["Filtered"]["MRR"] <= 1.0
+
+
+def test_packed_dataset_prefetch_and_final_eval(toy, tmp_path, capsys):
+    """The round-trip a real-dataset run uses: --dataset-npz, background sample threads, a time budget and the
+    final JSON line with raw / filtered ranking metrics."""
+    import json
+    p = str(tmp_path / "toy.npz")
+    np.savez_compressed(p, V=toy["V"], R=toy["R"], **{k: np.array(toy[k], dtype=np.int32)
+                                                       for k in ("train", "valid", "test")})
+    exp = tmp_path / "toy.exp"
+    exp.write_text(TOY_EXP.format(layers=2, concat="Yes"))
+    np.random.seed(0)
+    driver.main(["--settings", str(exp), "--dataset-npz", p, "--max-iterations", "60", "--prefetch", "2",
+                 "--time-budget", "60", "--no-periodic-eval", "--final-eval", "0"])
+    text = capsys.readouterr().out
+    assert "Validation filtered MRR" not in text
+    line = json.loads([l for l in text.splitlines() if l.startswith("{")][-1])
+    assert line["iterations"] == 60 and line["test_triples"] == len(toy["test"])
+    assert 0.0 < line["filtered"]["MRR"] <= 1.0 and line["raw"]["MRR"] <= line["filtered"]["MRR"] + 1e-12

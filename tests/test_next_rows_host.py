@@ -155,3 +155,29 @@ def test_tf_adam_and_clip_restatement_agrees_with_torch():
     small = [np.full((3,), 1e-3)]
     assert np.allclose(oracle.tf_clip_by_global_norm(small, 1.0)[0][0], small[0])
     assert np.all(oracle.tf_clip_by_global_norm([np.zeros(4)], 1.0)[0][0] == 0)
+
+
+def test_packed_dataset_and_sample_stream(tmp_path):
+    """train.py host plumbing that needs no GPU: the packed dataset form and the prefetching sample stream."""
+    from relationprediction_b200 import train as T
+    rng = np.random.RandomState(0)
+    arrs = {k: rng.randint(0, 9, size=(n, 3)).astype(np.int32) for k, n in (("train", 40), ("valid", 5), ("test", 6))}
+    p = str(tmp_path / "d.npz")
+    np.savez_compressed(p, V=16, R=9, **arrs)
+    splits, ents, rels = T.load_dataset_npz(p)
+    assert len(ents) == 16 and len(rels) == 9
+    for k in arrs:
+        assert splits[k].dtype == np.int32 and np.array_equal(splits[k], arrs[k])
+    counter = {"n": 0}
+    lock = __import__("threading").Lock()
+
+    def sample():
+        with lock:
+            counter["n"] += 1
+            return counter["n"]
+    for threads in (0, 3):
+        counter["n"] = 0
+        s = T.sample_stream(sample, threads)
+        got = [next(s) for _ in range(20)]
+        s.close()
+        assert len(set(got)) == 20 and min(got) >= 1      # every sample delivered once, none duplicated
