@@ -65,6 +65,32 @@ def sample_stream(sample, n_threads):
         stop.set()
 
 
+class EarlyStopper(object):
+    """Stopping rule of the reference's optimizer stack (optimization/shared/algorithms.py:119-161 as configured
+    by common/optimizer_parameter_parser.py:75-92): every CheckEvery iterations the validation score (filtered
+    MRR) is compared with the PREVIOUS check; if it did not strictly improve and the iteration count is past
+    BurninPhaseDuration, training stops; inside the burn-in the drop is ignored.  The previous score is always
+    replaced by the current one (not a running best)."""
+
+    def __init__(self, check_every, burnin=0):
+        self.check_every, self.burnin = int(check_every), int(burnin)
+        self.previous = None
+
+    def due(self, iteration):
+        return iteration % self.check_every == 0
+
+    def update(self, iteration, score):
+        stop = False
+        if self.previous is not None and not (score > self.previous):
+            if iteration > self.burnin:
+                print("Stopping criterion reached.")
+                stop = True
+            else:
+                print("Ignoring criterion while in burn-in phase.")
+        self.previous = score
+        return stop
+
+
 def merge_settings(settings, n_entities, n_relations, n_train):
     general = settings['General']
     general.put('EntityCount', n_entities)
@@ -129,6 +155,8 @@ def main(argv=None):
     ap.add_argument("--time-budget", type=float, default=None, help="stop training after this many seconds")
     ap.add_argument("--prefetch", type=int, default=0, help="background threads producing the per-step samples")
     ap.add_argument("--no-periodic-eval", action="store_true", help="skip the CheckEvery validation passes")
+    ap.add_argument("--no-early-stopping", action="store_true",
+                    help="keep the validation passes but never stop on them (only --max-iterations / --time-budget)")
     ap.add_argument("--final-eval", type=int, default=None, metavar="N",
                     help="after training rank the first N test triples (0 = all) and print one JSON line")
     ap.add_argument("--device", default="cuda:0")
@@ -185,7 +213,10 @@ def main(argv=None):
     max_norm = float(opt['MaxGradientNorm']) if 'MaxGradientNorm' in opt else None
     optimizer = ClippedAdam(weights, lr=lr, beta1=0.9, beta2=0.999, eps=1e-8, max_norm=max_norm)
     report_every = int(opt['ReportTrainLossEvery']) if 'ReportTrainLossEvery' in opt else 100
-    check_every = int(opt['EarlyStopping']['CheckEvery']) if 'EarlyStopping' in opt else None
+    stopper = None
+    if 'EarlyStopping' in opt and not args.no_periodic_eval:
+        es = opt['EarlyStopping']
+        stopper = EarlyStopper(es['CheckEvery'], es['BurninPhaseDuration'] if 'BurninPhaseDuration' in es else 0)
     max_it = args.max_iterations if args.max_iterations is not None else 10 ** 9
 
     running, it, last_avg = 0.0, 0, None
@@ -206,10 +237,12 @@ def main(argv=None):
             last_avg = running / report_every
             print("Average train loss for iteration %d-%d: %f" % (it - report_every + 1, it, last_avg))
             running = 0.0
-        if check_every and it % check_every == 0 and not args.no_periodic_eval:
-            summary = scorer.compute_scores(valid).get_summary()
-            print("Validation filtered MRR at iteration %d: %f" % (it, summary.results['Filtered']['MRR']))
+        if stopper is not None and stopper.due(it):
+            score = scorer.compute_scores(valid).get_summary().results['Filtered']['MRR']
+            print("Validation filtered MRR at iteration %d: %f" % (it, score))
             scorer.compute_scores(test).get_summary().pretty_print()
+            if stopper.update(it, score) and not args.no_early_stopping:
+                break
     train_seconds = time.time() - t_start
     stream.close()
     if args.final_eval is not None:

@@ -181,3 +181,20 @@ def test_packed_dataset_and_sample_stream(tmp_path):
         got = [next(s) for _ in range(20)]
         s.close()
         assert len(set(got)) == 20 and min(got) >= 1      # every sample delivered once, none duplicated
+
+
+def test_early_stopper_follows_reference_rule(capsys):
+    """optimization/shared/algorithms.py:139-161: compare with the PREVIOUS check (not the best), strict
+    improvement required, drops inside the burn-in are ignored."""
+    from relationprediction_b200.train import EarlyStopper
+    es = EarlyStopper("2000", "6000")
+    assert [es.due(i) for i in (1999, 2000, 4000, 4001)] == [False, True, True, False]
+    assert es.update(2000, 0.10) is False          # first check: nothing to compare with
+    assert es.update(4000, 0.09) is False          # drop inside the burn-in: ignored ...
+    assert "Ignoring criterion" in capsys.readouterr().out
+    assert es.update(6000, 0.095) is False         # ... and the comparison base moved to 0.09; 6000 is not > burn-in
+    assert es.update(8000, 0.20) is False
+    assert es.update(10000, 0.20) is True          # equal is not an improvement
+    assert "Stopping criterion reached" in capsys.readouterr().out
+    es2 = EarlyStopper(10)
+    assert es2.update(10, 0.5) is False and es2.update(20, 0.4) is True
