@@ -30,13 +30,16 @@ class AffineTransform(Model):
             hidden = torch.relu(hidden)
         return hidden
 
+    def _one_side(self, getter, mode):
+        if self.onehot_input:      # one-hot input times W is W itself
+            return self._finish(self.W)
+        return self._finish(getattr(self.next_component, getter)(mode=mode) @ self.W)
+
     def get_all_subject_codes(self, mode='train'):
-        hidden = self.W if self.onehot_input else self.next_component.get_all_subject_codes(mode=mode) @ self.W
-        return self._finish(hidden)
+        return self._one_side('get_all_subject_codes', mode)
 
     def get_all_object_codes(self, mode='train'):
-        hidden = self.W if self.onehot_input else self.next_component.get_all_object_codes(mode=mode) @ self.W
-        return self._finish(hidden)
+        return self._one_side('get_all_object_codes', mode)
 
     def get_all_codes(self, mode='train'):
         if self.onehot_input:

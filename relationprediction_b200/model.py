@@ -105,77 +105,60 @@ class Model(object):
         self.clear_cache()
         return self.get_loss(mode='train') + self.get_regularization()
 
-    # ---- chain protocol ----
-    def initialize_train(self):
-        return self.__local_run_delegate__('initialize_train')
-
-    def clear_cache(self):
-        return self.__local_run_delegate__('clear_cache')
-
-    def get_weights(self):
-        return self.__local_expand_delegate__('get_weights')
-
-    def set_variable(self, name, value):
-        return self.__local_run_delegate__('set_variable', name, value)
-
-    def get_train_input_variables(self):
-        return self.__local_expand_delegate__('get_train_input_variables')
-
-    def get_test_input_variables(self):
-        return self.__local_expand_delegate__('get_test_input_variables')
-
-    def get_loss(self, mode='train'):
-        return self.__delegate__('get_loss', mode)
-
-    def get_regularization(self):
-        return self.__local_expand_delegate__('get_regularization', base=0)
-
-    def get_all_subject_codes(self, mode='train'):
-        return self.__delegate__('get_all_subject_codes', mode)
-
-    def get_all_object_codes(self, mode='train'):
-        return self.__delegate__('get_all_object_codes', mode)
-
-    def get_all_codes(self, mode='train'):
-        return self.__delegate__('get_all_codes', mode)
-
-    def predict(self):
-        return self.__delegate__('predict')
-
-    def predict_all_subject_scores(self):
-        return self.__delegate__('predict_all_subject_scores')
-
-    def predict_all_object_scores(self):
-        return self.__delegate__('predict_all_object_scores')
-
-    def get_graph(self):
-        return self.__delegate__('get_graph')
-
-    def get_additional_ops(self):
-        return self.__local_expand_delegate__('get_additional_ops')
-
     def needs_graph(self):
+        nxt = self.next_component
+        return False if nxt is None else nxt.needs_graph()
+
+    # ---- the three call disciplines of the chain (code/model.py:148-182) ----
+    def __delegate__(self, name, *args, **kw):
+        """Pure forwarding to the next component; None at the end of the chain."""
+        nxt = self.next_component
+        return None if nxt is None else getattr(nxt, name)(*args, **kw)
+
+    def __local_run_delegate__(self, name, *args, **kw):
+        """Run `local_<name>` here if this component defines it, then continue down the chain."""
+        hook = getattr(self, 'local_' + name, None)
+        if hook is not None:
+            hook(*args, **kw)
+        if self.next_component is not None:
+            getattr(self.next_component, name)(*args, **kw)
+
+    def __local_expand_delegate__(self, name, *args, base=None, **kw):
+        """Collect `local_<name>` results along the chain, DEEPEST component first (this fixes the order
+        of get_weights() and of the feed lists)."""
+        hook = getattr(self, 'local_' + name, None)
+        mine = hook(*args, **kw) if hook is not None else ([] if base is None else base)
         if self.next_component is None:
-            return False
-        return self.next_component.needs_graph()
+            return mine
+        return getattr(self.next_component, name)(*args, **kw) + mine
 
-    def __delegate__(self, name, *args):
-        if self.next_component is not None:
-            return getattr(self.next_component, name)(*args)
-        return None
 
-    def __local_run_delegate__(self, name, *args):
-        local = 'local_' + name
-        if hasattr(self, local):
-            getattr(self, local)(*args)
-        if self.next_component is not None:
-            getattr(self.next_component, name)(*args)
+def _install_chain_protocol(cls):
+    """The public hooks of the plugin protocol, generated from one table: which discipline each follows."""
+    def forward(name):
+        return lambda self, *a, **k: self.__delegate__(name, *a, **k)
 
-    def __local_expand_delegate__(self, name, *args, base=None):
-        if base is None:
-            base = []
-        local = 'local_' + name
-        local_result = getattr(self, local)(*args) if hasattr(self, local) else base
-        if self.next_component is not None:
-            return getattr(self.next_component, name)(*args) + local_result
-        return local_result
+    def run(name):
+        return lambda self, *a, **k: self.__local_run_delegate__(name, *a, **k)
+
+    def collect(name, base):
+        return lambda self, *a, **k: self.__local_expand_delegate__(name, *a, base=base, **k)
+    table = {
+        forward: ('get_loss', 'get_all_subject_codes', 'get_all_object_codes', 'get_all_codes', 'predict',
+                  'predict_all_subject_scores', 'predict_all_object_scores', 'get_graph'),
+        run: ('initialize_train', 'clear_cache', 'set_variable'),
+    }
+    for make, names in table.items():
+        for name in names:
+            fn = make(name)
+            fn.__name__ = name
+            setattr(cls, name, fn)
+    for name, base in (('get_weights', None), ('get_train_input_variables', None),
+                       ('get_test_input_variables', None), ('get_additional_ops', None),
+                       ('get_regularization', 0)):
+        fn = collect(name, base)
+        fn.__name__ = name
+        setattr(cls, name, fn)
+
+
+_install_chain_protocol(Model)

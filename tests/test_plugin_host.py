@@ -117,3 +117,79 @@ def test_no_cpu_fallback_in_plugin_layers(toy):
     if not torch.cuda.is_available():
         with pytest.raises(Exception):   # graph handle / kernels need a CUDA device: loud failure
             model.train_loss(np.array(toy["train"]), np.array(toy["train"]), np.ones(43, np.float32))
+
+
+def test_chain_protocol_disciplines_with_dummy_components():
+    """The three call disciplines of the plugin chain (code/model.py:148-182) on a GPU-free dummy chain."""
+    from relationprediction_b200.model import Model
+    S = {'EntityCount': 3, 'RelationCount': 2, 'EdgeCount': 1}
+    log = []
+
+    class Bottom(Model):
+        def local_initialize_train(self):
+            log.append('bottom-init')
+
+        def local_get_weights(self):
+            return ['w_bottom']
+
+        def local_get_regularization(self):
+            return 2.0
+
+        def get_all_codes(self, mode='train'):
+            return ('codes', mode)
+
+        def get_loss(self, mode='train'):
+            return 'loss-' + mode
+
+        def needs_graph(self):
+            return True
+
+    class Middle(Model):          # defines nothing: everything passes through
+        pass
+
+    class Top(Model):
+        def local_initialize_train(self):
+            log.append('top-init')
+
+        def local_get_weights(self):
+            return ['w_top']
+
+        def local_set_variable(self, name, value):
+            log.append((name, value))
+
+        def local_get_regularization(self):
+            return 0.5
+    chain = Top(Middle(Bottom(None, S), S), S)
+    chain.initialize_train()
+    assert log == ['top-init', 'bottom-init']                      # local first, then down the chain
+    assert chain.get_weights() == ['w_bottom', 'w_top']            # deepest component first
+    assert chain.get_regularization() == 2.5                       # base 0, summed along the chain
+    assert chain.get_train_input_variables() == [] and chain.get_additional_ops() == []
+    assert chain.get_all_codes() == ('codes', 'train')             # defaults of the defining component apply
+    assert chain.get_all_codes(mode='test') == ('codes', 'test') and chain.get_all_codes('test') == ('codes', 'test')
+    assert chain.get_loss(mode='test') == 'loss-test'
+    assert chain.predict() is None and chain.get_graph() is None   # nobody defines them: None at the chain end
+    assert chain.needs_graph() is True and Middle(None, S).needs_graph() is False
+    chain.set_variable('x', 1)
+    assert log[-1] == ('x', 1)
+    assert chain.get_weights.__name__ == 'get_weights'
+
+
+def test_real_chain_weight_and_feed_order_on_cpu(toy):
+    """gcn_block.exp chain with its weights created on the CPU device: get_weights() order and the feed lists
+    are what the reference produces (AffineTransform, layer 1, layer 2, RelationEmbedding; [graph, X, Y])."""
+    V, R, E = 16, 9, 43
+    enc, dec = merged_settings(toy, "gcn_block.exp", V, R, E)
+    for s in (enc, dec):
+        s.put("InternalEncoderDimension", "20")
+        s.put("CodeDimension", "20")
+        s.put("NumberOfBasisFunctions", "4")
+    model = model_builder.build_decoder(model_builder.build_encoder(enc, toy["train"]), dec)
+    model.set_device("cpu")
+    model.initialize_train()
+    shapes = [tuple(w.shape) for w in model.get_weights()]
+    assert shapes == [(16, 20), (20,), (9, 4, 5, 5), (9, 4, 5, 5), (20, 20), (20,),
+                      (9, 4, 5, 5), (9, 4, 5, 5), (20, 20), (20,), (16, 20)]
+    assert [p.name for p in model.get_train_input_variables()] == ['graph_edges', 'X', 'Y']
+    assert [p.name for p in model.get_test_input_variables()] == ['graph_edges', 'X']
+    assert model.needs_graph()
