@@ -27,7 +27,7 @@ sys.path.insert(0, os.path.join(REF, "code"))
 import tf1_shim  # noqa: E402
 tf = tf1_shim.install()
 
-from common import settings_reader, io, model_builder, auxilliaries  # noqa: E402  (reference modules)
+from common import settings_reader, io, model_builder, auxilliaries, evaluation  # noqa: E402  (reference modules)
 from encoders.message_gcns.message_gcn import MessageGcn  # noqa: E402
 from decoders.bilinear_diag import BilinearDiag  # noqa: E402
 
@@ -62,6 +62,47 @@ def build(settings_file, overrides, train, V, R, seed):
     model = model_builder.build_decoder(encoder, dec)
     model.initialize_train()
     return model, general
+
+
+class EagerScoringAdapter(object):
+    """What Model.score_all_subjects / score_all_objects do through session.run (model.py:59-81), for the eager
+    stand-in: feed the registered test graph + the triples, rebuild the test-mode outputs."""
+
+    def __init__(self, model, test_graph):
+        self.model, self.test_graph = model, test_graph
+
+    def _feed(self, triplets):
+        MessageGcn.vertex_embedding_function['test'] = None
+        BilinearDiag.encoder_cache['test'] = None
+        for comp in chain(self.model):
+            if comp.__class__.__name__ == 'Representation':
+                comp.graph = None
+        gX, dX = self.model.get_test_input_variables()
+        gX.feed(self.test_graph)
+        dX.feed(np.asarray(triplets))
+
+    def score_all_subjects(self, triplets):
+        self._feed(triplets)
+        with torch.no_grad():
+            return self.model.predict_all_subject_scores().numpy()
+
+    def score_all_objects(self, triplets):
+        self._feed(triplets)
+        with torch.no_grad():
+            return self.model.predict_all_object_scores().numpy()
+
+
+def reference_ranking(model, train, ranked):
+    """The reference's own Scorer (common/evaluation.py) over the reference model: raw / filtered MRR, Hits@n."""
+    sc = evaluation.Scorer({'Metric': 'MRR'})
+    sc.register_data(train)
+    sc.register_data(ranked)
+    sc.register_degrees(train)
+    sc.register_model(EagerScoringAdapter(model, train))
+    sc.finalize_frequency_computation(np.concatenate((train, ranked), axis=0))
+    res = sc.compute_scores(ranked).get_summary().results
+    keys = ('MRR', 'H@1', 'H@3', 'H@10')
+    return np.array([[float(res[f][k]) for k in keys] for f in ('Raw', 'Filtered')])
 
 
 def run_case(name, settings_file, overrides, train, test, V, R, seed, grouping, out):
@@ -109,8 +150,13 @@ def run_case(name, settings_file, overrides, train, test, V, R, seed, grouping, 
         out[p + "predict"] = model.predict().numpy()
         out[p + "all_subjects"] = model.predict_all_subject_scores().numpy()
         out[p + "all_objects"] = model.predict_all_object_scores().numpy()
-    print("%-28s loss %.6f reg %.6f  weights %d  masks %d" % (name, float(out[p + "loss"]), float(out[p + "reg"]),
-                                                             len(weights), len(tf1_shim.dropout_masks)))
+    # ranking with the reference's own evaluation code: rows Raw / Filtered, columns MRR, H@1, H@3, H@10
+    ranked = np.concatenate((test, train[:40]), axis=0)
+    out[p + "ranked"] = ranked.astype(np.int32)
+    out[p + "ranking"] = reference_ranking(model, train, ranked)
+    print("%-28s loss %.6f reg %.6f  weights %d  masks %d  raw/filtered MRR %.4f %.4f" % (
+        name, float(out[p + "loss"]), float(out[p + "reg"]), len(weights), len(tf1_shim.dropout_masks),
+        out[p + "ranking"][0, 0], out[p + "ranking"][1, 0]))
 
 
 def main():

@@ -10,7 +10,7 @@ import torch
 
 from oracle import rgcn_oracle as oracle
 from relationprediction_b200 import ops
-from relationprediction_b200.common import model_builder
+from relationprediction_b200.common import evaluation, model_builder
 from relationprediction_b200.encoders.message_gcns.message_gcn import MessageGcn
 from test_plugin_host import merged_settings
 from test_reference_golden import ALL, load_case, split_weights
@@ -116,3 +116,15 @@ def test_host_chain_reproduces_reference_code_outputs(toy, oracle_backed_ops, na
                      (model.score_all_objects(c["test_X"]), c["all_objects"]),
                      (model.score_all_subjects(c["test_X"]), c["all_subjects"])):
         assert got.shape == ref.shape and np.abs(np.asarray(got, np.float64) - ref).max() < 100 * tol
+    # ranking: this repository's Scorer over this repository's model == the reference's Scorer over the
+    # reference's model (same weights): raw / filtered MRR and Hits@1/3/10 on test + 40 training triples
+    sc = evaluation.Scorer({'Metric': 'MRR'})
+    sc.register_data(c["test_graph"])
+    sc.register_data(c["ranked"])
+    sc.register_model(model)
+    res = sc.compute_scores(c["ranked"]).get_summary().results
+    got = np.array([[float(res[f][k]) for k in ('MRR', 'H@1', 'H@3', 'H@10')] for f in ('Raw', 'Filtered')])
+    if norm_mode == "canonical":       # float64 scores identical to the golden's => identical ranks
+        assert np.abs(got - c["ranking"]).max() < 1e-12
+    else:                              # float32 norm values can reorder near-ties
+        assert np.abs(got - c["ranking"]).max() < 5e-3
