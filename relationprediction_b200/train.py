@@ -16,7 +16,6 @@ import threading
 import time
 
 import numpy as np
-import torch
 
 from .optim import ClippedAdam
 from .common import auxilliaries, evaluation, io, model_builder, settings_reader

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import rgcn_oracle as oracle
-from relationprediction_b200.common import model_builder, settings_reader
+from relationprediction_b200.common import model_builder
 from conftest import synthetic_kg
 from test_plugin_host import merged_settings
 
