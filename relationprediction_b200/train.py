@@ -218,7 +218,9 @@ def main(argv=None):
         stopper = EarlyStopper(es['CheckEvery'], es['BurninPhaseDuration'] if 'BurninPhaseDuration' in es else 0)
     max_it = args.max_iterations if args.max_iterations is not None else 10 ** 9
 
-    running, it, last_avg = 0.0, 0, None
+    # the running loss stays on the device: reading it back every iteration would serialise the host-side
+    # sample transform of step i+1 behind the GPU work of step i
+    running, it, last_avg = None, 0, None
     stream = sample_stream(sample, args.prefetch)
     t_start = time.time()
     while it < max_it:
@@ -229,13 +231,13 @@ def main(argv=None):
         loss = model.train_loss(*next(stream))
         loss.backward()
         optimizer.step()
-        running += float(loss.detach())
+        running = loss.detach().clone() if running is None else running + loss.detach()
         if it == 1:
-            print("Initial loss: %f" % running)
+            print("Initial loss: %f" % float(running))
         if it % report_every == 0:
-            last_avg = running / report_every
+            last_avg = float(running) / report_every
             print("Average train loss for iteration %d-%d: %f" % (it - report_every + 1, it, last_avg))
-            running = 0.0
+            running = None
         if stopper is not None and stopper.due(it):
             score = scorer.compute_scores(valid).get_summary().results['Filtered']['MRR']
             print("Validation filtered MRR at iteration %d: %f" % (it, score))
