@@ -211,6 +211,9 @@ def main():
     ap.add_argument("--cpu-sample-edges", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (needs 4 pinned V*d buffers)")
+    ap.add_argument("--shard", choices=["node", "feature"], default="node",
+                    help="N > 1: 1-D node shard with halo all-to-all (default, north_star) or the experimental "
+                         "feature-sharded message passing (replicated graph, two transposes per layer)")
     ap.add_argument("--triples-npz", default=None,
                     help="use the triples of this .npz (arrays: triples [E,3], V, R) instead of the synthetic generator; "
                          "diagnostic only (e.g. the real FB15k-237 graph), the default bench stays synthetic")
@@ -257,7 +260,10 @@ def main():
     else:
         from relationprediction_b200 import parallel
         t0 = time.perf_counter()
-        layer = parallel.ShardedGraph(triples, V, R, rank, world, dev)
+        if args.shard == "feature":   # experimental: replicated graph, messages feature-parallel (parallel.py)
+            layer = parallel.FeatureShardedGraph(triples, V, R, rank, world, dev, B, s)
+        else:
+            layer = parallel.ShardedGraph(triples, V, R, rank, world, dev)
         prep_ms = (time.perf_counter() - t0) * 1e3
         graph = layer.graph
         V_loc, V_src = layer.n_local, layer.n_local + layer.n_halo
@@ -492,13 +498,19 @@ def main():
                     acc[name] = acc.get(name, 0.0) + ms / n_prof
                 _lib.profile_enable(False)
                 stages = {k: round(v, 5) for k, v in acc.items()}
-                M_loc = layer.graph_local.M if layer.overlap else layer.graph.M
-                M_halo = layer.graph_halo.M if layer.overlap else 0
                 wt_bytes = 2 * R * s * d * 4
-                alg = {"block_agg_fwd": M_loc * (4 * d + 12) + 8 * V_loc * d + wt_bytes,
-                       "block_aggregate": M_halo * (4 * d + 12) + 4 * V_loc * d + wt_bytes,
-                       "block_agg_dH": M_loc * (8 * d + 12) + 8 * V_loc * d + 2 * wt_bytes,
-                       "block_aggregate_bwd": M_halo * (8 * d + 12) + 4 * layer.n_halo * d + 2 * wt_bytes}
+                if args.shard == "feature":   # every rank walks ALL messages on d_local-wide rows
+                    M_all, dl, Vn = layer.graph.M, layer.d_local, layer.n_nodes
+                    wq = 2 * R * s * dl * 4
+                    alg = {"block_aggregate": M_all * (4 * dl + 12) + 4 * Vn * dl + wq,
+                           "block_aggregate_bwd": M_all * (8 * dl + 12) + 4 * Vn * dl + 2 * wq}
+                else:
+                    M_loc = layer.graph_local.M if layer.overlap else layer.graph.M
+                    M_halo = layer.graph_halo.M if layer.overlap else 0
+                    alg = {"block_agg_fwd": M_loc * (4 * d + 12) + 8 * V_loc * d + wt_bytes,
+                           "block_aggregate": M_halo * (4 * d + 12) + 4 * V_loc * d + wt_bytes,
+                           "block_agg_dH": M_loc * (8 * d + 12) + 8 * V_loc * d + 2 * wt_bytes,
+                           "block_aggregate_bwd": M_halo * (8 * d + 12) + 4 * layer.n_halo * d + 2 * wt_bytes}
                 mine = {k: v for k, v in acc.items() if k in alg and v > 0}
                 if mine:
                     top = max(mine, key=mine.get)
@@ -533,7 +545,8 @@ def main():
                 "config": {"workload": spec["name"], "V": V, "R": R, "E": E, "d": d, "B": B, "s": s,
                            "skewed": spec["skewed"], "dropout": "off (keep=1)", "relu": True,
                            "l2": "flushed between timed iterations (256 MB memset outside the event pair)",
-                           "parallelism": "1d-node-shard x%d" % world if world > 1 else "single",
+                           "parallelism": ("%s x%d" % ("feature-shard (experimental)" if args.shard == "feature"
+                                                       else "1d-node-shard", world)) if world > 1 else "single",
                            "messages": info[0], "dst_runs": info[9], "split_rows": info[7]},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "stages_ms": stages, "graph_prep_ms": prep_ms,

@@ -10,6 +10,8 @@ per-message normalisation uses GLOBAL degrees, so sharded results equal the sing
 The reference has no distributed code at all (single tf.Session, train.py:278); this module is the
 multi-GPU design for the hot path only.
 """
+import math
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -346,3 +348,143 @@ class ShardedGraph(object):
             n = g.numel()
             g.copy_(flat[off:off + n].view_as(g))
             off += n
+
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Feature-sharded message passing (block-diagonal layers only; EXPERIMENTAL, opt-in -- DESIGN.md section 7)
+# ------------------------------------------------------------------------------------------------------------
+def block_bounds(n_blocks, block_size, world):
+    """Contiguous block ranges per rank.  Blocks are dealt in groups of 4/gcd(s,4) so that every rank's column
+    count is a multiple of 4 floats (the kernels move rows as float4 quads)."""
+    g = 4 // math.gcd(int(block_size), 4)
+    if n_blocks % g != 0:
+        raise ValueError("feature sharding needs NumberOfBasisFunctions to be a multiple of %d for block size %d"
+                         % (g, block_size))
+    groups = n_blocks // g
+    if groups < world:
+        raise ValueError("feature sharding: only %d column groups for %d ranks" % (groups, world))
+    return [((groups * p) // world) * g for p in range(world + 1)]
+
+
+class _FeatureShardedBlockLayer(torch.autograd.Function):
+    """Block layer with the MESSAGE part computed feature-parallel and the self loop node-parallel.
+
+    Block-diagonal weights never mix features of different blocks, so a rank that holds the columns of its own
+    blocks for ALL nodes can aggregate every message of the graph without any neighbour exchange:
+
+      forward : all-to-all transpose H_local [n_local, d] -> Hf [V, d_q]   ||  S = dropout(H_local @ W_self)
+                Af = rgcn_block_aggregate(Hf, W[:, blocks_q])  on the FULL graph           [V, d_q]
+                all-to-all transpose back -> columns of out;  out = act(S + messages)
+      backward: G = dOut * act'  ->  transpose  ||  self-loop gradients (two local GEMMs)
+                rgcn_block_aggregate_backward -> dHf, dW[:, blocks_q]  ->  transpose back, dH += .
+
+    Traffic per GPU and direction: 2 transposes of V*d*4/N bytes, independent of the graph's locality."""
+
+    @staticmethod
+    def forward(ctx, H_local, Wf, Wb, Ws, fs, drop_mask, keep, relu):
+        H_local = H_local.contiguous()
+        work, Hf = fs.to_feature_async(H_local)
+        S = H_local @ Ws
+        if drop_mask is not None:
+            S = S * drop_mask.to(S.dtype) / keep
+        work.wait()
+        b0, b1 = fs.blocks
+        Wf_q, Wb_q = Wf[:, b0:b1].contiguous(), Wb[:, b0:b1].contiguous()
+        Af = torch.zeros(fs.n_nodes, fs.d_local, dtype=H_local.dtype, device=H_local.device)
+        ops.block_aggregate_(Af, Hf, Wf_q, Wb_q, fs.graph, b1 - b0)
+        out = fs.to_node_add(Af, S)
+        if relu:
+            out = torch.relu_(out)
+        ctx.fs, ctx.keep, ctx.relu = fs, keep, relu
+        ctx.save_for_backward(H_local, Wf_q, Wb_q, Ws, Hf, out, drop_mask if drop_mask is not None
+                              else torch.empty(0, device=H_local.device))
+        ctx.full_shapes = (Wf.shape, Wb.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        H_local, Wf_q, Wb_q, Ws, Hf, out, mask = ctx.saved_tensors
+        fs = ctx.fs
+        G = (dOut * (out > 0)) if ctx.relu else dOut
+        G = G.contiguous()
+        work, Gf = fs.to_feature_async(G)
+        Gs = G if mask.numel() == 0 else G * mask.to(G.dtype) / ctx.keep
+        dWs = H_local.t() @ Gs
+        dH = Gs @ Ws.t()
+        work.wait()
+        b0, b1 = fs.blocks
+        dHf, dWf_q, dWb_q = ops.block_aggregate_backward(Hf, Wf_q, Wb_q, Gf, fs.graph, b1 - b0)
+        dH = fs.to_node_add(dHf, dH)
+        # the other ranks' blocks get zeros here; allreduce_weight_grads (sum) assembles the full tables
+        dWf = torch.zeros(ctx.full_shapes[0], dtype=dWf_q.dtype, device=dWf_q.device)
+        dWb = torch.zeros(ctx.full_shapes[1], dtype=dWb_q.dtype, device=dWb_q.device)
+        dWf[:, b0:b1] = dWf_q
+        dWb[:, b0:b1] = dWb_q
+        return dH, dWf, dWb, dWs, None, None, None, None
+
+
+class FeatureShardedGraph(object):
+    """Replicated graph structure, features sharded by BLOCK for the message part, by node for everything else
+    (inputs, outputs and the self loop stay in the 1-D node shard's layout, so it is a drop-in for ShardedGraph
+    in block layers).  See _FeatureShardedBlockLayer."""
+
+    def __init__(self, triples, n_nodes, n_relations, rank, world, device, n_blocks, block_size,
+                 norm_mode="canonical", norm_f=None, norm_b=None, group=None):
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.device = torch.device(device)
+        self.n_nodes = int(n_nodes)
+        self.node_bounds = node_bounds(n_nodes, world)
+        self.lo, self.hi = self.node_bounds[rank], self.node_bounds[rank + 1]
+        self.n_local, self.n_halo, self.overlap, self.pipelined = self.hi - self.lo, 0, False, False
+        self.block_size = int(block_size)
+        self.block_bounds = block_bounds(n_blocks, block_size, world)
+        self.blocks = (self.block_bounds[rank], self.block_bounds[rank + 1])
+        self.col_bounds = [b * self.block_size for b in self.block_bounds]
+        self.d = self.col_bounds[-1]
+        self.d_local = self.col_bounds[rank + 1] - self.col_bounds[rank]
+        index = None
+        if self.device.type == "cuda":
+            index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.graph = ops.Graph(triples, n_nodes, n_relations, norm_mode=norm_mode, norm_f=norm_f, norm_b=norm_b,
+                               device=index)
+        rows = [self.node_bounds[p + 1] - self.node_bounds[p] for p in range(world)]
+        cols = [self.col_bounds[q + 1] - self.col_bounds[q] for q in range(world)]
+        # node -> feature: I send my rows' columns of rank q to q; I receive every rank's rows of MY columns
+        self._nf_send = [self.n_local * c for c in cols]
+        self._nf_recv = [r * self.d_local for r in rows]
+        self._cols = cols
+
+    # [n_local, d] -> [V, d_local]
+    def to_feature_async(self, X_local):
+        send = torch.cat([X_local[:, self.col_bounds[q]:self.col_bounds[q + 1]].reshape(-1)
+                          for q in range(self.world)])
+        recv = torch.empty(self.n_nodes * self.d_local, dtype=X_local.dtype, device=X_local.device)
+        work = dist.all_to_all_single(recv, send, output_split_sizes=self._nf_recv,
+                                      input_split_sizes=self._nf_send, group=self.group, async_op=True)
+        return work, recv.view(self.n_nodes, self.d_local)
+
+    # [V, d_local] -> added into the columns of a [n_local, d] base (the adjoint of to_feature)
+    def to_node_add(self, Xf, base):
+        recv = torch.empty(self.n_local * self.d, dtype=Xf.dtype, device=Xf.device)
+        dist.all_to_all_single(recv, Xf.contiguous().view(-1), output_split_sizes=self._nf_send,
+                               input_split_sizes=self._nf_recv, group=self.group)
+        out = base if base.is_contiguous() else base.contiguous()
+        off = 0
+        for q in range(self.world):
+            n = self.n_local * self._cols[q]
+            out[:, self.col_bounds[q]:self.col_bounds[q + 1]] += recv[off:off + n].view(self.n_local, self._cols[q])
+            off += n
+        return out
+
+    def block_layer(self, H_local, W_forward, W_backward, W_self, n_blocks, drop_mask=None, keep=1.0,
+                    relu=True):
+        if int(n_blocks) != self.block_bounds[-1] or W_forward.shape[2] != self.block_size:
+            raise ValueError("FeatureShardedGraph was planned for %d blocks of size %d"
+                             % (self.block_bounds[-1], self.block_size))
+        return _FeatureShardedBlockLayer.apply(H_local, W_forward, W_backward, W_self, self, drop_mask, keep, relu)
+
+    def basis_layer(self, *args, **kwargs):
+        raise NotImplementedError("basis weights are dense in the feature dimension: use the node shard")
+
+    allreduce_weight_grads = ShardedGraph.allreduce_weight_grads

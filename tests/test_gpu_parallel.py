@@ -1,5 +1,6 @@
-"""GPU (>= 2 devices): the 1-D node-sharded layer (halo all-to-all over NCCL) reproduces the single-GPU
-forward output, input gradient and (after the all-reduce) weight gradients."""
+"""GPU (>= 2 devices): the 1-D node-sharded layer (halo all-to-all over NCCL) -- and the experimental
+feature-sharded variant -- reproduce the single-GPU forward output, input gradient and (after the all-reduce)
+weight gradients."""
 import os
 import socket
 
@@ -31,10 +32,13 @@ def _worker(rank, world, port, V, R, E, d, B, out_dir, mode):
     try:
         from relationprediction_b200 import parallel
         tr = synthetic_kg(V, R, E, seed=5, skewed=True)
-        sg = parallel.ShardedGraph(tr, V, R, rank, world, dev, overlap=(mode != "plain"),
-                                   pipelined=(mode == "pipelined"))
-        assert sg.pipelined == (mode == "pipelined")
-        p = sg.plan
+        if mode == "feature":
+            sg = p = parallel.FeatureShardedGraph(tr, V, R, rank, world, dev, B, d // B)
+        else:
+            sg = parallel.ShardedGraph(tr, V, R, rank, world, dev, overlap=(mode != "plain"),
+                                       pipelined=(mode == "pipelined"))
+            assert sg.pipelined == (mode == "pipelined")
+            p = sg.plan
         g = torch.Generator().manual_seed(0)
         s = d // B
         H = torch.randn(V, d, generator=g)
@@ -53,7 +57,7 @@ def _worker(rank, world, port, V, R, E, d, B, out_dir, mode):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["pipelined", "overlapped", "plain"])
+@pytest.mark.parametrize("mode", ["pipelined", "overlapped", "plain", "feature"])
 @pytest.mark.parametrize("world", [2, 4])
 def test_sharded_block_layer_equals_single_gpu(tmp_path, world, mode):
     if torch.cuda.device_count() < world:

@@ -157,3 +157,112 @@ def test_pipelined_ring_exchange_world3_gloo(tmp_path):
     for r in range(world):
         got = np.load(tmp_path / ("ring_%d.npy" % r))
         np.testing.assert_allclose(got, expect[bounds[r]:bounds[r + 1]], rtol=1e-6)
+
+
+# ---- feature-sharded block layer (experimental): host logic on gloo, kernels stubbed by the oracle -------------
+class _OracleGraph(object):
+    def __init__(self, triples, n_entities, n_relations, norm_mode="canonical", norm_f=None, norm_b=None,
+                 device=None):
+        from oracle import rgcn_oracle as oracle
+        self.triples = np.asarray(triples, dtype=np.int32).reshape(-1, 3)
+        self.V_dst = self.V_src = int(n_entities)
+        self.M = 2 * len(self.triples)
+        self.nf, self.nb = oracle.graph_norms(self.triples, n_entities, norm_mode, np.float64)
+
+
+def _messages_only(X, Wf, Wb, graph):
+    from oracle import rgcn_oracle as oracle
+    zero_self = torch.zeros(X.shape[1], X.shape[1], dtype=X.dtype)
+    return oracle.concat_gcn_forward(X, graph.triples, Wf, Wb, zero_self, graph.nf, graph.nb, None, 1.0, False,
+                                     X.dtype)
+
+
+def _stub_aggregate_(out, X, Wf, Wb, graph, n_blocks):
+    assert Wf.shape[1] == n_blocks and X.shape == (graph.V_src, n_blocks * Wf.shape[2])
+    out += _messages_only(X, Wf, Wb, graph)
+    return out
+
+
+def _stub_aggregate_backward(X, Wf, Wb, G, graph, n_blocks, dWf=None, dWb=None):
+    with torch.enable_grad():      # called from inside an autograd.Function.backward
+        Xl, Wfl, Wbl = (t.detach().clone().requires_grad_(True) for t in (X, Wf, Wb))
+        gx, gf, gb = torch.autograd.grad(_messages_only(Xl, Wfl, Wbl, graph), [Xl, Wfl, Wbl], grad_outputs=G)
+    return gx, gf, gb
+
+
+def _feature_worker(rank, world, port, V, R, E, B, s, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from relationprediction_b200 import ops
+        ops.Graph, ops.block_aggregate_, ops.block_aggregate_backward = (_OracleGraph, _stub_aggregate_,
+                                                                          _stub_aggregate_backward)
+        d = B * s
+        tr = synthetic_kg(V, R, E, seed=3, skewed=True)
+        fs = parallel.FeatureShardedGraph(tr, V, R, rank, world, "cpu", B, s)
+        assert fs.d == d and fs.d_local % 4 == 0 and fs.n_halo == 0
+        g = torch.Generator().manual_seed(1)
+        dt = torch.float64
+        H = torch.randn(V, d, generator=g, dtype=dt)
+        Wf, Wb = (torch.randn(R, B, s, s, generator=g, dtype=dt).requires_grad_(True) for _ in range(2))
+        Ws = torch.randn(d, d, generator=g, dtype=dt).requires_grad_(True)
+        mask = (torch.rand(V, d, generator=g) < 0.8).to(torch.uint8)
+        dOut = torch.randn(V, d, generator=g, dtype=dt)
+        # the transposes are each other's adjoint and round-trip to the identity
+        Xl = H[fs.lo:fs.hi].contiguous()
+        work, Xf = fs.to_feature_async(Xl)
+        work.wait()
+        c0, c1 = fs.col_bounds[rank], fs.col_bounds[rank + 1]
+        assert torch.equal(Xf, H[:, c0:c1])
+        assert torch.equal(fs.to_node_add(Xf, torch.zeros_like(Xl)), Xl)
+        H_local = Xl.clone().requires_grad_(True)
+        out = fs.block_layer(H_local, Wf, Wb, Ws, B, mask[fs.lo:fs.hi], 0.8, True)
+        out.backward(dOut[fs.lo:fs.hi])
+        fs.allreduce_weight_grads([Wf, Wb, Ws])
+        np.savez(os.path.join(out_dir, "fs_%d.npz" % rank), out=out.detach().numpy(), dH=H_local.grad.numpy(),
+                 dWf=Wf.grad.numpy(), dWb=Wb.grad.numpy(), dWs=Ws.grad.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,B,s", [(2, 8, 4), (3, 6, 8), (2, 8, 5)])
+def test_feature_sharded_block_layer_gloo(tmp_path, world, B, s):
+    from oracle import rgcn_oracle as oracle
+    V, R, E = 61, 4, 500
+    d = B * s
+    port = _free_port()
+    mp.spawn(_feature_worker, args=(world, port, V, R, E, B, s, str(tmp_path)), nprocs=world, join=True)
+    tr = synthetic_kg(V, R, E, seed=3, skewed=True)
+    g = torch.Generator().manual_seed(1)
+    dt = torch.float64
+    H = torch.randn(V, d, generator=g, dtype=dt).requires_grad_(True)
+    Wf, Wb = (torch.randn(R, B, s, s, generator=g, dtype=dt).requires_grad_(True) for _ in range(2))
+    Ws = torch.randn(d, d, generator=g, dtype=dt).requires_grad_(True)
+    mask = (torch.rand(V, d, generator=g) < 0.8).to(torch.uint8)
+    dOut = torch.randn(V, d, generator=g, dtype=dt)
+    nf, nb = oracle.graph_norms(tr, V, "canonical", np.float64)
+    ref = oracle.concat_gcn_forward(H, tr, Wf, Wb, Ws, nf, nb, mask, 0.8, True, dt)
+    ref.backward(dOut)
+    bounds = parallel.node_bounds(V, world)
+    for rank in range(world):
+        z = np.load(tmp_path / ("fs_%d.npz" % rank))
+        lo, hi = bounds[rank], bounds[rank + 1]
+        np.testing.assert_allclose(z["out"], ref.detach().numpy()[lo:hi], rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(z["dH"], H.grad.numpy()[lo:hi], rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(z["dWf"], Wf.grad.numpy(), rtol=1e-10, atol=1e-10)   # summed over ranks
+        np.testing.assert_allclose(z["dWb"], Wb.grad.numpy(), rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(z["dWs"], Ws.grad.numpy(), rtol=1e-10, atol=1e-10)
+
+
+def test_block_bounds_keep_rows_float4_aligned():
+    assert parallel.block_bounds(100, 5, 8) == [0, 12, 24, 36, 48, 60, 72, 84, 100]
+    assert parallel.block_bounds(64, 8, 8) == [0, 8, 16, 24, 32, 40, 48, 56, 64]
+    for B, s, world in [(100, 5, 8), (100, 5, 3), (64, 8, 4), (12, 6, 2)]:
+        b = parallel.block_bounds(B, s, world)
+        assert b[0] == 0 and b[-1] == B and all(x < y for x, y in zip(b, b[1:]))
+        assert all(((y - x) * s) % 4 == 0 for x, y in zip(b, b[1:]))
+    with pytest.raises(ValueError):
+        parallel.block_bounds(10, 5, 2)      # 10 blocks of 5 cannot be dealt in groups of 4 blocks
+    with pytest.raises(ValueError):
+        parallel.block_bounds(4, 8, 8)       # fewer column groups than ranks
