@@ -537,7 +537,10 @@ __global__ void __launch_bounds__(RGCN_THREADS, (FUSE_DW || S * NV > 16) ? 1 : (
 // row is exchanged through a double-buffered shared-memory row per group and ONE named barrier
 // (bar.sync id, 32*G) per run.
 // ------------------------------------------------------------------------------------------------
-template <int S, int G, bool FUSE_DW>
+// SEL = true (opt-in, RGCN_RELG_SEL=1; not yet validated on a GPU): a quad's four output columns lie in at most
+// two consecutive blocks, so the S inputs of each of those two blocks are read from shared memory ONCE
+// (2*S LDS instead of 4*S) and routed to the columns with selects -- the kernel is L1-wavefront bound.
+template <int S, int G, bool FUSE_DW, bool SEL = false>
 __global__ void __launch_bounds__(RGCN_THREADS, FUSE_DW ? 2 : 3)
     k_block_relg(const WorkItem* __restrict__ items, int n_items, const int32_t* __restrict__ r_row,
                  const int32_t* __restrict__ r_nbr, const float* __restrict__ r_norm,
@@ -571,6 +574,12 @@ __global__ void __launch_bounds__(RGCN_THREADS, FUSE_DW ? 2 : 3)
 #pragma unroll
     for (int c = 0; c < 4; ++c) xo[k][c] = ((colq[k] + c) / S) * S;
   }
+  bool hi[NV][4];  // column c of quad k belongs to the SECOND of the (at most two) blocks the quad touches
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) hi[k][c] = xo[k][c] != xo[k][0];
+  }
   float4 xs[NV], hcur[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) xs[k] = hcur[k] = zero4();
@@ -588,10 +597,26 @@ __global__ void __launch_bounds__(RGCN_THREADS, FUSE_DW ? 2 : 3)
     for (int k = 0; k < NV; ++k) {
       if (colq[k] < d) {
         float4 y = zero4();
+        float xa[S], xh[S];
+        if (SEL) {
+#pragma unroll
+          for (int j = 0; j < S; ++j) {
+            xa[j] = xb[xo[k][0] + j];
+            xh[j] = xb[xo[k][0] + S + j];  // unconditional: stays inside the 512-float buffer (d <= 512 - S), unused unless hi
+          }
+        }
 #pragma unroll
         for (int j = 0; j < S; ++j) {
-          const float x0 = xb[xo[k][0] + j], x1 = xb[xo[k][1] + j];
-          const float x2 = xb[xo[k][2] + j], x3 = xb[xo[k][3] + j];
+          float x0, x1, x2, x3;
+          if (SEL) {
+            x0 = xa[j];
+            x1 = hi[k][1] ? xh[j] : xa[j];
+            x2 = hi[k][2] ? xh[j] : xa[j];
+            x3 = hi[k][3] ? xh[j] : xa[j];
+          } else {
+            x0 = xb[xo[k][0] + j], x1 = xb[xo[k][1] + j];
+            x2 = xb[xo[k][2] + j], x3 = xb[xo[k][3] + j];
+          }
           y.x = fmaf(wreg[j][k].x, x0, y.x);
           y.y = fmaf(wreg[j][k].y, x1, y.y);
           y.z = fmaf(wreg[j][k].z, x2, y.z);
@@ -636,10 +661,13 @@ __global__ void __launch_bounds__(RGCN_THREADS, FUSE_DW ? 2 : 3)
         const float* xr = X + (size_t)src * ldx;
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-          const bool ok = colq[k] < d;
-          x[u][k] = ok ? ldg4(xr + colq[k]) : zero4();
+          // SEL: lanes past the row end load the row's last quad instead of nothing (their weights are zero and
+          // they never store), which removes the predicated-move scaffolding around every gather
+          const bool ok = SEL ? true : colq[k] < d;
+          const int cq = SEL ? min(colq[k], d - 4) : colq[k];
+          x[u][k] = ok ? ldg4(xr + cq) : zero4();
           if (FUSE_DW)
-            hx[FUSE_DW ? u : 0][k] = (ok && starts[u]) ? ldg4(Hrow + (size_t)rv[u] * ldh + colq[k]) : zero4();
+            hx[FUSE_DW ? u : 0][k] = (ok && starts[u]) ? ldg4(Hrow + (size_t)rv[u] * ldh + cq) : zero4();
         }
       }
 #pragma unroll
@@ -1163,7 +1191,13 @@ int launch_block_rel(const WorkItem* items, int n_items, const int32_t* r_row, c
     if (G == 4 || G == 2) {
       const int groups = RGCN_WARPS_PER_BLOCK / G;
       dim3 grid((n_items + groups - 1) / groups);
-      if (G == 4) {
+      static const bool sel = [] { const char* e = std::getenv("RGCN_RELG_SEL"); return e && std::atoi(e) == 1; }();
+      if (G == 4 && sel) {
+        if (fuse)
+          k_block_relg<5, 4, true, true><<<grid, RGCN_THREADS, 0, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt);
+        else
+          k_block_relg<5, 4, false, true><<<grid, RGCN_THREADS, 0, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt);
+      } else if (G == 4) {
         if (fuse)
           k_block_relg<5, 4, true><<<grid, RGCN_THREADS, 0, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt);
         else
