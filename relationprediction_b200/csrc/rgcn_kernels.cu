@@ -1191,7 +1191,8 @@ int launch_block_rel(const WorkItem* items, int n_items, const int32_t* r_row, c
     if (G == 4 || G == 2) {
       const int groups = RGCN_WARPS_PER_BLOCK / G;
       dim3 grid((n_items + groups - 1) / groups);
-      static const bool sel = [] { const char* e = std::getenv("RGCN_RELG_SEL"); return e && std::atoi(e) == 1; }();
+      const char* sel_env = std::getenv("RGCN_RELG_SEL");  // read per launch so tests can toggle it
+      const bool sel = sel_env && std::atoi(sel_env) == 1;
       if (G == 4 && sel) {
         if (fuse)
           k_block_relg<5, 4, true, true><<<grid, RGCN_THREADS, 0, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt);
