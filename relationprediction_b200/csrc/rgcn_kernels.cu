@@ -377,7 +377,10 @@ __global__ void __launch_bounds__(RGCN_THREADS, 1)
 // by L2-sized supertiles of rows, graph.cu).  Weight traffic drops from d*s*4 bytes per run to
 // d*s*4 bytes per item; the price is a non-deterministic fp32 summation order across items.
 // ------------------------------------------------------------------------------------------------
-template <int S, int NV, bool FUSE_DW>
+// LEAN = true (opt-in, RGCN_LEAN=1; not yet validated on a GPU): lanes past the row end gather a clamped
+// column instead of being predicated off (their weights are zero and they never store) -- the predicated form
+// costs ~4 moves + a zero-init per 128-bit load in SASS.
+template <int S, int NV, bool FUSE_DW, bool LEAN = false>
 __global__ void __launch_bounds__(RGCN_THREADS, (FUSE_DW || S * NV > 16) ? 1 : (S * NV > 8 ? 2 : 3))
     k_block_rel(const WorkItem* __restrict__ items, int n_items, const int32_t* __restrict__ r_row,
                 const int32_t* __restrict__ r_nbr, const float* __restrict__ r_norm,
@@ -489,8 +492,9 @@ __global__ void __launch_bounds__(RGCN_THREADS, (FUSE_DW || S * NV > 16) ? 1 : (
         const float* xr = X + (size_t)src * ldx + c0;
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-          const int lc = 4 * (lane + 32 * k);
-          const bool ok = c0 + lc < d;
+          const int lc0 = 4 * (lane + 32 * k);
+          const bool ok = LEAN ? true : c0 + lc0 < d;
+          const int lc = LEAN ? min(lc0, d - 4 - c0) : lc0;
           x[u][k] = ok ? ldg4(xr + lc) : zero4();
           if (FUSE_DW)  // the run's own H row travels with the run's first gathered row
             hx[FUSE_DW ? u : 0][k] = (ok && starts[u]) ? ldg4(Hrow + (size_t)rv[u] * ldh + c0 + lc) : zero4();
@@ -537,7 +541,7 @@ __global__ void __launch_bounds__(RGCN_THREADS, (FUSE_DW || S * NV > 16) ? 1 : (
 // row is exchanged through a double-buffered shared-memory row per group and ONE named barrier
 // (bar.sync id, 32*G) per run.
 // ------------------------------------------------------------------------------------------------
-// SEL = true (opt-in, RGCN_RELG_SEL=1; not yet validated on a GPU): a quad's four output columns lie in at most
+// SEL = true (opt-in, RGCN_LEAN=1; not yet validated on a GPU): a quad's four output columns lie in at most
 // two consecutive blocks, so the S inputs of each of those two blocks are read from shared memory ONCE
 // (2*S LDS instead of 4*S) and routed to the columns with selects -- the kernel is L1-wavefront bound.
 template <int S, int G, bool FUSE_DW, bool SEL = false>
@@ -1134,16 +1138,21 @@ int launch_block_dw(const WorkItem* items, int n_items, const int32_t* r_dst, co
 }
 
 
-template <int S, int NV, bool FUSE>
+template <int S, int NV, bool FUSE, bool LEAN = false>
 static int launch_block_rel_t(const WorkItem* items, int n_items, const int32_t* r_row,
                               const int32_t* r_nbr, const float* r_norm, const float* X, int ldx,
                               int d, const float* Wt, float* out, const float* Hrow, int ldh,
                               float* dWt, cudaStream_t st) {
   const int slabs = (d + NV * 128 - 1) / (NV * 128);
   dim3 grid((n_items + RGCN_WARPS_PER_BLOCK - 1) / RGCN_WARPS_PER_BLOCK, slabs);
-  k_block_rel<S, NV, FUSE><<<grid, RGCN_THREADS, 0, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx,
-                                                           d, Wt, out, Hrow, ldh, dWt);
+  k_block_rel<S, NV, FUSE, LEAN><<<grid, RGCN_THREADS, 0, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx,
+                                                                 d, Wt, out, Hrow, ldh, dWt);
   return check_launch("k_block_rel");
+}
+
+static bool lean_kernels_requested() {  // read per launch so tests can toggle it
+  const char* e = std::getenv("RGCN_LEAN");
+  return e && std::atoi(e) == 1;
 }
 
 bool block_rel_supported(int d, int s) {
@@ -1191,8 +1200,7 @@ int launch_block_rel(const WorkItem* items, int n_items, const int32_t* r_row, c
     if (G == 4 || G == 2) {
       const int groups = RGCN_WARPS_PER_BLOCK / G;
       dim3 grid((n_items + groups - 1) / groups);
-      const char* sel_env = std::getenv("RGCN_RELG_SEL");  // read per launch so tests can toggle it
-      const bool sel = sel_env && std::atoi(sel_env) == 1;
+      const bool sel = lean_kernels_requested();
       if (G == 4 && sel) {
         if (fuse)
           k_block_relg<5, 4, true, true><<<grid, RGCN_THREADS, 0, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt);
@@ -1215,6 +1223,13 @@ int launch_block_rel(const WorkItem* items, int n_items, const int32_t* r_row, c
   } else if (s == 4) {
     switch (nv) { case 1: RL(4, 1); case 2: RL(4, 2); case 3: RL(4, 3); default: RL(4, 4); }
   } else if (s == 8) {
+    if (lean_kernels_requested()) {
+      if (nv == 1)
+        return fuse ? launch_block_rel_t<8, 1, true, true>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt, st)
+                    : launch_block_rel_t<8, 1, false, true>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt, st);
+      return fuse ? launch_block_rel_t<8, 2, true, true>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt, st)
+                  : launch_block_rel_t<8, 2, false, true>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt, st);
+    }
     if (nv == 1) RL(8, 1);
     RL(8, 2);
   } else if (s == 16) {
