@@ -1,0 +1,21 @@
+#!/bin/bash
+# A/B of the opt-in variants that were written without GPU access (one B200, ~2 min):
+#   1. parity of the lean kernels (the xfail-guarded test reports XPASS / XFAIL per shape)
+#   2. default vs RGCN_LEAN=1 on the FB15k-237 shape (s=5 group kernel) and on the synthetic shape (s=8)
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_parity.py -q -m gpu -k lean -rxX 2>&1 | tail -15
+for lean in 0 1; do
+  RGCN_LEAN=$lean python bench.py --steps 100 --no-cpu-baseline --no-e2e > gpurun_out/ab_fb_lean$lean.json 2>/dev/null
+  RGCN_LEAN=$lean python bench.py --workload synthetic --scale 0.02 --steps 30 --no-cpu-baseline --no-e2e \
+      > gpurun_out/ab_syn_lean$lean.json 2>/dev/null
+done
+python - <<'PY'
+import json
+for name in ("fb", "syn"):
+    for lean in (0, 1):
+        try:
+            j = json.loads(open("gpurun_out/ab_%s_lean%d.json" % (name, lean)).read().strip().splitlines()[-1])
+            print(name, "lean=%d" % lean, "%.1f M-edges/s" % j["value"], "%.4f ms" % j["ms_per_step"], j.get("stages_ms"))
+        except Exception as exc:
+            print(name, lean, "failed:", exc)
+PY
