@@ -76,6 +76,15 @@ int rgcn_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb
 int rgcn_sample_edge_neighborhood(const int32_t* triples_host, int64_t E, int32_t V, int64_t sample_size,
                                   uint64_t seed, int32_t* out_edges_host);
 
+/* The same sampler with the per-dataset incidence structure built once: create a handle for the training
+ * triples, then draw any number of samples from it.  Draws are thread-compatible (the handle is read-only, every
+ * draw owns its scratch copies), so host threads can prepare samples concurrently.  A draw with the same seed
+ * returns exactly what rgcn_sample_edge_neighborhood returns. */
+typedef struct rgcn_sampler rgcn_sampler_t;
+int rgcn_sampler_create(const int32_t* triples_host, int64_t E, int32_t V, rgcn_sampler_t** out);
+int rgcn_sampler_draw(const rgcn_sampler_t* sampler, int64_t sample_size, uint64_t seed, int32_t* out_edges_host);
+void rgcn_sampler_destroy(rgcn_sampler_t* sampler);
+
 /* Next row N1: global-norm clipping + Adam with TensorFlow-1.x semantics
  * (optimization/tensorflow_backend/algorithms.py:65-68 and :36-42).  Call rgcn_sumsq_accumulate on every
  * gradient tensor into one zeroed device float, then rgcn_adam_update on every (param, grad, m, v) with that

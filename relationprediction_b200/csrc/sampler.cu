@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <new>
 #include <random>
 #include <string>
 #include <vector>
@@ -50,46 +51,78 @@ struct Fenwick {
 
 }  // namespace
 
-extern "C" int rgcn_sample_edge_neighborhood(const int32_t* triples_host, int64_t E, int32_t V,
-                                             int64_t sample_size, uint64_t seed,
-                                             int32_t* out_edges_host) {
-  if (!triples_host || !out_edges_host || E <= 0 || V <= 0 || sample_size < 0 || sample_size > E) {
-    rgcn_set_error("rgcn_sample_edge_neighborhood: need 0 <= sample_size <= E, E > 0, V > 0");
+// Immutable per-dataset part: incidence lists in their pristine order.  A draw copies the mutable arrays
+// (~20 B per edge, a memcpy) instead of rebuilding them, which was more than half of a 30 000-edge sample.
+struct rgcn_sampler {
+  int64_t E = 0;
+  int32_t V = 0;
+  std::vector<int32_t> sub, obj;             // endpoints of every edge
+  std::vector<int64_t> off;                  // V+1 list offsets
+  std::vector<int32_t> inc_edge, inc_other;  // 2E entries: every edge once per endpoint
+  std::vector<int32_t> pos_s, pos_o;         // where the edge sits in its subject's / object's list
+  std::vector<int64_t> any_tree;             // Fenwick tree over [degree > 0]
+};
+
+namespace {
+
+int sampler_build(const int32_t* triples_host, int64_t E, int32_t V, rgcn_sampler& sp) {
+  if (!triples_host || E <= 0 || V <= 0 || 2 * E >= (int64_t)1 << 31) {
+    rgcn_set_error("edge sampler: need E > 0, V > 0 and fewer than 2^30 edges");
     return RGCN_ERR_INVALID;
   }
-  // incidence lists: every edge appears once in its subject's and once in its object's list
-  std::vector<int64_t> off((size_t)V + 1, 0);
+  sp.E = E;
+  sp.V = V;
+  sp.sub.resize((size_t)E);
+  sp.obj.resize((size_t)E);
+  sp.off.assign((size_t)V + 1, 0);
   for (int64_t e = 0; e < E; ++e) {
     const int32_t s = triples_host[3 * e], o = triples_host[3 * e + 2];
     if (s < 0 || s >= V || o < 0 || o >= V) {
-      rgcn_set_error("rgcn_sample_edge_neighborhood: entity id out of range");
+      rgcn_set_error("edge sampler: entity id out of range");
       return RGCN_ERR_INVALID;
     }
-    off[s + 1]++;
-    off[o + 1]++;
+    sp.sub[e] = s;
+    sp.obj[e] = o;
+    sp.off[s + 1]++;
+    sp.off[o + 1]++;
   }
-  for (int32_t v = 0; v < V; ++v) off[v + 1] += off[v];
-  std::vector<int32_t> inc_edge((size_t)2 * E), inc_other((size_t)2 * E);
-  std::vector<int64_t> pos_s((size_t)E), pos_o((size_t)E);  // where the edge sits in each endpoint's list
-  {
-    std::vector<int64_t> cur(off.begin(), off.end() - 1);
-    for (int64_t e = 0; e < E; ++e) {
-      const int32_t s = triples_host[3 * e], o = triples_host[3 * e + 2];
-      pos_s[e] = cur[s]++;
-      inc_edge[pos_s[e]] = (int32_t)e;
-      inc_other[pos_s[e]] = o;
-      pos_o[e] = cur[o]++;
-      inc_edge[pos_o[e]] = (int32_t)e;
-      inc_other[pos_o[e]] = s;
-    }
+  for (int32_t v = 0; v < V; ++v) sp.off[v + 1] += sp.off[v];
+  sp.inc_edge.resize((size_t)2 * E);
+  sp.inc_other.resize((size_t)2 * E);
+  sp.pos_s.resize((size_t)E);
+  sp.pos_o.resize((size_t)E);
+  std::vector<int64_t> cur(sp.off.begin(), sp.off.end() - 1);
+  for (int64_t e = 0; e < E; ++e) {
+    const int32_t s = sp.sub[e], o = sp.obj[e];
+    sp.pos_s[e] = (int32_t)cur[s]++;
+    sp.inc_edge[sp.pos_s[e]] = (int32_t)e;
+    sp.inc_other[sp.pos_s[e]] = o;
+    sp.pos_o[e] = (int32_t)cur[o]++;
+    sp.inc_edge[sp.pos_o[e]] = (int32_t)e;
+    sp.inc_other[sp.pos_o[e]] = s;
   }
+  Fenwick any(V);
+  for (int32_t v = 0; v < V; ++v)
+    if (sp.off[v + 1] > sp.off[v]) any.add(v, 1);
+  sp.any_tree = any.t;
+  return RGCN_OK;
+}
+
+int sampler_draw(const rgcn_sampler& sp, int64_t sample_size, uint64_t seed, int32_t* out_edges_host) {
+  const int64_t E = sp.E;
+  const int32_t V = sp.V;
+  if (!out_edges_host || sample_size < 0 || sample_size > E) {
+    rgcn_set_error("edge sampler: need 0 <= sample_size <= E");
+    return RGCN_ERR_INVALID;
+  }
+  const std::vector<int64_t>& off = sp.off;
+  std::vector<int32_t> inc_edge(sp.inc_edge), inc_other(sp.inc_other), pos_s(sp.pos_s), pos_o(sp.pos_o);
   std::vector<int64_t> live((size_t)V);  // number of unpicked entries at the front of each list
   for (int32_t v = 0; v < V; ++v) live[v] = off[v + 1] - off[v];
   std::vector<char> seen((size_t)V, 0);
   Fenwick w_seen(V);  // weight = live[v] if seen[v] else 0
   Fenwick w_any(V);   // weight = 1 if live[v] > 0
-  for (int32_t v = 0; v < V; ++v)
-    if (live[v] > 0) w_any.add(v, 1);
+  w_any.t = sp.any_tree;
 
   std::mt19937_64 rng(seed);
   auto uniform = [&](int64_t n) { return (int64_t)(rng() % (uint64_t)n); };
@@ -102,13 +135,11 @@ extern "C" int rgcn_sample_edge_neighborhood(const int32_t* triples_host, int64_
       std::swap(inc_edge[p], inc_edge[last]);
       std::swap(inc_other[p], inc_other[last]);
       // the moved entry belongs to edge e2: fix whichever of its two positions pointed at `last`
-      if (pos_s[e2] == last && triples_host[3 * (int64_t)e2] == v)
-        pos_s[e2] = p;
+      if (pos_s[e2] == last && sp.sub[e2] == v)
+        pos_s[e2] = (int32_t)p;
       else
-        pos_o[e2] = p;
+        pos_o[e2] = (int32_t)p;
     }
-    const int32_t e = inc_edge[last];
-    (void)e;
     live[v]--;
     if (seen[v]) w_seen.add(v, -1);
     if (live[v] == 0) w_any.add(v, -1);
@@ -128,7 +159,7 @@ extern "C" int rgcn_sample_edge_neighborhood(const int32_t* triples_host, int64_
     } else {
       const int64_t alive = w_any.total();
       if (alive <= 0) {
-        rgcn_set_error("rgcn_sample_edge_neighborhood: ran out of edges");
+        rgcn_set_error("edge sampler: ran out of edges");
         return RGCN_ERR_INVALID;
       }
       v = w_any.find(uniform(alive));
@@ -139,7 +170,7 @@ extern "C" int rgcn_sample_edge_neighborhood(const int32_t* triples_host, int64_
     const int32_t other = inc_other[p];
     out_edges_host[i] = e;
     // drop the edge from both endpoints' lists (a self loop sits twice in the same list)
-    const int32_t s = triples_host[3 * (int64_t)e], o = triples_host[3 * (int64_t)e + 2];
+    const int32_t s = sp.sub[e], o = sp.obj[e];
     if (s == o) {
       // two entries in v's list: remove the one at the larger position first so the other index stays valid
       const int64_t a = std::max(pos_s[e], pos_o[e]), b = std::min(pos_s[e], pos_o[e]);
@@ -152,4 +183,64 @@ extern "C" int rgcn_sample_edge_neighborhood(const int32_t* triples_host, int64_
     mark_seen(other);
   }
   return RGCN_OK;
+}
+
+}  // namespace
+
+extern "C" int rgcn_sampler_create(const int32_t* triples_host, int64_t E, int32_t V, rgcn_sampler** out) {
+  if (!out) {
+    rgcn_set_error("rgcn_sampler_create: null output");
+    return RGCN_ERR_INVALID;
+  }
+  *out = nullptr;
+  rgcn_sampler* sp = new (std::nothrow) rgcn_sampler();
+  if (!sp) return RGCN_ERR_NOMEM;
+  try {
+    const int rc = sampler_build(triples_host, E, V, *sp);
+    if (rc != RGCN_OK) {
+      delete sp;
+      return rc;
+    }
+  } catch (const std::bad_alloc&) {
+    delete sp;
+    rgcn_set_error("rgcn_sampler_create: out of host memory");
+    return RGCN_ERR_NOMEM;
+  }
+  *out = sp;
+  return RGCN_OK;
+}
+
+// thread-compatible: concurrent draws on one handle are fine (the handle is read-only, each draw owns its copies)
+extern "C" int rgcn_sampler_draw(const rgcn_sampler* sp, int64_t sample_size, uint64_t seed,
+                                 int32_t* out_edges_host) {
+  if (!sp) {
+    rgcn_set_error("rgcn_sampler_draw: null handle");
+    return RGCN_ERR_INVALID;
+  }
+  try {
+    return sampler_draw(*sp, sample_size, seed, out_edges_host);
+  } catch (const std::bad_alloc&) {
+    rgcn_set_error("rgcn_sampler_draw: out of host memory");
+    return RGCN_ERR_NOMEM;
+  }
+}
+
+extern "C" void rgcn_sampler_destroy(rgcn_sampler* sp) { delete sp; }
+
+extern "C" int rgcn_sample_edge_neighborhood(const int32_t* triples_host, int64_t E, int32_t V,
+                                             int64_t sample_size, uint64_t seed,
+                                             int32_t* out_edges_host) {
+  if (!triples_host || !out_edges_host || E <= 0 || V <= 0 || sample_size < 0 || sample_size > E) {
+    rgcn_set_error("rgcn_sample_edge_neighborhood: need 0 <= sample_size <= E, E > 0, V > 0");
+    return RGCN_ERR_INVALID;
+  }
+  rgcn_sampler sp;
+  try {
+    const int rc = sampler_build(triples_host, E, V, sp);
+    if (rc != RGCN_OK) return rc;
+    return sampler_draw(sp, sample_size, seed, out_edges_host);
+  } catch (const std::bad_alloc&) {
+    rgcn_set_error("rgcn_sample_edge_neighborhood: out of host memory");
+    return RGCN_ERR_NOMEM;
+  }
 }

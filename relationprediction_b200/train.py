@@ -118,6 +118,42 @@ def sample_edge_neighborhood_fast(triples, n_entities, sample_size):
     return out
 
 
+class EdgeNeighborhoodSampler(object):
+    """The library sampler with the per-dataset incidence structure built once (rgcn_sampler_create); draw()
+    may be called from several host threads at once.  Seeds come from numpy's global stream."""
+
+    def __init__(self, triples, n_entities):
+        import ctypes
+
+        from . import _lib
+        self._lib = _lib
+        self._tri = np.ascontiguousarray(triples, dtype=np.int32)
+        self._h = ctypes.c_void_p()
+        rc = _lib.load().rgcn_sampler_create(ctypes.c_void_p(self._tri.ctypes.data), self._tri.shape[0],
+                                             int(n_entities), ctypes.byref(self._h))
+        _lib.check(rc, "rgcn_sampler_create")
+
+    def draw(self, sample_size, seed=None):
+        import ctypes
+        out = np.empty(int(sample_size), dtype=np.int32)
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1))
+        rc = self._lib.load().rgcn_sampler_draw(self._h, int(sample_size), int(seed), ctypes.c_void_p(out.ctypes.data))
+        self._lib.check(rc, "rgcn_sampler_draw")
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.load().rgcn_sampler_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: the module globals may already be gone
+            pass
+
+
 def sample_edge_neighborhood(adj_list, degrees, n_triplets, sample_size):
     """Neighbourhood-expansion edge sampler (train.py:161-198), same sequential algorithm (reference
     restatement; kept as the statistical oracle of sample_edge_neighborhood_fast)."""
@@ -192,12 +228,16 @@ def main(argv=None):
         adj_list[o].append((i, s))
     degrees = np.array([len(a) for a in adj_list])
 
+    edge_sampler = None
+    if encoder.needs_graph() and 'GraphBatchSize' in general and int(general['GraphBatchSize']) < len(train):
+        edge_sampler = EdgeNeighborhoodSampler(train, len(entities))
+
     def sample():
         if not encoder.needs_graph():
             X, Y = ns.transform(train)
             return (X, Y)
         if 'GraphBatchSize' in general and int(general['GraphBatchSize']) < len(train):
-            ids = sample_edge_neighborhood_fast(train, len(entities), int(general['GraphBatchSize']))
+            ids = edge_sampler.draw(int(general['GraphBatchSize']))
         else:
             ids = np.arange(len(train))
         graph_batch = train[ids]

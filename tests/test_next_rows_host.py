@@ -4,6 +4,7 @@ sampler (common/auxilliaries.py)."""
 import os
 
 import numpy as np
+import pytest
 
 from relationprediction_b200.common import auxilliaries, evaluation
 from conftest import GOLDEN
@@ -198,3 +199,40 @@ def test_early_stopper_follows_reference_rule(capsys):
     assert "Stopping criterion reached" in capsys.readouterr().out
     es2 = EarlyStopper(10)
     assert es2.update(10, 0.5) is False and es2.update(20, 0.4) is True
+
+
+def test_sampler_handle_matches_one_shot_and_is_thread_compatible():
+    """rgcn_sampler_create / _draw: same seed -> same sample as rgcn_sample_edge_neighborhood; concurrent draws on
+    one handle do not disturb each other (the handle is read-only)."""
+    import ctypes
+    import threading
+    from relationprediction_b200 import _lib
+    from relationprediction_b200.train import EdgeNeighborhoodSampler
+    rng = np.random.RandomState(4)
+    V, E = 300, 4000
+    tr = np.stack([rng.randint(0, V, E), rng.randint(0, 5, E), (rng.zipf(1.5, E) - 1) % V], 1).astype(np.int32)
+    tr[:7, 2] = tr[:7, 0]                                    # a few self loops
+    s = EdgeNeighborhoodSampler(tr, V)
+    for seed, n in ((1, 500), (2, 4000), (3, 0), (4, 1)):
+        one = np.empty(max(n, 1), dtype=np.int32)
+        rc = _lib.load().rgcn_sample_edge_neighborhood(ctypes.c_void_p(tr.ctypes.data), E, V, n, seed,
+                                                       ctypes.c_void_p(one.ctypes.data))
+        assert rc == 0
+        got = s.draw(n, seed=seed)
+        assert np.array_equal(got, one[:n]) and len(set(got.tolist())) == n
+    expect = {seed: s.draw(1500, seed=seed) for seed in range(8)}
+    results = {}
+
+    def work(seed):
+        for _ in range(5):
+            results[seed] = s.draw(1500, seed=seed)
+    threads = [threading.Thread(target=work, args=(seed,)) for seed in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for seed in range(8):
+        assert np.array_equal(results[seed], expect[seed])
+    with pytest.raises(_lib.RgcnError):
+        s.draw(E + 1)
+    s.close()
