@@ -104,3 +104,17 @@ def test_early_stopping_breaks_the_loop_on_cpu(toy, tmp_path, capsys, cpu_driver
                  "--final-eval", "0", "--no-early-stopping"])
     text = capsys.readouterr().out
     assert json.loads([l for l in text.splitlines() if l.startswith("{")][-1])["iterations"] == 130
+
+
+def test_graph_batch_sampling_path_on_cpu(toy, tmp_path, capsys, cpu_driver):
+    """GraphBatchSize < |train| (the FB15k-237 configuration): every step draws a neighbourhood sample from the
+    library's sampler handle, splits it, and corrupts it; prefetch threads share the one handle."""
+    write_toy(toy, tmp_path)
+    exp = tmp_path / "toy.exp"
+    exp.write_text(TOY_EXP.format(layers=2, concat="Yes").replace("\tGraphSplitSize=0.5",
+                                                                   "\tGraphSplitSize=0.5\n\tGraphBatchSize=20"))
+    np.random.seed(0)
+    driver.main(["--settings", str(exp), "--dataset", str(tmp_path), "--max-iterations", "25", "--device", "cpu",
+                 "--prefetch", "3", "--no-periodic-eval", "--final-eval", "0"])
+    line = json.loads([l for l in capsys.readouterr().out.splitlines() if l.startswith("{")][-1])
+    assert line["iterations"] == 25 and 0.0 < line["filtered"]["MRR"] <= 1.0
