@@ -19,3 +19,14 @@ for name in ("fb", "syn"):
         except Exception as exc:
             print(name, lean, "failed:", exc)
 PY
+# 3. the component-major path (block_algo = 2): parity, then the FB15k-237-shape bench
+python -m pytest tests/test_gpu_parity.py -q -m gpu -k component_major -rxX 2>&1 | tail -8
+RGCN_BLOCK_ALGO=2 python bench.py --steps 100 --no-cpu-baseline --no-e2e > gpurun_out/ab_fb_cm.json 2>/dev/null
+python - <<'PY'
+import json
+try:
+    j = json.loads(open("gpurun_out/ab_fb_cm.json").read().strip().splitlines()[-1])
+    print("fb component-major", "%.1f M-edges/s" % j["value"], "%.4f ms" % j["ms_per_step"], j.get("stages_ms"))
+except Exception as exc:
+    print("component-major bench failed:", exc)
+PY

@@ -141,6 +141,27 @@ def test_lean_group_kernel_opt_in(monkeypatch, d, B):
         assert_close("d" + k, grads[k], ref_g[k].numpy())
 
 
+@pytest.mark.xfail(reason="experimental component-major path (RGCN_BLOCK_ALGO=2, csrc/block_cm.cu) written without "
+                          "GPU access: reports XPASS once it is validated, never blocks the suite", strict=False)
+@pytest.mark.parametrize("d,B,drop", [(500, 100, False), (500, 100, True), (40, 8, False), (260, 52, True)])
+def test_component_major_path_opt_in(monkeypatch, d, B, drop):
+    monkeypatch.setenv("RGCN_BLOCK_ALGO", "2")
+    V, R, E = 1500, 23, 12000
+    tr = synthetic_kg(V, R, E, seed=11, skewed=True)
+    rng = np.random.RandomState(5)
+    H = rng.normal(0, 1, (V, d)).astype(np.float32)
+    dOut = rng.normal(0, 1, (V, d)).astype(np.float32)
+    w = oracle.init_block_layer(rng, R, d, B)
+    mask = (rng.uniform(size=(V, d)) < 0.8).astype(np.uint8) if drop else None
+    keep = 0.8 if drop else 1.0
+    nf, nb = oracle.graph_norms(tr, V)
+    ref_out, ref_g = oracle.layer_fwd_bwd("block", H, tr, w, nf, nb, dOut, mask, keep, True, torch.float64)
+    out, grads = run_block(tr, V, R, d, B, H, w, dOut, mask, keep, True)
+    assert_close("out", out, ref_out.numpy())
+    for k in ("H", "W_forward", "W_backward", "W_self"):
+        assert_close("d" + k, grads[k], ref_g[k].numpy())
+
+
 def test_block_layer_supertiles(monkeypatch):
     """Weight-id-major path with several supertiles per view (forced small)."""
     monkeypatch.setenv("RGCN_SUPERTILE_ROWS", "100")
