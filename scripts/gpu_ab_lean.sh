@@ -3,7 +3,7 @@
 #   1. parity of the lean kernels (the xfail-guarded test reports XPASS / XFAIL per shape)
 #   2. default vs RGCN_LEAN=1 on the FB15k-237 shape (s=5 group kernel) and on the synthetic shape (s=8)
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_parity.py -q -m gpu -k lean -rxX 2>&1 | tail -15
+RGCN_RUN_EXPERIMENTAL=1 python -m pytest tests/test_gpu_parity.py -q -m gpu -k lean -rxX 2>&1 | tail -15
 for lean in 0 1; do
   RGCN_LEAN=$lean python bench.py --steps 100 --no-cpu-baseline --no-e2e > gpurun_out/ab_fb_lean$lean.json 2>/dev/null
   RGCN_LEAN=$lean python bench.py --workload synthetic --scale 0.02 --steps 30 --no-cpu-baseline --no-e2e \
@@ -20,7 +20,7 @@ for name in ("fb", "syn"):
             print(name, lean, "failed:", exc)
 PY
 # 3. the component-major path (block_algo = 2): parity, then the FB15k-237-shape bench
-python -m pytest tests/test_gpu_parity.py -q -m gpu -k component_major -rxX 2>&1 | tail -8
+RGCN_RUN_EXPERIMENTAL=1 python -m pytest tests/test_gpu_parity.py -q -m gpu -k component_major -rxX 2>&1 | tail -8
 RGCN_BLOCK_ALGO=2 python bench.py --steps 100 --no-cpu-baseline --no-e2e > gpurun_out/ab_fb_cm.json 2>/dev/null
 python - <<'PY'
 import json

@@ -13,6 +13,11 @@ from relationprediction_b200 import ops
 from conftest import synthetic_kg
 
 pytestmark = pytest.mark.gpu
+
+# kernels written without GPU access run only on request (scripts/gpu_ab_lean.sh): a faulting kernel would poison
+# the CUDA context for every later test of the process
+experimental = pytest.mark.skipif(os.environ.get("RGCN_RUN_EXPERIMENTAL") != "1",
+                                  reason="set RGCN_RUN_EXPERIMENTAL=1 to run the not-yet-validated kernels")
 TOL = 1e-4
 DEV = "cuda:0"
 
@@ -122,6 +127,7 @@ def test_block_layer_fwd_bwd_vs_oracle(V, R, E, d, B, skewed, drop):
         assert_close("d" + k, grads[k], ref_g[k].numpy())
 
 
+@experimental
 @pytest.mark.xfail(reason="opt-in lean kernels (RGCN_LEAN=1; s=5 group kernel, s=8 rel-major) written without GPU access: "
                           "reports XPASS once it is validated, never blocks the suite", strict=False)
 @pytest.mark.parametrize("d,B", [(500, 100), (40, 8), (260, 52), (512, 64), (200, 25)])
@@ -141,6 +147,7 @@ def test_lean_group_kernel_opt_in(monkeypatch, d, B):
         assert_close("d" + k, grads[k], ref_g[k].numpy())
 
 
+@experimental
 @pytest.mark.xfail(reason="experimental component-major path (RGCN_BLOCK_ALGO=2, csrc/block_cm.cu) written without "
                           "GPU access: reports XPASS once it is validated, never blocks the suite", strict=False)
 @pytest.mark.parametrize("d,B,drop", [(500, 100, False), (500, 100, True), (40, 8, False), (260, 52, True)])
