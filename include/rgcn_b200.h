@@ -50,7 +50,9 @@ int64_t rgcn_launch_count(void);
 
 /* Library options.  "block_algo": 0 = destination-major aggregation (deterministic summation order,
  * epilogue fused), 1 = weight-id-major aggregation (block weights in registers, vector reductions
- * in L2; fastest, fp32 summation order not reproducible run to run), -1 = auto (default).
+ * in L2; fastest, fp32 summation order not reproducible run to run), -1 = auto (default),
+ * 2 = EXPERIMENTAL component-major path for 5x5 blocks (rgcn_block_forward / rgcn_block_backward only;
+ * falls back to 1 for other shapes; not yet validated on hardware -- never selected automatically).
  * The environment variable RGCN_BLOCK_ALGO overrides the option. */
 int rgcn_set_option(const char* name, int64_t value);
 
