@@ -46,4 +46,7 @@ class AffineTransform(Model):
             h = self._finish(self.W)
             return h, None, h
         codes = self.next_component.get_all_codes(mode=mode)
+        if codes[0] is codes[2]:   # one entity-code matrix (every R-GCN encoder): project it once, and keep it ONE
+            h = self._finish(codes[0] @ self.W)   # tensor so the DistMult kernel can gather both ends from it
+            return h, codes[1], h
         return self._finish(codes[0] @ self.W), codes[1], self._finish(codes[2] @ self.W)

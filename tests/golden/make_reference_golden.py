@@ -77,9 +77,10 @@ class EagerScoringAdapter(object):
         for comp in chain(self.model):
             if comp.__class__.__name__ == 'Representation':
                 comp.graph = None
-        gX, dX = self.model.get_test_input_variables()
-        gX.feed(self.test_graph)
-        dX.feed(np.asarray(triplets))
+        feeds = self.model.get_test_input_variables()
+        if self.model.needs_graph():
+            feeds[0].feed(self.test_graph)
+        feeds[-1].feed(np.asarray(triplets))
 
     def score_all_subjects(self, triplets):
         self._feed(triplets)
@@ -116,10 +117,11 @@ def run_case(name, settings_file, overrides, train, test, V, R, seed, grouping, 
     graph_split = train[rng.choice(len(train), size=split, replace=False)]
     np.random.seed(seed + 3)
     X, Y = auxilliaries.NegativeSampler(int(general['NegativeSampleRate']), V).transform(train)
-    gX, dX, dY = model.get_train_input_variables()
-    gX.feed(graph_split)
-    dX.feed(X)
-    dY.feed(Y)
+    feeds = model.get_train_input_variables()       # [graph_edges, X, Y], or [X, Y] for the graph-less encoder
+    if model.needs_graph():
+        feeds[0].feed(graph_split)
+    feeds[-2].feed(X)
+    feeds[-1].feed(Y)
     weights = model.get_weights()
     loss = model.get_loss(mode='train')
     reg = model.get_regularization()
@@ -141,9 +143,10 @@ def run_case(name, settings_file, overrides, train, test, V, R, seed, grouping, 
     for comp in chain(model):
         if hasattr(comp, 'graph') and comp.__class__.__name__ == 'Representation':
             comp.graph = None
-    tgX, tdX = model.get_test_input_variables()
-    tgX.feed(train)
-    tdX.feed(test)
+    tfeeds = model.get_test_input_variables()
+    if model.needs_graph():
+        tfeeds[0].feed(train)
+    tfeeds[-1].feed(test)
     with torch.no_grad():
         out[p + "test_graph"] = train.astype(np.int32)
         out[p + "test_X"] = test.astype(np.int32)
@@ -189,6 +192,14 @@ def main():
              "canonical", out)
     run_case("block_toy_1layer_canonical", "gcn_block.exp", widths(16, 4) + one, toy_train, toy_test, tV, tR, 6,
              "canonical", out)
+    # the two remaining factory branches on the path: the graph-less DistMult baseline (settings/distmult.exp,
+    # Name=embedding) and the output projection (UseOutputTransform=Yes) on top of the block layers
+    run_case("distmult_toy_canonical", "distmult.exp", [('Shared', 'CodeDimension', '24')], toy_train, toy_test,
+             tV, tR, 7, "canonical", out)
+    run_case("block_toy_outproj_canonical", "gcn_block.exp",
+             [('Encoder', 'InternalEncoderDimension', '20'), ('Shared', 'CodeDimension', '12'),
+              ('Encoder', 'NumberOfBasisFunctions', '4'), ('Encoder', 'UseOutputTransform', 'Yes')],
+             toy_train, toy_test, tV, tR, 8, "canonical", out)
     np.savez_compressed(os.path.join(HERE, "reference_model_golden.npz"), **out)
     print("wrote reference_model_golden.npz (%d arrays)" % len(out))
 

@@ -10,13 +10,10 @@ import torch
 from relationprediction_b200.common import model_builder
 from relationprediction_b200.encoders.message_gcns.message_gcn import MessageGcn
 from test_plugin_host import merged_settings
-from test_reference_golden import ALL, load_case, split_weights
+from test_reference_golden import ALL, CASE_SETTINGS, load_case, split_weights
 
 pytestmark = pytest.mark.gpu
 
-WIDTHS = {"block_toy_s5": ("gcn_block.exp", 40, 8), "block_syn_s8": ("gcn_block.exp", 32, 4),
-          "basis_toy": ("gcn_basis.exp", 24, 5), "basis_syn": ("gcn_basis.exp", 20, 3),
-          "basis_toy_1layer": ("gcn_basis.exp", 24, 2), "block_toy_1layer": ("gcn_block.exp", 16, 4)}
 
 
 def rel(a, b):
@@ -36,17 +33,14 @@ def layers_of(model):
 @pytest.mark.parametrize("name,variant,grouping,norm_mode", ALL)
 def test_product_matches_reference_code_outputs(toy, name, variant, grouping, norm_mode):
     c = load_case(name + "_" + grouping)
-    settings_file, d, B = WIDTHS[name]
+    settings_file, overrides = CASE_SETTINGS[name]
     V, R = int(c["V"]), int(c["R"])
     graph_split, X, Y = c["graph_split"], c["X"], c["Y"]
     enc, dec = merged_settings(toy, settings_file, V, R, len(c["test_graph"]))
     for s in (enc, dec):
-        s.put("InternalEncoderDimension", str(d))
-        s.put("CodeDimension", str(d))
-        s.put("NumberOfBasisFunctions", str(B))
+        for k, v in overrides.items():
+            s.put(k, v)
         s.put("NormalizationMode", norm_mode)
-        if name.endswith("_1layer"):
-            s.put("NumberOfLayers", "1")
     model = model_builder.build_decoder(model_builder.build_encoder(enc, c["test_graph"]), dec)
     model.set_device("cuda:0")
     model.initialize_train()
@@ -64,7 +58,7 @@ def test_product_matches_reference_code_outputs(toy, name, variant, grouping, no
         assert abs(layer.dropout_keep_probability - 0.8) < 1e-12
         layer.make_drop_mask = (lambda rows, mode, m=m, k=layer.dropout_keep_probability:
                                 (m, k) if mode == 'train' else (None, 1.0))
-    total = model.train_loss(graph_split, X, Y)
+    total = model.train_loss(*((graph_split, X, Y) if model.needs_graph() else (X, Y)))
     total.backward()
     ref_total = float(c["loss"]) + float(c["reg"])
     assert abs(total.item() - ref_total) <= 1e-4 * abs(ref_total)

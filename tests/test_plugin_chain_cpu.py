@@ -13,11 +13,8 @@ from relationprediction_b200 import ops
 from relationprediction_b200.common import evaluation, model_builder
 from relationprediction_b200.encoders.message_gcns.message_gcn import MessageGcn
 from test_plugin_host import merged_settings
-from test_reference_golden import ALL, load_case, split_weights
+from test_reference_golden import ALL, CASE_SETTINGS, load_case, split_weights
 
-WIDTHS = {"block_toy_s5": ("gcn_block.exp", 40, 8), "block_syn_s8": ("gcn_block.exp", 32, 4),
-          "basis_toy": ("gcn_basis.exp", 24, 5), "basis_syn": ("gcn_basis.exp", 20, 3),
-          "basis_toy_1layer": ("gcn_basis.exp", 24, 2), "block_toy_1layer": ("gcn_block.exp", 16, 4)}
 DT = torch.float64
 
 
@@ -71,16 +68,13 @@ def rel(a, b):
 @pytest.mark.parametrize("name,variant,grouping,norm_mode", ALL)
 def test_host_chain_reproduces_reference_code_outputs(toy, oracle_backed_ops, name, variant, grouping, norm_mode):
     c = load_case(name + "_" + grouping)
-    settings_file, d, B = WIDTHS[name]
+    settings_file, overrides = CASE_SETTINGS[name]
     V, R = int(c["V"]), int(c["R"])
     enc, dec = merged_settings(toy, settings_file, V, R, len(c["test_graph"]))
     for s in (enc, dec):
-        s.put("InternalEncoderDimension", str(d))
-        s.put("CodeDimension", str(d))
-        s.put("NumberOfBasisFunctions", str(B))
+        for k, v in overrides.items():
+            s.put(k, v)
         s.put("NormalizationMode", norm_mode)
-        if name.endswith("_1layer"):
-            s.put("NumberOfLayers", "1")
     model = model_builder.build_decoder(model_builder.build_encoder(enc, c["test_graph"]), dec)
     model.set_device("cpu")
     model.initialize_train()
@@ -99,7 +93,9 @@ def test_host_chain_reproduces_reference_code_outputs(toy, oracle_backed_ops, na
         m = torch.tensor(c["mask%d" % i])
         layer.make_drop_mask = (lambda rows, mode, m=m, k=layer.dropout_keep_probability:
                                 (m, k) if mode == 'train' else (None, 1.0))
-    total = model.train_loss(c["graph_split"], c["X"], c["Y"])
+    feed = (c["graph_split"], c["X"], c["Y"]) if model.needs_graph() else (c["X"], c["Y"])
+    assert model.needs_graph() == (variant != "embedding")
+    total = model.train_loss(*feed)
     total.backward()
     ref_total = float(c["loss"]) + float(c["reg"])
     # the tf_unsorted_compat norms travel through the product as float32 values (explicit norm arrays)

@@ -28,18 +28,44 @@ def load_case(name):
     return {k[len(p):]: z[k] for k in z.files if k.startswith(p)}
 
 
+# settings file + the overrides the generator applied, per golden case (shared by the CPU-chain and GPU tests)
+CASE_SETTINGS = {
+    "block_toy_s5": ("gcn_block.exp", {"InternalEncoderDimension": "40", "CodeDimension": "40",
+                                       "NumberOfBasisFunctions": "8"}),
+    "block_syn_s8": ("gcn_block.exp", {"InternalEncoderDimension": "32", "CodeDimension": "32",
+                                       "NumberOfBasisFunctions": "4"}),
+    "basis_toy": ("gcn_basis.exp", {"InternalEncoderDimension": "24", "CodeDimension": "24",
+                                    "NumberOfBasisFunctions": "5"}),
+    "basis_syn": ("gcn_basis.exp", {"InternalEncoderDimension": "20", "CodeDimension": "20",
+                                    "NumberOfBasisFunctions": "3"}),
+    "basis_toy_1layer": ("gcn_basis.exp", {"InternalEncoderDimension": "24", "CodeDimension": "24",
+                                           "NumberOfBasisFunctions": "2", "NumberOfLayers": "1"}),
+    "block_toy_1layer": ("gcn_block.exp", {"InternalEncoderDimension": "16", "CodeDimension": "16",
+                                           "NumberOfBasisFunctions": "4", "NumberOfLayers": "1"}),
+    "distmult_toy": ("distmult.exp", {"CodeDimension": "24"}),
+    "block_toy_outproj": ("gcn_block.exp", {"InternalEncoderDimension": "20", "CodeDimension": "12",
+                                            "NumberOfBasisFunctions": "4", "UseOutputTransform": "Yes"}),
+}
+
+
 def split_weights(c, variant):
     """Reference get_weights() order (model.py:169-182: next component first): AffineTransform [W, b],
-    per layer [W_forward, W_backward, (C_forward, C_backward,) W_self, b], RelationEmbedding [W_relation]."""
+    per layer [W_forward, W_backward, (C_forward, C_backward,) W_self, b], (output AffineTransform [W, b],)
+    RelationEmbedding [W_relation].  The graph-less baseline is AffineTransform [W, b] + [W_relation]."""
     n = int(c["n_weights"])
+    if variant == "embedding":
+        assert n == 3
+        return ["W_in", "b_in", "W_relation"], 0
+    tail = ["W_out", "b_out", "W_relation"] if variant == "block_outproj" else ["W_relation"]
+    variant = "block" if variant == "block_outproj" else variant
     per = 4 if variant == "block" else 6
-    n_layers = (n - 3) // per
+    n_layers = (n - 2 - len(tail)) // per
     names = ["W_in", "b_in"]
     for l in range(n_layers):
         keys = (["W_forward", "W_backward", "W_self", "b"] if variant == "block"
                 else ["W_forward", "W_backward", "C_forward", "C_backward", "W_self", "b"])
         names += ["L%d.%s" % (l, k) for k in keys]
-    names += ["W_relation"]
+    names += tail
     assert len(names) == n
     return names, n_layers
 
@@ -52,13 +78,21 @@ def oracle_run(c, variant, norm_mode):
                     for l in range(n_layers)]}
     V, R = int(c["V"]), int(c["R"])
     masks = [c["mask%d" % i] for i in range(int(c["n_masks"]))]
-    codes = oracle.encoder_forward(p, c["graph_split"], V, R, variant, mode="train", drop_masks=masks, keep=KEEP,
-                                   norm_mode=norm_mode, dtype=torch.float64, norm_dtype=np.float64)
+
+    def encode(graph, mode):
+        if variant == "embedding":       # model_builder.py:27-40: codes = W (one-hot input, no bias, no ReLU)
+            return oracle.affine_onehot(leaves["W_in"], leaves["b_in"], use_bias=False, use_nonlinearity=False)
+        h = oracle.encoder_forward(p, graph, V, R, "block" if variant == "block_outproj" else variant, mode=mode,
+                                   drop_masks=masks if mode == "train" else None, keep=KEEP, norm_mode=norm_mode,
+                                   dtype=torch.float64, norm_dtype=np.float64)
+        if variant == "block_outproj":   # model_builder.py:170-176: linear projection with bias, no ReLU
+            h = h @ leaves["W_out"] + leaves["b_out"]
+        return h
+    codes = encode(c["graph_split"] if variant != "embedding" else None, "train")
     loss, reg, _ = oracle.distmult_loss(codes, leaves["W_relation"], c["X"], c["Y"], torch.float64)
     (loss + LAMBDA * reg).backward()
     with torch.no_grad():
-        tc = oracle.encoder_forward(p, c["test_graph"], V, R, variant, mode="test", norm_mode=norm_mode,
-                                    dtype=torch.float64, norm_dtype=np.float64)
+        tc = encode(c["test_graph"], "test").detach()
     return names, leaves, loss.item(), LAMBDA * reg.item(), tc
 
 
@@ -68,7 +102,9 @@ def rel(a, b):
 
 
 ALL = [(n, v, g, m) for n, v in CASES for g, m in GROUPINGS] + [
-    ("basis_toy_1layer", "basis", "canonical", "canonical"), ("block_toy_1layer", "block", "canonical", "canonical")]
+    ("basis_toy_1layer", "basis", "canonical", "canonical"), ("block_toy_1layer", "block", "canonical", "canonical"),
+    ("distmult_toy", "embedding", "canonical", "canonical"),
+    ("block_toy_outproj", "block_outproj", "canonical", "canonical")]
 
 
 @pytest.mark.parametrize("name,variant,grouping,norm_mode", ALL)
@@ -79,7 +115,8 @@ def test_oracle_matches_reference_code_outputs(name, variant, grouping, norm_mod
     assert abs(reg - float(c["reg"])) <= 1e-10 * abs(float(c["reg"]))
     for i, nm in enumerate(names):
         if bool(c["g%d_unused" % i]):
-            assert nm.endswith(".b"), nm          # only the never-added layer biases receive no gradient
+            # only the never-added layer biases (and the baseline's unused input bias) receive no gradient
+            assert nm.endswith(".b") or (variant == "embedding" and nm == "b_in"), nm
             assert leaves[nm].grad is None
             continue
         assert rel(leaves[nm].grad.numpy(), c["g%d" % i]) < 1e-10, nm
