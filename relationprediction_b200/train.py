@@ -194,12 +194,21 @@ def main(argv=None):
                     help="keep the validation passes but never stop on them (only --max-iterations / --time-budget)")
     ap.add_argument("--final-eval", type=int, default=None, metavar="N",
                     help="after training rank the first N test triples (0 = all) and print one JSON line")
+    ap.add_argument("--set", action="append", default=[], metavar="Section.Key=Value",
+                    help="override one settings entry after the file is read, e.g. "
+                         "--set Encoder.NumberOfBasisFunctions=2 (repeatable)")
     ap.add_argument("--device", default="cuda:0")
     args = ap.parse_args(argv)
     if (args.dataset is None) == (args.dataset_npz is None):
         ap.error("give exactly one of --dataset / --dataset-npz")
 
     settings = settings_reader.read(args.settings)
+    for item in args.set:
+        path, _, value = item.partition("=")
+        section, _, key = path.partition(".")
+        if not key or section not in settings:
+            ap.error("--set expects Section.Key=Value with an existing section, got %r" % item)
+        settings[section].put(key, value)
     print(settings)
     if args.dataset_npz is not None:
         splits, entities, relations = load_dataset_npz(args.dataset_npz)

@@ -118,3 +118,18 @@ def test_graph_batch_sampling_path_on_cpu(toy, tmp_path, capsys, cpu_driver):
                  "--prefetch", "3", "--no-periodic-eval", "--final-eval", "0"])
     line = json.loads([l for l in capsys.readouterr().out.splitlines() if l.startswith("{")][-1])
     assert line["iterations"] == 25 and 0.0 < line["filtered"]["MRR"] <= 1.0
+
+
+def test_settings_overrides_on_the_command_line(toy, tmp_path, capsys, cpu_driver):
+    """--set Section.Key=Value edits the parsed settings before the merge (how BASELINE configs[2] turns the shipped
+    gcn_basis.exp into the WN18 B=2, d=200 configuration)."""
+    write_toy(toy, tmp_path)
+    exp = tmp_path / "toy.exp"
+    exp.write_text(TOY_EXP.format(layers=2, concat="No"))
+    model, _ = driver.main(["--settings", str(exp), "--dataset", str(tmp_path), "--max-iterations", "2", "--device", "cpu",
+                            "--no-periodic-eval", "--set", "Encoder.NumberOfBasisFunctions=3",
+                            "--set", "Encoder.InternalEncoderDimension=12", "--set", "Shared.CodeDimension=12"])
+    shapes = [tuple(w.shape) for w in model.get_weights()]
+    assert shapes[2] == (12, 3, 12) and shapes[4] == (toy["R"], 3) and shapes[-1] == (toy["V"], 12)
+    with pytest.raises(SystemExit):
+        driver.main(["--settings", str(exp), "--dataset", str(tmp_path), "--set", "Nope.Key=1", "--device", "cpu"])
