@@ -1,6 +1,6 @@
 #!/bin/bash
 # WN18 (BASELINE configs[2]): shipped gcn_basis.exp with B=2, d=200 (the edits BASELINE.md names), time-boxed
-# training, full test set.  Needs .scratch/wn18_full.npz (scripts/pack_dataset.py /root/reference/data/<wn18 dir>).
+# training, full test set.  Needs .scratch/wn18_full.npz (scripts/pack_dataset.py /root/reference/data/wn18 .scratch/wn18_full.npz).
 mkdir -p gpurun_out
 python - <<'PY'
 import json
