@@ -122,3 +122,27 @@ def test_error_codes_instead_of_exceptions():
     assert rc == -5  # RGCN_ERR_NODEVICE: no silent CPU path
     assert b"host-only" in lib.rgcn_last_error()
     assert lib.rgcn_graph_export(g.handle, 99, buf, 1024) == -1
+
+
+def test_next_row_entry_points_reject_bad_arguments_without_a_gpu():
+    """Argument validation of the optimizer and sampler entry points happens before any device work."""
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(64)
+    assert lib.rgcn_adam_update(None, buf, buf, buf, 4, 0.01, 0.9, 0.999, 1e-8, 1, None, 0.0, None) == -1
+    assert lib.rgcn_adam_update(buf, buf, buf, buf, 4, 0.01, 0.9, 0.999, 1e-8, 0, None, 0.0, None) == -1  # 1-based step
+    assert b"step" in lib.rgcn_last_error()
+    assert lib.rgcn_adam_update(buf, buf, buf, buf, 0, 0.01, 0.9, 0.999, 1e-8, 1, None, 0.0, None) == 0     # empty tensor
+    assert lib.rgcn_sumsq_accumulate(None, 4, buf, None) == -1
+    assert lib.rgcn_sumsq_accumulate(buf, 0, buf, None) == 0
+    h = ctypes.c_void_p()
+    tri = np.array([[0, 0, 1], [1, 0, 7]], np.int32)
+    assert lib.rgcn_sampler_create(ctypes.c_void_p(tri.ctypes.data), 2, 5, ctypes.byref(h)) == -1          # id 7 >= V
+    assert not h.value
+    assert lib.rgcn_sampler_create(ctypes.c_void_p(tri.ctypes.data), 2, 8, None) == -1
+    assert lib.rgcn_sampler_create(ctypes.c_void_p(tri.ctypes.data), 2, 8, ctypes.byref(h)) == 0 and h.value
+    out = np.empty(4, np.int32)
+    assert lib.rgcn_sampler_draw(h, 3, 1, ctypes.c_void_p(out.ctypes.data)) == -1                           # > E
+    assert lib.rgcn_sampler_draw(None, 1, 1, ctypes.c_void_p(out.ctypes.data)) == -1
+    assert lib.rgcn_sampler_draw(h, 2, 1, ctypes.c_void_p(out.ctypes.data)) == 0 and sorted(out[:2].tolist()) == [0, 1]
+    lib.rgcn_sampler_destroy(h)
+    lib.rgcn_sampler_destroy(None)
