@@ -127,6 +127,10 @@ int rgcn_graph_create_messages(const int32_t* dst_host, const int32_t* src_host,
                                int32_t V_dst, int32_t V_src, int32_t n_relw, int device,
                                void* stream, rgcn_graph_t** out);
 
+/* Opt-in stream-ordered destroy: GPU-prepared graphs return their arrays with cudaFreeAsync on `stream` (no
+ * device synchronisation); every kernel that used the graph must be ordered before `stream`'s tail.  Host-prepared
+ * graphs take the synchronous path of rgcn_graph_destroy. */
+int rgcn_graph_destroy_async(rgcn_graph_t* graph, void* stream);
 int rgcn_graph_destroy(rgcn_graph_t* g);
 
 /* info[0]=M messages, [1]=V_dst, [2]=V_src, [3]=n_relw, [4]=#dst work items, [5]=#src work items,

@@ -452,36 +452,61 @@ extern "C" int rgcn_graph_create(const int32_t* triples_host, int64_t E, int32_t
                out);
 }
 
+namespace {
+
+template <typename FreeFn>
+void free_device_arrays(rgcn_graph_t* g, FreeFn free_fn) {
+  free_fn(g->by_dst.d_rowptr);
+  free_fn(g->by_src.d_rowptr);
+  free_fn(g->by_dst.d_mid);
+  free_fn(g->by_src.d_mid);
+  free_fn(g->d_msg_norm);
+  free_fn(g->by_dst.d_nbr);
+  free_fn(g->by_dst.d_relw);
+  free_fn(g->by_dst.d_norm);
+  free_fn(g->by_dst.d_items);
+  free_fn(g->by_dst.d_split_nitems);
+  free_fn(g->by_dst.d_split_rows);
+  free_fn(g->by_src.d_nbr);
+  free_fn(g->by_src.d_relw);
+  free_fn(g->by_src.d_norm);
+  free_fn(g->by_src.d_items);
+  free_fn(g->by_src.d_split_nitems);
+  free_fn(g->by_src.d_split_rows);
+  for (RelSide* rs : {&g->by_rel, &g->by_rel_src}) {
+    free_fn(rs->d_ptr);
+    free_fn(rs->d_mid);
+    free_fn(rs->d_row);
+    free_fn(rs->d_nbr);
+    free_fn(rs->d_norm);
+    free_fn(rs->d_items);
+  }
+}
+
+}  // namespace
+
 extern "C" int rgcn_graph_destroy(rgcn_graph_t* g) {
   if (!g) return RGCN_OK;
   if (g->device >= 0) {
     cudaSetDevice(g->device);
-    cudaFree(g->by_dst.d_rowptr);
-    cudaFree(g->by_src.d_rowptr);
-    cudaFree(g->by_dst.d_mid);
-    cudaFree(g->by_src.d_mid);
-    cudaFree(g->d_msg_norm);
-    cudaFree(g->by_dst.d_nbr);
-    cudaFree(g->by_dst.d_relw);
-    cudaFree(g->by_dst.d_norm);
-    cudaFree(g->by_dst.d_items);
-    cudaFree(g->by_dst.d_split_nitems);
-    cudaFree(g->by_dst.d_split_rows);
-    cudaFree(g->by_src.d_nbr);
-    cudaFree(g->by_src.d_relw);
-    cudaFree(g->by_src.d_norm);
-    cudaFree(g->by_src.d_items);
-    cudaFree(g->by_src.d_split_nitems);
-    cudaFree(g->by_src.d_split_rows);
-    for (RelSide* rs : {&g->by_rel, &g->by_rel_src}) {
-      cudaFree(rs->d_ptr);
-      cudaFree(rs->d_mid);
-      cudaFree(rs->d_row);
-      cudaFree(rs->d_nbr);
-      cudaFree(rs->d_norm);
-      cudaFree(rs->d_items);
-    }
+    free_device_arrays(g, [](void* p) { cudaFree(p); });
   }
+  delete g;
+  return RGCN_OK;
+}
+
+// Stream-ordered variant (opt-in): a graph prepared on the GPU takes its arrays from the stream-ordered pool, so
+// they can be returned with cudaFreeAsync on `stream` -- no device synchronisation.  The caller guarantees that
+// every kernel that used the graph was launched on `stream` (or is ordered before it).  Host-prepared graphs
+// (cudaMalloc) fall back to the synchronous path.
+extern "C" int rgcn_graph_destroy_async(rgcn_graph_t* g, void* stream) {
+  if (!g) return RGCN_OK;
+  if (g->device < 0 || !g->built_on_device) return rgcn_graph_destroy(g);
+  cudaSetDevice(g->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  free_device_arrays(g, [st](void* p) {
+    if (p) cudaFreeAsync(p, st);
+  });
   delete g;
   return RGCN_OK;
 }

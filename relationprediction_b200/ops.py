@@ -5,6 +5,7 @@ forward/backward below is ONE call into librgcn_b200.so (include/rgcn_b200.h).  
 eager-torch fallback: tensors that are not CUDA fp32 raise.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -97,7 +98,11 @@ class Graph:
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
-            self._lib.rgcn_graph_destroy(self._h)
+            if self.device is not None and os.environ.get("RGCN_ASYNC_FREE") == "1":
+                # opt-in (not yet validated on a GPU): stream-ordered frees on the current stream, no device sync
+                self._lib.rgcn_graph_destroy_async(self._h, _stream(self.device))
+            else:
+                self._lib.rgcn_graph_destroy(self._h)
             self._h = ctypes.c_void_p(0)
 
     def __del__(self):
