@@ -30,3 +30,14 @@ try:
 except Exception as exc:
     print("component-major bench failed:", exc)
 PY
+# 4. stream-ordered graph destroy in the training loop (ms per iteration, 20 s each; needs .scratch/fb15k237_full.npz)
+python - <<'PY'
+import json
+t = json.load(open("tests/golden/toy_golden.json"))
+open("gpurun_out/gcn_block.exp", "w").write(t["settings_text"]["gcn_block.exp"])
+PY
+for af in 0 1; do
+  RGCN_ASYNC_FREE=$af timeout 120 python -m relationprediction_b200.train --settings gpurun_out/gcn_block.exp \
+      --dataset-npz .scratch/fb15k237_full.npz --time-budget 20 --prefetch 16 --no-periodic-eval --final-eval 500 \
+      2>&1 | tail -1 | python -c "import sys, json; j = json.loads(sys.stdin.read()); print('async_free=$af', j['ms_per_iteration'], 'ms/iteration', j['filtered'])"
+done
