@@ -183,6 +183,12 @@ def run_reference(args, rank, world):
     sample_E = min(spec["E"], args.cpu_sample_edges)
     step = oracle_step_factory(spec, sample_E)
     cores = best_cpu_threads(step)
+    # keep the whole --steps K run within a few minutes: shrink the per-step sample if K steps of it would not
+    est = time_cpu(step, 1, 1)
+    budget_s = 150.0
+    if est * args.steps > budget_s and sample_E > 2000:
+        sample_E = max(2000, int(sample_E * budget_s / (est * args.steps)))
+        step = oracle_step_factory(spec, sample_E)
     sec = time_cpu(step, args.steps, max(1, min(args.warmup, 1)))
     val = sample_E / sec / 1e6
     sample = "%d of %d triples of the same synthetic KG (same V, R, d, B), fp32, best of {8,16,32,64,all} torch threads = %d of %d host cores" % (
