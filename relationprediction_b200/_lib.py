@@ -115,9 +115,14 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
+    # always go through build(): it is a fingerprint comparison when the .so is current, and it rebuilds a
+    # stale library after csrc / header edits instead of loading it against the new ctypes signatures
+    from . import build as _build
+    try:
         _build.build()
+    except Exception as e:  # no nvcc on this host: a library whose stamp matches the sources is still fine
+        if not (os.path.exists(LIB_PATH) and _build.is_current()):
+            raise RgcnError("librgcn_b200.so is missing or stale and could not be rebuilt: %s" % e) from e
     try:
         lib = ctypes.CDLL(LIB_PATH)
     except OSError as e:  # loud failure: the CUDA library IS the product path

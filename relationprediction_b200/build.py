@@ -32,6 +32,15 @@ def _fingerprint():
     return h.hexdigest()
 
 
+def is_current():
+    """True when the built library's stamp matches the sources' fingerprint."""
+    stamp = os.path.join(LIBDIR, "librgcn_b200.stamp")
+    if not (os.path.exists(LIB) and os.path.exists(stamp)):
+        return False
+    with open(stamp) as fh:
+        return fh.read().strip() == _fingerprint()
+
+
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, "librgcn_b200.stamp")
@@ -49,7 +58,7 @@ def build(force=False, verbose=False):
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
-    cmd += ["-L", os.path.join(cuda_home, "lib64"), "-lcublas", "-lcudart",
+    cmd += ["-L", os.path.join(cuda_home, "lib64"), "-lcudart",
             "-Xlinker", "-rpath," + os.path.join(cuda_home, "lib64"), "-o", LIB]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

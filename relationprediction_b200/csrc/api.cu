@@ -1,113 +1,46 @@
 // api.cu -- C-ABI entry points of librgcn_b200.so (see include/rgcn_b200.h).
-// Orchestrates per-layer work on ONE stream: weight re-layout -> dense self-loop GEMM (cuBLAS fp32,
-// a plain library GEMM) -> warp-centric aggregation kernel with the fused epilogue.
-#include <cublas_v2.h>
+// Orchestrates per-layer work on ONE stream: weight re-layout -> dense self-loop GEMM (own tcgen05 3xTF32
+// kernel, gemm_tf32x3.cu) -> warp-centric aggregation kernels.  No vendor-library compute anywhere.
 #include <cuda_runtime.h>
 
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <string>
 
 #include "kernels.cuh"
 
 namespace {
 
-std::mutex g_cublas_mu;
-cublasHandle_t g_cublas[64] = {nullptr};
-
-int get_cublas(int device, cudaStream_t st, cublasHandle_t* out) {
-  if (device < 0 || device >= 64) {
-    rgcn_set_error("bad device ordinal");
+// GEMM dispatch.  Every dense product of the layers runs on this library's own tcgen05 3xTF32 kernels
+// (gemm_tf32x3.cu): the NT/NN forms (contraction along the contiguous dimension of A) through
+// k_gemm_tf32x3 with the small operand B pre-split into hi/lo planes, the V-long reductions A^T B through
+// k_gemm_tn_tf32x3.  There is NO library fallback: a shape the kernels do not cover is an explicit
+// RGCN_ERR_INVALID (all layer entry points require d % 4 == 0, which makes every internal shape valid).
+// Row-major: C[m,n] = op(A) op(B) + beta * C with beta in {0, 1};  split_ws: 2*n*k floats.
+int gemm_any(cudaStream_t st, float* split_ws, bool ta, bool tb, int64_t m, int64_t n, int64_t k,
+             const float* A, int64_t lda, const float* B, int64_t ldb, float beta, float* C, int64_t ldc) {
+  if (m == 0 || n == 0) return RGCN_OK;
+  if (beta != 0.f && beta != 1.f) {
+    rgcn_set_error("gemm: beta must be 0 or 1");
     return RGCN_ERR_INVALID;
   }
-  std::lock_guard<std::mutex> lk(g_cublas_mu);
-  if (!g_cublas[device]) {
-    cublasStatus_t s = cublasCreate(&g_cublas[device]);
-    if (s != CUBLAS_STATUS_SUCCESS) {
-      g_cublas[device] = nullptr;
-      rgcn_set_error("cublasCreate failed: " + std::to_string((int)s));
-      return RGCN_ERR_CUDA;
-    }
-    // true fp32 accumulate and multiply: the 1e-4 parity bar rules out single-pass TF32
-    cublasSetMathMode(g_cublas[device], CUBLAS_DEFAULT_MATH);
-  }
-  cublasStatus_t s = cublasSetStream(g_cublas[device], st);
-  if (s != CUBLAS_STATUS_SUCCESS) {
-    rgcn_set_error("cublasSetStream failed");
-    return RGCN_ERR_CUDA;
-  }
-  *out = g_cublas[device];
-  return RGCN_OK;
-}
-
-// gemm_mode: 2 (default) = own tcgen05 3xTF32 kernel (gemm_tf32x3.cu) where it applies, else cuBLAS;
-// 0 = cuBLAS SGEMM (fp32 FMA pipes), 1 = cuBLAS fp32 emulation via BF16x9 on the tensor
-// cores (falls back to 0 when the loaded cuBLAS does not support it)
-int g_gemm_mode = 2;
-bool g_emulation_unavailable = false;
-
-// Row-major GEMM: C[m,n] = alpha * op(A) * op(B) + beta * C, op(A) is m x k, op(B) is k x n.
-int gemm_rm(cublasHandle_t h, bool ta, bool tb, int64_t m, int64_t n, int64_t k, float alpha,
-            const float* A, int64_t lda, const float* B, int64_t ldb, float beta, float* C,
-            int64_t ldc) {
-  if (m == 0 || n == 0) return RGCN_OK;
   if (k == 0) {
-    // cuBLAS rejects k = 0 with some leading dimensions; emulate beta scaling (beta is 0 or 1 here)
-    if (beta == 0.f) {
-      cudaStream_t st;
-      cublasGetStream(h, &st);
-      return rgcn_check_cuda(cudaMemset2DAsync(C, ldc * sizeof(float), 0, n * sizeof(float), m, st),
-                             "memset2d");
-    }
+    if (beta == 0.f)
+      return rgcn_check_cuda(cudaMemset2DAsync(C, ldc * sizeof(float), 0, n * sizeof(float), m, st), "memset2d");
     return RGCN_OK;
   }
-  int mode = g_gemm_mode;
-  if (const char* e = std::getenv("RGCN_GEMM_MODE")) mode = std::atoi(e);
-  cublasStatus_t s = CUBLAS_STATUS_NOT_SUPPORTED;
-  if (mode == 1 && !g_emulation_unavailable) {
-    // fp32 emulation on the bf16 tensor cores (3 x bf16 split, 9 products): fp32-level accuracy
-    s = cublasGemmEx(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, (int)n, (int)m,
-                     (int)k, &alpha, B, CUDA_R_32F, (int)ldb, A, CUDA_R_32F, (int)lda, &beta, C,
-                     CUDA_R_32F, (int)ldc, CUBLAS_COMPUTE_32F_EMULATED_16BFX9, CUBLAS_GEMM_DEFAULT);
-    if (s != CUBLAS_STATUS_SUCCESS) g_emulation_unavailable = true;
-  }
-  if (s != CUBLAS_STATUS_SUCCESS)
-    s = cublasSgemm(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, (int)n, (int)m,
-                    (int)k, &alpha, B, (int)ldb, A, (int)lda, &beta, C, (int)ldc);
-  if (s != CUBLAS_STATUS_SUCCESS) {
-    rgcn_set_error("cublasSgemm failed: status " + std::to_string((int)s));
-    return RGCN_ERR_CUDA;
-  }
-  return RGCN_OK;
-}
-
-// GEMM dispatch: the tcgen05 3xTF32 kernel (gemm_tf32x3.cu) whenever the contraction runs along the
-// contiguous dimension of A (every GEMM of the layers except the V-long reductions A^T B), cuBLAS
-// otherwise.  split_ws: 2*n*k floats for the hi/lo split of B.
-int gemm_any(cublasHandle_t h, float* split_ws, bool ta, bool tb, int64_t m, int64_t n, int64_t k,
-             float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta, float* C,
-             int64_t ldc) {
-  int mode = g_gemm_mode;
-  if (const char* e = std::getenv("RGCN_GEMM_MODE")) mode = std::atoi(e);
-  const bool ok = mode == 2 && !ta && alpha == 1.f && (beta == 0.f || beta == 1.f) && k > 0 && m > 0 &&
-                  k % 4 == 0 && n % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 && split_ws &&
-                  m < 0x7fffffffLL;
-  if (mode == 2 && ta && !tb && alpha == 1.f && (beta == 0.f || beta == 1.f) && m % 4 == 0 &&
-      n % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 && k < 0x7fffffffLL &&
-      !std::getenv("RGCN_NO_TN_GEMM")) {
-    cudaStream_t st;
-    cublasGetStream(h, &st);
+  const bool aligned = n % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0;
+  if (ta && !tb && aligned && m % 4 == 0 && k < 0x7fffffffLL && m < 0x7fffffffLL && n < 0x7fffffffLL)
     return launch_gemm_tn_tf32x3(A, lda, B, ldb, C, ldc, (int)m, (int)n, (int)k, beta != 0.f, st);
+  if (!ta && aligned && k % 4 == 0 && split_ws && m < 0x7fffffffLL && n < 0x7fffffffLL && k < 0x7fffffffLL) {
+    float* hi = split_ws;
+    float* lo = split_ws + (size_t)n * k;
+    int rc = launch_gemm_split_b(B, ldb, (int)n, (int)k, tb ? 0 : 1, hi, lo, st);
+    if (rc) return rc;
+    return launch_gemm_tf32x3(A, lda, hi, lo, k, C, ldc, (int)m, (int)n, (int)k, beta != 0.f, st);
   }
-  if (!ok) return gemm_rm(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-  cudaStream_t st;
-  cublasGetStream(h, &st);
-  float* hi = split_ws;
-  float* lo = split_ws + (size_t)n * k;
-  int rc = launch_gemm_split_b(B, ldb, (int)n, (int)k, tb ? 0 : 1, hi, lo, st);
-  if (rc) return rc;
-  return launch_gemm_tf32x3(A, lda, hi, lo, k, C, ldc, (int)m, (int)n, (int)k, beta != 0.f, st);
+  rgcn_set_error("gemm: unsupported shape (dimensions and leading dimensions must be multiples of 4)");
+  return RGCN_ERR_INVALID;
 }
 
 // ---- optional stage timing -------------------------------------------------------------------
@@ -224,10 +157,6 @@ static bool use_rel_major(int d, int s) {
 extern "C" int rgcn_set_option(const char* name, int64_t value) {
   if (name && std::string(name) == "block_algo") {
     g_block_algo = (int)value;
-    return RGCN_OK;
-  }
-  if (name && std::string(name) == "gemm_mode") {
-    g_gemm_mode = (int)value;
     return RGCN_OK;
   }
   rgcn_set_error("rgcn_set_option: unknown option");
@@ -371,10 +300,7 @@ extern "C" int rgcn_block_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
     rc = rgcn_check_cuda(cudaMemsetAsync(Mc, 0, (size_t)g->V_dst * d * sizeof(float), st), "memset(Mc)");
     if (rc) return rc;
     MARK("block_relayout");
-    cublasHandle_t hc;
-    rc = get_cublas(g->device, st, &hc);
-    if (rc) return rc;
-    rc = gemm_any(hc, split_ws, false, false, g->V_dst, d, d, 1.f, H, d, Wself, d, 0.f, out, d);
+    rc = gemm_any(st, split_ws, false, false, g->V_dst, d, d, H, d, Wself, d, 0.f, out, d);
     if (rc) return rc;
     MARK("gemm_self_loop");
     rc = launch_mask_relu(out, drop_mask, 1.0f / keep, 0, (int64_t)g->V_dst * d, st);
@@ -401,11 +327,8 @@ extern "C" int rgcn_block_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
         "memset(scratch)");
     if (rc) return rc;
   }
-  cublasHandle_t h;
-  rc = get_cublas(g->device, st, &h);
-  if (rc) return rc;
   // self-loop term S = H[0:V_dst] @ W_self written straight into `out` (gcn_basis_concat.py:65-66)
-  rc = gemm_any(h, split_ws, false, false, g->V_dst, d, d, 1.f, H, d, Wself, d, 0.f, out, d);
+  rc = gemm_any(st, split_ws, false, false, g->V_dst, d, d, H, d, Wself, d, 0.f, out, d);
   if (rc) return rc;
   MARK("gemm_self_loop");
   if (use_rel_major(d, s)) {
@@ -470,13 +393,10 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
     rc = launch_grad_prologue(dOut, out, drop_mask, 1.0f / keep, relu, (int64_t)g->V_dst * d, Gm, dSm, st);
     if (rc) return rc;
     MARK("grad_prologue");
-    cublasHandle_t hc;
-    rc = get_cublas(g->device, st, &hc);
-    if (rc) return rc;
-    rc = gemm_any(hc, split_ws, true, false, d, d, g->V_dst, 1.f, H, d, dSm, d, 0.f, dWself, d);
+    rc = gemm_any(st, split_ws, true, false, d, d, g->V_dst, H, d, dSm, d, 0.f, dWself, d);
     if (rc) return rc;
     MARK("gemm_dWself");
-    rc = gemm_any(hc, split_ws, false, true, g->V_dst, d, d, 1.f, dSm, d, Wself, d, 0.f, dH, d);
+    rc = gemm_any(st, split_ws, false, true, g->V_dst, d, d, dSm, d, Wself, d, 0.f, dH, d);
     if (rc) return rc;
     if (g->V_src > g->V_dst) {
       rc = rgcn_check_cuda(cudaMemsetAsync(dH + (size_t)g->V_dst * d, 0,
@@ -527,15 +447,12 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   rc = launch_grad_prologue(dOut, out, drop_mask, 1.0f / keep, relu, (int64_t)g->V_dst * d, G, dS, st);
   if (rc) return rc;
   MARK("grad_prologue");
-  cublasHandle_t h;
-  rc = get_cublas(g->device, st, &h);
-  if (rc) return rc;
   // dW_self = H[0:V_dst]^T dS
-  rc = gemm_any(h, split_ws, true, false, d, d, g->V_dst, 1.f, H, d, dS, d, 0.f, dWself, d);
+  rc = gemm_any(st, split_ws, true, false, d, d, g->V_dst, H, d, dS, d, 0.f, dWself, d);
   if (rc) return rc;
   MARK("gemm_dWself");
   // dH[0:V_dst] = dS W_self^T ; halo rows start at zero
-  rc = gemm_any(h, split_ws, false, true, g->V_dst, d, d, 1.f, dS, d, Wself, d, 0.f, dH, d);
+  rc = gemm_any(st, split_ws, false, true, g->V_dst, d, d, dS, d, Wself, d, 0.f, dH, d);
   if (rc) return rc;
   if (g->V_src > g->V_dst) {
     rc = rgcn_check_cuda(cudaMemsetAsync(dH + (size_t)g->V_dst * d, 0,
@@ -756,17 +673,14 @@ extern "C" int rgcn_basis_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
   rc = launch_basis_agg(a, Ccat, B, g->n_relw, /*layout=*/0, saved, st);
   if (rc) return rc;
   MARK("basis_agg_fwd");
-  cublasHandle_t h;
-  rc = get_cublas(g->device, st, &h);
-  if (rc) return rc;
-  rc = gemm_any(h, split_ws, false, false, g->V_dst, d, d, 1.f, H, d, Wself, d, 0.f, out, d);
+  rc = gemm_any(st, split_ws, false, false, g->V_dst, d, d, H, d, Wself, d, 0.f, out, d);
   if (rc) return rc;
   rc = launch_mask_relu(out, drop_mask, 1.0f / keep, 0, (int64_t)g->V_dst * d, st);
   if (rc) return rc;
   // out += Agg_f @ Vf.reshape(d*B, d) + Agg_b @ Vb.reshape(d*B, d)    (gcn_basis.py:60-68 re-associated)
-  rc = gemm_any(h, split_ws, false, false, g->V_dst, d, dB, 1.f, saved, 2 * dB, Vf, d, 1.f, out, d);
+  rc = gemm_any(st, split_ws, false, false, g->V_dst, d, dB, saved, 2 * dB, Vf, d, 1.f, out, d);
   if (rc) return rc;
-  rc = gemm_any(h, split_ws, false, false, g->V_dst, d, dB, 1.f, saved + dB, 2 * dB, Vb, d, 1.f, out, d);
+  rc = gemm_any(st, split_ws, false, false, g->V_dst, d, dB, saved + dB, 2 * dB, Vb, d, 1.f, out, d);
   if (rc) return rc;
   MARK("basis_gemms_fwd");
   rc = launch_mask_relu(out, nullptr, 1.f, relu, (int64_t)g->V_dst * d, st);
@@ -813,12 +727,9 @@ extern "C" int rgcn_basis_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   MARK("start");
   rc = launch_grad_prologue(dOut, out, drop_mask, 1.0f / keep, relu, (int64_t)g->V_dst * d, G, dS, st);
   if (rc) return rc;
-  cublasHandle_t h;
-  rc = get_cublas(g->device, st, &h);
+  rc = gemm_any(st, split_ws, true, false, d, d, g->V_dst, H, d, dS, d, 0.f, dWself, d);
   if (rc) return rc;
-  rc = gemm_any(h, split_ws, true, false, d, d, g->V_dst, 1.f, H, d, dS, d, 0.f, dWself, d);
-  if (rc) return rc;
-  rc = gemm_any(h, split_ws, false, true, g->V_dst, d, d, 1.f, dS, d, Wself, d, 0.f, dH, d);
+  rc = gemm_any(st, split_ws, false, true, g->V_dst, d, d, dS, d, Wself, d, 0.f, dH, d);
   if (rc) return rc;
   if (g->V_src > g->V_dst) {
     rc = rgcn_check_cuda(cudaMemsetAsync(dH + (size_t)g->V_dst * d, 0,
@@ -828,14 +739,14 @@ extern "C" int rgcn_basis_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   }
   MARK("basis_self_loop_bwd");
   // dV_dir.reshape(d*B, d) = Agg_dir^T G
-  rc = gemm_any(h, split_ws, true, false, dB, d, g->V_dst, 1.f, saved, 2 * dB, G, d, 0.f, dVf, d);
+  rc = gemm_any(st, split_ws, true, false, dB, d, g->V_dst, saved, 2 * dB, G, d, 0.f, dVf, d);
   if (rc) return rc;
-  rc = gemm_any(h, split_ws, true, false, dB, d, g->V_dst, 1.f, saved + dB, 2 * dB, G, d, 0.f, dVb, d);
+  rc = gemm_any(st, split_ws, true, false, dB, d, g->V_dst, saved + dB, 2 * dB, G, d, 0.f, dVb, d);
   if (rc) return rc;
   // dAgg_dir = G V_dir.reshape(d*B, d)^T
-  rc = gemm_any(h, split_ws, false, true, g->V_dst, dB, d, 1.f, G, d, Vf, d, 0.f, dAgg, 2 * dB);
+  rc = gemm_any(st, split_ws, false, true, g->V_dst, dB, d, G, d, Vf, d, 0.f, dAgg, 2 * dB);
   if (rc) return rc;
-  rc = gemm_any(h, split_ws, false, true, g->V_dst, dB, d, 1.f, G, d, Vb, d, 0.f, dAgg + dB, 2 * dB);
+  rc = gemm_any(st, split_ws, false, true, g->V_dst, dB, d, G, d, Vb, d, 0.f, dAgg + dB, 2 * dB);
   if (rc) return rc;
   MARK("basis_gemms_dV_dAgg");
   // dC[w,b] = sum_m norm_m < H[src_m], dAgg[dst_m][dir][:,b] >
@@ -855,9 +766,9 @@ extern "C" int rgcn_basis_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   rc = launch_basis_agg(as, Ccat, B, g->n_relw, /*layout=*/1, P, st);
   if (rc) return rc;
   MARK("basis_agg_dH");
-  rc = gemm_any(h, split_ws, false, true, g->V_src, d, dB, 1.f, P, 2 * dB, Vf, dB, 1.f, dH, d);
+  rc = gemm_any(st, split_ws, false, true, g->V_src, d, dB, P, 2 * dB, Vf, dB, 1.f, dH, d);
   if (rc) return rc;
-  rc = gemm_any(h, split_ws, false, true, g->V_src, d, dB, 1.f, P + dB, 2 * dB, Vb, dB, 1.f, dH, d);
+  rc = gemm_any(st, split_ws, false, true, g->V_src, d, dB, P + dB, 2 * dB, Vb, dB, 1.f, dH, d);
   MARK("basis_gemms_dH");
   return rc;
 }

@@ -132,7 +132,8 @@ class _OverlappedBlockLayer(torch.autograd.Function):
         with torch.no_grad():
             out = ops._BlockLayerFn.apply(H_local, Wf, Wb, Ws, sg.graph_local, n_blocks, drop_mask, keep, False)
         work.wait()
-        ops.block_aggregate_(out, H_halo, Wf, Wb, sg.graph_halo, n_blocks)
+        if p.n_halo > 0:  # a rank whose messages all have local sources has no halo graph work at all
+            ops.block_aggregate_(out, H_halo, Wf, Wb, sg.graph_halo, n_blocks)
         if relu:
             out.relu_()
         ctx.sg, ctx.n_blocks, ctx.keep, ctx.relu, ctx.mask = sg, n_blocks, keep, relu, drop_mask
@@ -146,7 +147,11 @@ class _OverlappedBlockLayer(torch.autograd.Function):
         p = sg.plan
         G = (dOut * (out > 0)) if ctx.relu else dOut
         G = G.contiguous()
-        dHalo, dWf, dWb = ops.block_aggregate_backward(H_halo, Wf, Wb, G, sg.graph_halo, B)
+        if p.n_halo > 0:
+            dHalo, dWf, dWb = ops.block_aggregate_backward(H_halo, Wf, Wb, G, sg.graph_halo, B)
+        else:  # empty halo: nothing to send back, no halo contribution to the block weight gradients
+            dHalo = torch.empty(0, G.shape[1], dtype=G.dtype, device=G.device)
+            dWf, dWb = torch.zeros_like(Wf), torch.zeros_like(Wb)
         back = torch.empty(int(p.send_counts.sum()), G.shape[1], dtype=G.dtype, device=G.device)
         work = dist.all_to_all_single(back, dHalo, output_split_sizes=p.send_counts.tolist(),
                                       input_split_sizes=p.recv_counts.tolist(), group=sg.group, async_op=True)

@@ -197,6 +197,9 @@ def main(argv=None):
     ap.add_argument("--set", action="append", default=[], metavar="Section.Key=Value",
                     help="override one settings entry after the file is read, e.g. "
                          "--set Encoder.NumberOfBasisFunctions=2 (repeatable)")
+    ap.add_argument("--no-save", action="store_true", help="do not write checkpoints (default: the reference's "
+                    "ModelSaver cadence to General.ExperimentName)")
+    ap.add_argument("--save-path", default=None, help="checkpoint path prefix (default: General.ExperimentName)")
     ap.add_argument("--device", default="cuda:0")
     args = ap.parse_args(argv)
     if (args.dataset is None) == (args.dataset_npz is None):
@@ -204,11 +207,18 @@ def main(argv=None):
 
     settings = settings_reader.read(args.settings)
     for item in args.set:
+        # dotted path into nested sections: Optimizer.Algorithm.learning_rate=0.005 reaches [Algorithm] inside
+        # [Optimizer] (the settings reader nests sub-sections as Settings objects)
         path, _, value = item.partition("=")
-        section, _, key = path.partition(".")
-        if not key or section not in settings:
-            ap.error("--set expects Section.Key=Value with an existing section, got %r" % item)
-        settings[section].put(key, value)
+        parts = path.split(".")
+        node = settings
+        for name in parts[:-1]:
+            if not name or name not in node:
+                ap.error("--set expects Section[.SubSection].Key=Value with existing sections, got %r" % item)
+            node = node[name]
+        if len(parts) < 2 or not parts[-1] or not hasattr(node, "put"):
+            ap.error("--set expects Section[.SubSection].Key=Value, got %r" % item)
+        node.put(parts[-1], value)
     print(settings)
     if args.dataset_npz is not None:
         splits, entities, relations = load_dataset_npz(args.dataset_npz)
@@ -257,6 +267,10 @@ def main(argv=None):
 
     weights = [w for w in model.get_weights()]
     algo = opt['Algorithm']
+    if 'Name' in algo and str(algo['Name']).lower() != 'adam':
+        # the reference also wires AdaGrad / GradientDescent (optimization/optimize.py:152-203); only the
+        # Adam update is built here (both target configs use it) -- refuse instead of silently substituting it
+        raise SystemExit("Optimizer.Algorithm.Name=%s is not supported by this driver (only Adam)" % algo['Name'])
     lr = float(algo['learning_rate'])
     max_norm = float(opt['MaxGradientNorm']) if 'MaxGradientNorm' in opt else None
     optimizer = ClippedAdam(weights, lr=lr, beta1=0.9, beta2=0.999, eps=1e-8, max_norm=max_norm)
@@ -266,6 +280,19 @@ def main(argv=None):
         es = opt['EarlyStopping']
         stopper = EarlyStopper(es['CheckEvery'], es['BurninPhaseDuration'] if 'BurninPhaseDuration' in es else 0)
     max_it = args.max_iterations if args.max_iterations is not None else 10 ** 9
+    # ModelSaver cadence of the reference (common/optimizer_parameter_parser.py:92-103): SaveEveryN, else the
+    # early-stopping CheckEvery, else every iteration; path = General.ExperimentName; skipped on the stopping step
+    save_every, save_path = None, None
+    if not args.no_save and 'ExperimentName' in opt:
+        save_path = args.save_path if args.save_path else str(opt['ExperimentName'])
+        if 'SaveEveryN' in opt:
+            save_every = int(opt['SaveEveryN'])
+        elif 'EarlyStopping' in opt:
+            save_every = int(opt['EarlyStopping']['CheckEvery'])
+        else:
+            save_every = 1
+        if os.path.dirname(save_path):
+            os.makedirs(os.path.dirname(save_path), exist_ok=True)
 
     # the running loss stays on the device: reading it back every iteration would serialise the host-side
     # sample transform of step i+1 behind the GPU work of step i
@@ -293,6 +320,8 @@ def main(argv=None):
             scorer.compute_scores(test).get_summary().pretty_print()
             if stopper.update(it, score) and not args.no_early_stopping:
                 break
+        if save_every is not None and it % save_every == 0:
+            model.save(save_path)
     train_seconds = time.time() - t_start
     stream.close()
     if args.final_eval is not None:

@@ -71,7 +71,8 @@ def test_toy_training_runs_and_learns(toy, tmp_path, capsys, layers, concat):
     exp.write_text(TOY_EXP.format(layers=layers, concat=concat))
     np.random.seed(0)
     torch.manual_seed(0)
-    model, scorer = driver.main(["--settings", str(exp), "--dataset", str(tmp_path), "--max-iterations", "80"])
+    model, scorer = driver.main(["--settings", str(exp), "--dataset", str(tmp_path), "--max-iterations", "80",
+                                 "--save-path", str(tmp_path / "ckpt" / "Toy")])
     text = capsys.readouterr().out
     assert "Initial loss" in text and "Validation filtered MRR" in text
     losses = [float(l.split(":")[-1]) for l in text.splitlines() if l.startswith("Average train loss")]
@@ -91,7 +92,7 @@ def test_packed_dataset_prefetch_and_final_eval(toy, tmp_path, capsys):
     exp.write_text(TOY_EXP.format(layers=2, concat="Yes"))
     np.random.seed(0)
     driver.main(["--settings", str(exp), "--dataset-npz", p, "--max-iterations", "60", "--prefetch", "2",
-                 "--time-budget", "60", "--no-periodic-eval", "--final-eval", "0"])
+                 "--time-budget", "60", "--no-periodic-eval", "--final-eval", "0", "--no-save"])
     text = capsys.readouterr().out
     assert "Validation filtered MRR" not in text
     line = json.loads([l for l in text.splitlines() if l.startswith("{")][-1])

