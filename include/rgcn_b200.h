@@ -53,7 +53,11 @@ int64_t rgcn_launch_count(void);
  * in L2; fastest, fp32 summation order not reproducible run to run), -1 = auto (default),
  * 2 = EXPERIMENTAL component-major path for 5x5 blocks (rgcn_block_forward / rgcn_block_backward only;
  * falls back to 1 for other shapes; not yet validated on hardware -- never selected automatically).
- * The environment variable RGCN_BLOCK_ALGO overrides the option. */
+ * The environment variable RGCN_BLOCK_ALGO overrides the option.
+ * "graph_views": which sorted views GPU-prepared graphs created AFTER the call get: 1 = the two CSR views
+ * (deterministic block mode, basis layers), 2 = the two weight-id-major views (default block kernels),
+ * 3 = all four (default).  A 200 M-message graph saves ~5 GB and half its preparation time with 2; entry
+ * points return RGCN_ERR_INVALID when the view they walk is absent. */
 int rgcn_set_option(const char* name, int64_t value);
 
 /* Dense fp32-accurate GEMM on the tcgen05 tensor cores (3xTF32 split, TMEM accumulators):
@@ -126,6 +130,20 @@ int rgcn_graph_create_messages(const int32_t* dst_host, const int32_t* src_host,
                                const int32_t* relw_host, const float* norm_host, int64_t M,
                                int32_t V_dst, int32_t V_src, int32_t n_relw, int device,
                                void* stream, rgcn_graph_t** out);
+
+/* The same two constructors for index arrays that ALREADY live on `device` (int32 / float device pointers,
+ * same shapes and meaning as the _host arguments above): the node-sharded path partitions the edge list on
+ * the GPU and bench.py generates its synthetic graphs there, so a 100 M-edge list never visits the host.
+ * GPU preparation only (device must be >= 0); the arrays are read on `stream` and may be freed by the caller
+ * as soon as the call returns.  Replaces the same reference code as rgcn_graph_create
+ * (extras/graph_representations.py:21-27, :84-93, :124-133). */
+int rgcn_graph_create_device(const int32_t* triples_dev, int64_t E, int32_t V, int32_t R, int norm_mode,
+                             const float* norm_f_dev, const float* norm_b_dev, int device, void* stream,
+                             rgcn_graph_t** out);
+int rgcn_graph_create_messages_device(const int32_t* dst_dev, const int32_t* src_dev,
+                                      const int32_t* relw_dev, const float* norm_dev, int64_t M,
+                                      int32_t V_dst, int32_t V_src, int32_t n_relw, int device,
+                                      void* stream, rgcn_graph_t** out);
 
 /* Opt-in stream-ordered destroy: GPU-prepared graphs return their arrays with cudaFreeAsync on `stream` (no
  * device synchronisation); every kernel that used the graph must be ordered before `stream`'s tail.  Host-prepared

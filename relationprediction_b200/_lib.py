@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "librgcn_b200.so")
 EXPORTED_SYMBOLS = [
     "rgcn_version", "rgcn_last_error", "rgcn_launch_count", "rgcn_profile_enable", "rgcn_profile_read",
     "rgcn_set_option", "rgcn_gemm_tf32x3", "rgcn_gemm_tn_tf32x3", "rgcn_graph_destroy_async", "rgcn_sample_edge_neighborhood", "rgcn_sampler_create", "rgcn_sampler_draw", "rgcn_sampler_destroy", "rgcn_sumsq_accumulate", "rgcn_adam_update",
-    "rgcn_graph_create", "rgcn_graph_create_messages", "rgcn_graph_destroy", "rgcn_graph_info",
+    "rgcn_graph_create", "rgcn_graph_create_messages", "rgcn_graph_create_device", "rgcn_graph_create_messages_device",
+    "rgcn_graph_destroy", "rgcn_graph_info",
     "rgcn_graph_export_bytes", "rgcn_graph_export",
     "rgcn_block_workspace_bytes", "rgcn_block_forward", "rgcn_block_backward",
     "rgcn_block_aggregate_workspace_bytes", "rgcn_block_aggregate", "rgcn_block_aggregate_backward",
@@ -70,6 +71,11 @@ def _declare(lib):
     lib.rgcn_graph_create_messages.restype = c_int
     lib.rgcn_graph_create_messages.argtypes = [vp, vp, vp, vp, c_int64, c_int32, c_int32, c_int32,
                                                c_int, vp, POINTER(vp)]
+    lib.rgcn_graph_create_device.restype = c_int
+    lib.rgcn_graph_create_device.argtypes = [vp, c_int64, c_int32, c_int32, c_int, vp, vp, c_int, vp, POINTER(vp)]
+    lib.rgcn_graph_create_messages_device.restype = c_int
+    lib.rgcn_graph_create_messages_device.argtypes = [vp, vp, vp, vp, c_int64, c_int32, c_int32, c_int32,
+                                                      c_int, vp, POINTER(vp)]
     lib.rgcn_graph_destroy.restype = c_int
     lib.rgcn_graph_destroy.argtypes = [vp]
     lib.rgcn_graph_destroy_async.restype = c_int

@@ -107,6 +107,16 @@ int common_checks(const rgcn_graph_t* g, int32_t d, int32_t B, const char* who) 
   return RGCN_OK;
 }
 
+// the views a code path walks must have been built (rgcn_set_option("graph_views", ...))
+int need_views(const rgcn_graph_t* g, bool csr, bool rel, const char* who) {
+  if ((csr && !g->has_csr) || (rel && !g->has_rel)) {
+    rgcn_set_error(std::string(who) + ": the graph was prepared without the " + (csr && !g->has_csr ? "CSR" : "weight-id-major") +
+                   " views this path needs (option graph_views)");
+    return RGCN_ERR_INVALID;
+  }
+  return RGCN_OK;
+}
+
 int layer_checks(const rgcn_graph_t* g, int32_t d, int32_t B, const char* who) {
   int rc = common_checks(g, d, B, who);
   if (rc) return rc;
@@ -147,6 +157,21 @@ static bool use_cm(int d, int s) {
   return algo == 2 && block_cm_supported(d, s);
 }
 
+// 3 = weight-id-major with TMA-staged gathers (block_staged.cu) where the block size supports it
+static bool use_staged(int d, int s) {
+  int algo = g_block_algo;
+  if (const char* e = std::getenv("RGCN_BLOCK_ALGO")) algo = std::atoi(e);
+  return algo == 3 && block_stg_supported(d, s);
+}
+
+static int launch_block_relmajor(const WorkItem* items, int n_items, const int32_t* r_row, const int32_t* r_nbr,
+                                 const float* r_norm, const float* X, int ldx, int d, int s, const float* Wt,
+                                 float* out, const float* Hrow, int ldh, float* dWt, cudaStream_t st) {
+  if (use_staged(d, s))
+    return launch_block_stg(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, s, Wt, out, Hrow, ldh, dWt, st);
+  return launch_block_rel(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, s, Wt, out, Hrow, ldh, dWt, st);
+}
+
 static bool use_rel_major(int d, int s) {
   int algo = g_block_algo;
   if (const char* e = std::getenv("RGCN_BLOCK_ALGO")) algo = std::atoi(e);
@@ -157,6 +182,14 @@ static bool use_rel_major(int d, int s) {
 extern "C" int rgcn_set_option(const char* name, int64_t value) {
   if (name && std::string(name) == "block_algo") {
     g_block_algo = (int)value;
+    return RGCN_OK;
+  }
+  if (name && std::string(name) == "graph_views") {
+    if (value < 1 || value > 3) {
+      rgcn_set_error("rgcn_set_option: graph_views must be 1 (CSR), 2 (weight-id major) or 3 (both)");
+      return RGCN_ERR_INVALID;
+    }
+    g_graph_views = (int)value;
     return RGCN_OK;
   }
   rgcn_set_error("rgcn_set_option: unknown option");
@@ -283,6 +316,11 @@ extern "C" int rgcn_block_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
   rc = rgcn_check_cuda(cudaSetDevice(g->device), "cudaSetDevice");
   if (rc) return rc;
   const int s = d / B, R = g->n_relw / 2;
+  {
+    const bool relm = use_rel_major(d, s) || use_cm(d, s);
+    rc = need_views(g, !relm, relm, "rgcn_block_forward");
+    if (rc) return rc;
+  }
   const int slabs = slabs_for(d);
   const int64_t n_split = g->by_dst.n_split;
   Carver ws(workspace, workspace_bytes);
@@ -335,7 +373,7 @@ extern "C" int rgcn_block_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
     // out = dropout(S);  out[dst] += W_r . sum(norm x)  (L2 vector reductions);  out = relu(out)
     rc = launch_mask_relu(out, drop_mask, 1.0f / keep, 0, (int64_t)g->V_dst * d, st);
     if (rc) return rc;
-    rc = launch_block_rel(g->by_rel.d_items, (int)g->by_rel.n_items, g->by_rel.d_row,
+    rc = launch_block_relmajor(g->by_rel.d_items, (int)g->by_rel.n_items, g->by_rel.d_row,
                           g->by_rel.d_nbr, g->by_rel.d_norm, H, d, d, s, Wt, out, nullptr, 0, nullptr,
                           st);
     if (rc) return rc;
@@ -375,6 +413,11 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   rc = rgcn_check_cuda(cudaSetDevice(g->device), "cudaSetDevice");
   if (rc) return rc;
   const int s = d / B, R = g->n_relw / 2;
+  {
+    const bool relm = use_rel_major(d, s) || use_cm(d, s);
+    rc = need_views(g, !relm, true, "rgcn_block_backward");
+    if (rc) return rc;
+  }
   const int slabs = slabs_for(d);
   const int64_t n_split = g->by_src.n_split;
   const int64_t wt = (int64_t)g->n_relw * s * d;
@@ -478,7 +521,7 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   const bool rel = use_rel_major(d, s);
   const bool fused = rel && block_rel_fuse_dw_supported(d, s) && !std::getenv("RGCN_NO_FUSE_DW");
   if (rel) {
-    rc = launch_block_rel(g->by_rel_src.d_items, (int)g->by_rel_src.n_items, g->by_rel_src.d_row,
+    rc = launch_block_relmajor(g->by_rel_src.d_items, (int)g->by_rel_src.n_items, g->by_rel_src.d_row,
                           g->by_rel_src.d_nbr, g->by_rel_src.d_norm, G, d, d, s, Wtt, dH,
                           fused ? H : nullptr, d, fused ? dWt : nullptr, st);
   } else {
@@ -533,6 +576,11 @@ extern "C" int rgcn_block_aggregate(const rgcn_graph_t* g, int32_t d, int32_t B,
   rc = rgcn_check_cuda(cudaSetDevice(g->device), "cudaSetDevice");
   if (rc) return rc;
   const int s = d / B, R = g->n_relw / 2;
+  {
+    const bool relm = use_rel_major(d, s) || use_cm(d, s);
+    rc = need_views(g, !relm, relm, "rgcn_block_aggregate");
+    if (rc) return rc;
+  }
   const int slabs = slabs_for(d);
   const int64_t n_split = g->by_dst.n_split;
   Carver ws(workspace, workspace_bytes);
@@ -543,7 +591,7 @@ extern "C" int rgcn_block_aggregate(const rgcn_graph_t* g, int32_t d, int32_t B,
   rc = launch_block_relayout(Wf, Wb, R, B, s, 0, Wt, st);
   if (rc) return rc;
   if (use_rel_major(d, s)) {
-    rc = launch_block_rel(g->by_rel.d_items, (int)g->by_rel.n_items, g->by_rel.d_row, g->by_rel.d_nbr,
+    rc = launch_block_relmajor(g->by_rel.d_items, (int)g->by_rel.n_items, g->by_rel.d_row, g->by_rel.d_nbr,
                           g->by_rel.d_norm, X, d, d, s, Wt, out, nullptr, 0, nullptr, st);
   } else {
     if (n_split > 0) {
@@ -578,6 +626,11 @@ extern "C" int rgcn_block_aggregate_backward(const rgcn_graph_t* g, int32_t d, i
   rc = rgcn_check_cuda(cudaSetDevice(g->device), "cudaSetDevice");
   if (rc) return rc;
   const int s = d / B, R = g->n_relw / 2;
+  {
+    const bool relm = use_rel_major(d, s) || use_cm(d, s);
+    rc = need_views(g, !relm, true, "rgcn_block_aggregate_backward");
+    if (rc) return rc;
+  }
   const int slabs = slabs_for(d);
   const int64_t n_split = g->by_src.n_split;
   const int64_t wt = (int64_t)g->n_relw * s * d;
@@ -596,7 +649,7 @@ extern "C" int rgcn_block_aggregate_backward(const rgcn_graph_t* g, int32_t d, i
   const bool rel = use_rel_major(d, s);
   const bool fused = rel && block_rel_fuse_dw_supported(d, s) && !std::getenv("RGCN_NO_FUSE_DW");
   if (rel) {
-    rc = launch_block_rel(g->by_rel_src.d_items, (int)g->by_rel_src.n_items, g->by_rel_src.d_row,
+    rc = launch_block_relmajor(g->by_rel_src.d_items, (int)g->by_rel_src.n_items, g->by_rel_src.d_row,
                           g->by_rel_src.d_nbr, g->by_rel_src.d_norm, G, d, d, s, Wtt, dX,
                           fused ? X : nullptr, d, fused ? dWt : nullptr, st);
   } else {
@@ -645,6 +698,8 @@ extern "C" int rgcn_basis_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
                                   float keep, int relu, float* out, float* saved, void* workspace,
                                   int64_t workspace_bytes, void* stream) {
   int rc = layer_checks(g, d, B, "rgcn_basis_forward");
+  if (rc) return rc;
+  rc = need_views(g, true, false, "rgcn_basis_forward");
   if (rc) return rc;
   if (!H || !Vf || !Vb || !Cf || !Cb || !Wself || !out || !saved || !workspace || keep <= 0.f) {
     rgcn_set_error("rgcn_basis_forward: null pointer or keep <= 0");
@@ -696,6 +751,8 @@ extern "C" int rgcn_basis_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
                                    float* dCb, float* dWself, void* workspace,
                                    int64_t workspace_bytes, void* stream) {
   int rc = layer_checks(g, d, B, "rgcn_basis_backward");
+  if (rc) return rc;
+  rc = need_views(g, true, false, "rgcn_basis_backward");
   if (rc) return rc;
   if (!H || !Vf || !Vb || !Cf || !Cb || !Wself || !saved || !dOut || !dH || !dVf || !dVb || !dCf ||
       !dCb || !dWself || !workspace || (relu && !out) || keep <= 0.f) {

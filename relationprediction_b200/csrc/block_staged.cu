@@ -1,0 +1,380 @@
+// block_staged.cu -- weight-id-major block-diagonal aggregation with TMA-STAGED gathers (sm_100a).
+//
+// Same arithmetic and the same work items as k_block_rel (rgcn_kernels.cu): a warp owns one (work item,
+// column slab) = up to item_max messages of ONE weight id, keeps that weight block slab in REGISTERS,
+// pre-sums runs of messages with the same accumulation row and adds each run's transformed row into
+// out[row] with 128-bit vector reductions that resolve in L2.  What changes is the data path of the gathered
+// rows.  ncu on the HBM-bound shape (d = 512, s = 8, profiles/r2_ncu_synthetic.md) showed k_block_rel stalled
+// on its own gathers (long-scoreboard 3.2 of 3.5 resident warps per scheduler, 16 warps/SM at 128 registers,
+// DRAM 38 %, L2 45 %, issue 50 %): the rows in flight lived in registers, so occupancy bounded the bytes in
+// flight.  Here every warp drives a private ring of DEPTH row slots in shared memory: one elected lane issues
+// cp.async.bulk (TMA bulk copy, global -> shared, mbarrier complete_tx) for the row of message m + DEPTH the
+// moment message m has been read out of its slot, so DEPTH-1 rows per warp are always in flight without
+// holding a single register, the consumer reads its quads with conflict-free LDS.128, and the former
+// register -> shared -> register bounce (STS.128 + 8 scalar LDS per run) disappears: the lanes that share a
+// block exchange their quads with shuffles.
+//
+// Reference arithmetic: encoders/message_gcns/gcn_basis_concat.py:35-52 (messages) and :69-75 (the two
+// normalised SpMMs); FUSE_DW also produces the block weight gradient in the same walk (what tf.gradients
+// derives for W_forward / W_backward, optimization/abstract.py:117-118).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "kernels.cuh"
+
+#define FULL 0xffffffffu
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init_a(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// TMA bulk copy global -> shared (1-D, 16 B granular); completion is signalled on `bar` as transaction bytes
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void red4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void fma4(float4& a, float s, const float4& x) {
+  a.x = fmaf(s, x.x, a.x);
+  a.y = fmaf(s, x.y, a.y);
+  a.z = fmaf(s, x.z, a.z);
+  a.w = fmaf(s, x.w, a.w);
+}
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 shfl_xor4(const float4& v, int m) {
+  return make_float4(__shfl_xor_sync(FULL, v.x, m), __shfl_xor_sync(FULL, v.y, m), __shfl_xor_sync(FULL, v.z, m),
+                     __shfl_xor_sync(FULL, v.w, m));
+}
+__device__ __forceinline__ float comp(const float4& v, int c) {  // c is a compile-time constant after unrolling
+  return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w));
+}
+
+// S  : block size (4, 8 or 16): S/4 consecutive lanes share a block and exchange their quads with shuffles
+// NV : quads per lane; a column slab is NV*128 columns (NV*512 bytes per gathered row)
+// NW : warps per CTA (every warp is its own producer: no cross-warp synchronisation anywhere)
+// NG : group buffers per warp.  A GROUP is GS = 8 consecutive messages: its rows are requested together -- lane g
+//      issues the bulk copy of the group's g-th row -- and land on ONE mbarrier (expect_tx = the group's bytes), so
+//      the issue and wait overheads are paid once per 8 messages; group i + NG - 1 is requested when group i starts
+//      to be consumed, i.e. 8 (NG - 2) .. 8 (NG - 1) rows per warp are in flight.
+// TAIL : the last slab is narrower than NV*128 columns (d % (NV*128) != 0): lanes past the row end read zeros
+constexpr int GS = 8;
+template <int S, int NV, bool FUSE_DW, bool TAIL, int NW, int NG>
+__global__ void __launch_bounds__(NW * 32, 1)
+    k_block_stg(const WorkItem* __restrict__ items, int n_items, int n_slabs, const int32_t* __restrict__ r_row,
+                const int32_t* __restrict__ r_nbr, const float* __restrict__ r_norm, const float* __restrict__ X, int ldx,
+                int d, const float* __restrict__ Wt, float* __restrict__ out, const float* __restrict__ Hrow, int ldh,
+                float* __restrict__ dWt) {
+  static_assert(S == 4 || S == 8 || S == 16, "block size");
+  static_assert(NG >= 2 && (NG - 1) * GS <= 32, "the fetch cursor must stay within the next index batch");
+  constexpr int G = S / 4;                      // lanes per block
+  constexpr int SLAB_B = NV * 512;              // bytes of one row slab
+  constexpr int RING_B = NG * GS * SLAB_B;      // bytes of one ring (gathered rows; FUSE_DW: a second one for H rows)
+  constexpr int WARP_B = RING_B * (FUSE_DW ? 2 : 1);
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t gring_a = smem_u32(smem) + (uint32_t)warp * WARP_B;
+  const uint32_t hring_a = gring_a + RING_B;
+  const uint32_t full_a = smem_u32(smem) + (uint32_t)NW * WARP_B + (uint32_t)warp * NG * 8;
+  if (lane == 0) {
+    for (int s = 0; s < NG; ++s) mbar_init_a(full_a + s * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const int rel = lane & (G - 1);  // position of this lane's quad inside its block
+  uint32_t gcnt = 0;               // groups requested so far by this warp (buffer = gcnt % NG, phase = gcnt / NG)
+  uint32_t ccnt = 0;               // groups consumed so far
+
+  const int64_t n_units = (int64_t)n_items * n_slabs;
+  for (int64_t unit = (int64_t)blockIdx.x * NW + warp; unit < n_units; unit += (int64_t)gridDim.x * NW) {
+    const int item = (int)(unit / n_slabs);
+    const int c0 = (int)(unit % n_slabs) * (NV * 128);
+    const int4 itv = __ldg(reinterpret_cast<const int4*>(items) + item);
+    const int beg = itv.x, n = itv.y - itv.x, w = itv.z;
+    const int ng = (n + GS - 1) / GS;
+    const uint32_t vb = (uint32_t)min(NV * 128, d - c0) * 4u;  // valid bytes of this slab (d % 4 == 0)
+    const float* Xc = X + c0;
+    const float* Hc = FUSE_DW ? Hrow + c0 : nullptr;
+
+    bool ok[NV];
+    int col[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      col[k] = c0 + 4 * (lane + 32 * k);
+      ok[k] = col[k] < d;
+    }
+
+    // ---- index batches: `cur` = the 32 messages [b0, b0 + 32) being consumed, `nxt` = the following 32 (requests
+    //      run at most (NG-1)*8 <= 32 messages ahead).  start bit i: message i opens a run (row differs from its
+    //      predecessor's); a run is transformed once, at its last message
+    int b0 = 0;
+    int cur_row = 0, cur_nbr = 0, nxt_row = 0, nxt_nbr = 0;
+    float cur_nm = 0.f, nxt_nm = 0.f;
+    if (lane < n) {
+      cur_row = __ldg(r_row + beg + lane);
+      cur_nbr = __ldg(r_nbr + beg + lane);
+      cur_nm = __ldg(r_norm + beg + lane);
+    }
+    if (32 + lane < n) {
+      nxt_row = __ldg(r_row + beg + 32 + lane);
+      nxt_nbr = __ldg(r_nbr + beg + 32 + lane);
+      nxt_nm = __ldg(r_norm + beg + 32 + lane);
+    }
+    auto start_bits = [&](int row_reg, int prev_row_last) {
+      int p = __shfl_up_sync(FULL, row_reg, 1);
+      if (lane == 0) p = prev_row_last;
+      return __ballot_sync(FULL, row_reg != p);
+    };
+    uint32_t cur_start = start_bits(cur_row, -1);
+    uint32_t nxt_start = start_bits(nxt_row, __shfl_sync(FULL, cur_row, 31));
+
+    // request group gi (0 <= gi < ng, warp-uniform): lane g < cnt issues the copy of message gi*8 + g
+    auto request = [&](int gi) {
+      const int q_rel = gi * GS - b0;           // first message of the group relative to the current batch: 0 .. 56
+      const bool in_cur = q_rel < 32;           // a group never straddles batches (8 | 32)
+      const int sl = (q_rel + (lane & (GS - 1))) & 31;
+      const int src = __shfl_sync(FULL, in_cur ? cur_nbr : nxt_nbr, sl);
+      const int cnt = min(GS, n - gi * GS);
+      const uint32_t buf = gcnt % NG;
+      uint32_t tx = (uint32_t)cnt * vb;
+      int hrow = 0;
+      bool st = false;
+      if (FUSE_DW) {
+        hrow = __shfl_sync(FULL, in_cur ? cur_row : nxt_row, sl);
+        const uint32_t sb = ((in_cur ? cur_start : nxt_start) >> (q_rel & 31)) & ((1u << cnt) - 1u);
+        st = (sb >> (lane & (GS - 1))) & 1u;
+        tx += (uint32_t)__popc(sb) * vb;
+      }
+      if (lane == 0) mbar_expect_tx_a(full_a + buf * 8, tx);
+      __syncwarp();
+      if (lane < cnt) {
+        const uint32_t off = (buf * GS + lane) * SLAB_B;
+        bulk_g2s_a(gring_a + off, Xc + (size_t)(uint32_t)src * (uint32_t)ldx, vb, full_a + buf * 8);
+        if (FUSE_DW && st) bulk_g2s_a(hring_a + off, Hc + (size_t)(uint32_t)hrow * (uint32_t)ldh, vb, full_a + buf * 8);
+      }
+      ++gcnt;
+    };
+    for (int gi = 0; gi < min(NG - 1, ng); ++gi) request(gi);
+
+    // ---- weights of this (weight id, slab) -> registers, pre-arranged by exchange distance r = lane ^ source lane
+    float4 wsel[G][4][NV];
+    float4 acc[FUSE_DW ? G : 1][4][NV];
+    const float* wr = Wt + (size_t)w * S * d;
+#pragma unroll
+    for (int r = 0; r < G; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          wsel[r][j][k] = ok[k] ? ldg4(wr + (size_t)(4 * (rel ^ r) + j) * d + col[k]) : zero4();
+          if (FUSE_DW) acc[FUSE_DW ? r : 0][j][k] = zero4();
+        }
+
+    float4 xs[NV], hq[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) xs[k] = hq[k] = zero4();
+
+    // one transform per run: y = T . xs over the block (quads of the lanes sharing the block arrive by shuffle);
+    // the same products feed the weight gradient (xs = summed upstream gradient, hq = the run's own input row)
+    auto flush = [&](int row) {
+      float4 y[NV];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) y[k] = zero4();
+#pragma unroll
+      for (int r = 0; r < G; ++r) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const float4 v = (r == 0) ? xs[k] : shfl_xor4(xs[k], r);  // quad of the lane at exchange distance r
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float xv = comp(v, j);
+            fma4(y[k], xv, wsel[r][j][k]);
+            if (FUSE_DW) fma4(acc[FUSE_DW ? r : 0][j][k], xv, hq[k]);
+          }
+        }
+      }
+      float* po = out + (size_t)(uint32_t)row * (uint32_t)d;
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+        if (!TAIL || ok[k]) red4(po + col[k], y[k]);
+    };
+
+    uint32_t ends_mask = 0;
+    auto make_ends = [&]() {  // message t of the current batch closes its run when its successor opens one / the item ends
+      const int nb = min(32, n - b0);
+      ends_mask = (cur_start >> 1) | ((b0 + nb < n) ? ((nxt_start & 1u) << 31) : (1u << (nb - 1)));
+    };
+    make_ends();
+
+    for (int gi = 0; gi < ng; ++gi) {
+      if (gi + NG - 1 < ng) request(gi + NG - 1);  // its buffer held group gi - 1, fully consumed
+      const uint32_t buf = ccnt % NG;
+      mbar_wait_a(full_a + buf * 8, (ccnt / NG) & 1u);
+      ++ccnt;
+      const uint32_t gbase = gring_a + buf * GS * SLAB_B + lane * 16;
+      const uint32_t hbase = hring_a + buf * GS * SLAB_B + lane * 16;
+      const int cnt = min(GS, n - gi * GS);
+      const int tb0 = gi * GS - b0;
+      for (int t = 0; t < cnt; ++t) {
+        const int tb = tb0 + t;
+        const float nm = __shfl_sync(FULL, cur_nm, tb);
+        const bool st = (cur_start >> tb) & 1u;
+        float4 x[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          x[k] = lds4(gbase + t * SLAB_B + k * 512);
+          if (TAIL && !ok[k]) x[k] = zero4();  // bytes past the row end were not copied
+        }
+        if (st) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) xs[k] = make_float4(nm * x[k].x, nm * x[k].y, nm * x[k].z, nm * x[k].w);
+          if (FUSE_DW) {  // the run's own input row
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+              hq[k] = lds4(hbase + t * SLAB_B + k * 512);
+              if (TAIL && !ok[k]) hq[k] = zero4();
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) fma4(xs[k], nm, x[k]);
+        }
+        if ((ends_mask >> tb) & 1u) flush(__shfl_sync(FULL, cur_row, tb));
+      }
+      if (tb0 + GS == 32 && gi + 1 < ng) {  // the batch is used up: rotate
+        b0 += 32;
+        cur_row = nxt_row;
+        cur_nbr = nxt_nbr;
+        cur_nm = nxt_nm;
+        cur_start = nxt_start;
+        nxt_row = nxt_nbr = 0;
+        nxt_nm = 0.f;
+        if (b0 + 32 + lane < n) {
+          nxt_row = __ldg(r_row + beg + b0 + 32 + lane);
+          nxt_nbr = __ldg(r_nbr + beg + b0 + 32 + lane);
+          nxt_nm = __ldg(r_norm + beg + b0 + 32 + lane);
+        }
+        nxt_start = start_bits(nxt_row, __shfl_sync(FULL, cur_row, 31));
+        make_ends();
+      }
+    }
+    if (FUSE_DW) {
+#pragma unroll
+      for (int r = 0; r < G; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float* pw = dWt + ((size_t)w * S + 4 * (rel ^ r) + j) * d;
+#pragma unroll
+          for (int k = 0; k < NV; ++k)
+            if (!TAIL || ok[k]) red4(pw + col[k], acc[FUSE_DW ? r : 0][j][k]);
+        }
+    }
+  }
+}
+
+template <int S, int NV, bool FUSE, bool TAIL, int NW, int NG>
+int launch_stg_t(const WorkItem* items, int n_items, const int32_t* r_row, const int32_t* r_nbr, const float* r_norm,
+                 const float* X, int ldx, int d, const float* Wt, float* out, const float* Hrow, int ldh, float* dWt,
+                 cudaStream_t st) {
+  constexpr int SLAB_B = NV * 512;
+  constexpr int smem = NW * NG * GS * SLAB_B * (FUSE ? 2 : 1) + NW * NG * 8;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  auto kern = k_block_stg<S, NV, FUSE, TAIL, NW, NG>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = rgcn_check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                             "cudaFuncSetAttribute(staged smem)");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  const int n_slabs = (d + NV * 128 - 1) / (NV * 128);
+  const int64_t units = (int64_t)n_items * n_slabs;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = (int)std::min<int64_t>((units + NW - 1) / NW, sms);  // persistent: one CTA per SM
+  if (grid < 1) grid = 1;
+  kern<<<grid, NW * 32, smem, st>>>(items, n_items, n_slabs, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt);
+  ++g_rgcn_launches;
+  return rgcn_check_cuda(cudaGetLastError(), "k_block_stg");
+}
+
+}  // namespace
+
+bool block_stg_supported(int d, int s) { return (s == 4 || s == 8 || s == 16) && d % s == 0 && d % 4 == 0; }
+
+int launch_block_stg(const WorkItem* items, int n_items, const int32_t* r_row, const int32_t* r_nbr,
+                     const float* r_norm, const float* X, int ldx, int d, int s, const float* Wt, float* out,
+                     const float* Hrow, int ldh, float* dWt, cudaStream_t st) {
+  if (n_items == 0) return RGCN_OK;
+  if (!block_stg_supported(d, s) || (ldx % 4) != 0 || (dWt && (ldh % 4) != 0)) {
+    rgcn_set_error("staged block kernel: unsupported shape");
+    return RGCN_ERR_INVALID;
+  }
+  const bool fuse = dWt != nullptr;
+#define ARGS items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt, st
+#define STG(S_, NV_, FUSE_, NW_, NG_)                                                    \
+  do {                                                                                   \
+    if (d % ((NV_)*128) != 0) return launch_stg_t<S_, NV_, FUSE_, true, NW_, NG_>(ARGS); \
+    return launch_stg_t<S_, NV_, FUSE_, false, NW_, NG_>(ARGS);                          \
+  } while (0)
+  // Configurations (one persistent CTA per SM; registers from -Xptxas -v, ptxas budgets them for the block rounded
+  // up to 4 warps; shared memory = warps x groups x 8 rows x slab bytes, twice that for the fused backward):
+  //   forward        : 2 quads per lane (1 KB slabs), 12 warps x 2 groups = 192 KB   (RGCN_STG_FWD=1: 14 warps;
+  //                    =2: 1 quad per lane, 16 warps x 3 groups)
+  //   fused backward : weights + gradient accumulators in registers (1 quad per lane: ~147), 12 warps x 2 groups x
+  //                    (gathered-row ring + input-row ring) = 192 KB;  s = 16: 8 warps (230 registers)
+  int fwd_cfg = 0;
+  if (const char* e = std::getenv("RGCN_STG_FWD")) fwd_cfg = std::atoi(e);
+  if (s == 4) {
+    if (!fuse) {
+      if (d <= 128 || fwd_cfg == 2) STG(4, 1, false, 16, 3);
+      if (fwd_cfg == 1) STG(4, 2, false, 14, 2);
+      STG(4, 2, false, 12, 2);
+    }
+    STG(4, 1, true, 12, 2);
+  } else if (s == 8) {
+    if (!fuse) {
+      if (d <= 128 || fwd_cfg == 2) STG(8, 1, false, 16, 3);
+      if (fwd_cfg == 1) STG(8, 2, false, 14, 2);
+      STG(8, 2, false, 12, 2);
+    }
+    STG(8, 1, true, 12, 2);
+  } else {
+    if (!fuse) STG(16, 1, false, 16, 3);
+    STG(16, 1, true, 8, 2);
+  }
+#undef ARGS
+#undef STG
+#undef STG
+}

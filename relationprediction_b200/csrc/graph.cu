@@ -37,6 +37,10 @@ int rgcn_check_cuda(cudaError_t e, const char* what) {
   return RGCN_ERR_CUDA;
 }
 
+// which sorted views new graphs get: bit 0 = the two CSR views, bit 1 = the two weight-id-major views
+// (rgcn_set_option("graph_views", mask); GPU-prepared graphs only -- the host builder always builds all four)
+int g_graph_views = 3;
+
 namespace {
 
 // Stable LSD counting sort of message ids by (major, minor).  Returns perm (sorted -> message id)
@@ -175,6 +179,8 @@ rgcn_graph* new_graph(int64_t M, int32_t V_dst, int32_t V_src, int32_t n_relw, i
   // message-id permutations are only needed by rgcn_graph_export: skip them on very large graphs
   g->keep_mid = M <= (int64_t)(16 << 20);
   if (const char* e = std::getenv("RGCN_KEEP_MID")) g->keep_mid = std::atoi(e) != 0;
+  g->has_csr = (g_graph_views & 1) != 0;
+  g->has_rel = (g_graph_views & 2) != 0;
   return g;
 }
 
@@ -228,6 +234,7 @@ int build(const int32_t* dst, const int32_t* src, const int32_t* relw, const flo
     *out = g;
     return RGCN_OK;
   }
+  g->has_csr = g->has_rel = true;  // the host builder always produces all four views
   for (int64_t m = 0; m < M; ++m) {
     if (dst[m] < 0 || dst[m] >= V_dst || src[m] < 0 || src[m] >= V_src || relw[m] < 0 ||
         relw[m] >= n_relw) {
@@ -450,6 +457,72 @@ extern "C" int rgcn_graph_create(const int32_t* triples_host, int64_t E, int32_t
   }
   return build(dst.data(), src.data(), relw.data(), norm.data(), M, V, V, 2 * R, device, stream,
                out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Constructors over index arrays that already live on the device (the node-sharded path partitions the
+// edge list on the GPU, bench.py generates it there): nothing visits the host, GPU preparation only.
+// ------------------------------------------------------------------------------------------------
+extern "C" int rgcn_graph_create_messages_device(const int32_t* dst_dev, const int32_t* src_dev,
+                                                 const int32_t* relw_dev, const float* norm_dev, int64_t M,
+                                                 int32_t V_dst, int32_t V_src, int32_t n_relw, int device,
+                                                 void* stream, rgcn_graph_t** out) {
+  if (!out) {
+    rgcn_set_error("out is null");
+    return RGCN_ERR_INVALID;
+  }
+  *out = nullptr;
+  if (device < 0) {
+    rgcn_set_error("rgcn_graph_create_messages_device: needs a device ordinal");
+    return RGCN_ERR_NODEVICE;
+  }
+  if (M < 0 || M > 0x7fffffffLL || V_dst < 0 || V_src < 0 || n_relw <= 0 ||
+      (M > 0 && (!dst_dev || !src_dev || !relw_dev || !norm_dev))) {
+    rgcn_set_error("rgcn_graph_create_messages_device: bad sizes or null array");
+    return RGCN_ERR_INVALID;
+  }
+  rgcn_graph* g = new_graph(M, V_dst, V_src, n_relw, device);
+  if (!g) return RGCN_ERR_NOMEM;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = rgcn_check_cuda(cudaSetDevice(device), "cudaSetDevice");
+  if (!rc) rc = rgcn_check_messages_device(dst_dev, src_dev, relw_dev, M, V_dst, V_src, n_relw, st);
+  if (!rc) rc = rgcn_build_on_device(g, dst_dev, src_dev, relw_dev, norm_dev, st);
+  if (rc) {
+    rgcn_graph_destroy(g);
+    return rc;
+  }
+  *out = g;
+  return RGCN_OK;
+}
+
+extern "C" int rgcn_graph_create_device(const int32_t* triples_dev, int64_t E, int32_t V, int32_t R,
+                                        int norm_mode, const float* norm_f_dev, const float* norm_b_dev,
+                                        int device, void* stream, rgcn_graph_t** out) {
+  if (!out) {
+    rgcn_set_error("out is null");
+    return RGCN_ERR_INVALID;
+  }
+  *out = nullptr;
+  if (device < 0) {
+    rgcn_set_error("rgcn_graph_create_device: needs a device ordinal");
+    return RGCN_ERR_NODEVICE;
+  }
+  if (E < 0 || V < 0 || R <= 0 || (E > 0 && !triples_dev) || 2 * E > 0x7fffffffLL || norm_mode < 0 ||
+      norm_mode > 2 || (norm_mode == RGCN_NORM_EXPLICIT && E > 0 && (!norm_f_dev || !norm_b_dev))) {
+    rgcn_set_error("rgcn_graph_create_device: bad arguments");
+    return RGCN_ERR_INVALID;
+  }
+  rgcn_graph* g = new_graph(2 * E, V, V, 2 * R, device);
+  if (!g) return RGCN_ERR_NOMEM;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = rgcn_check_cuda(cudaSetDevice(device), "cudaSetDevice");
+  if (!rc) rc = rgcn_build_from_triples_device(g, triples_dev, E, V, R, norm_mode, norm_f_dev, norm_b_dev, st);
+  if (rc) {
+    rgcn_graph_destroy(g);
+    return rc;
+  }
+  *out = g;
+  return RGCN_OK;
 }
 
 namespace {

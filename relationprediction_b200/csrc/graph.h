@@ -73,6 +73,8 @@ struct rgcn_graph {
   int supertile_rows = 8192;
   bool built_on_device = false;  // structures were built by graph_device.cu (host vectors empty)
   bool keep_mid = true;          // keep message-id permutations / original-order norm for export
+  bool has_csr = true;           // by_dst / by_src built (deterministic block mode, basis layers)
+  bool has_rel = true;           // by_rel / by_rel_src built (weight-id-major block kernels)
   float* d_msg_norm = nullptr;
 };
 
@@ -89,5 +91,6 @@ int rgcn_check_messages_device(const int32_t* d_dst, const int32_t* d_src, const
                                int64_t M, int32_t V_dst, int32_t V_src, int32_t n_relw,
                                cudaStream_t st);
 
+extern int g_graph_views;  // graph.cu
 void rgcn_set_error(const std::string& s);
 int rgcn_check_cuda(cudaError_t e, const char* what);

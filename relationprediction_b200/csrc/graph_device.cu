@@ -264,18 +264,21 @@ int scan_i32(Scratch& sc, const int32_t* in, int32_t* out, int64_t n, cudaStream
 //   -- one cudaStreamSynchronize for all four views --
 //   phase B: allocate the work-item arrays (sizes now known on the host) and fill them.
 struct ViewTmp {
-  Scratch sc;
+  Scratch sc;  // survives until phase B: only the item / split offsets (4 B per row or key)
   int32_t* item_off = nullptr;
   int32_t* split_off = nullptr;
   int32_t n_keys = 0;
   explicit ViewTmp(cudaStream_t st) : sc(st) {}
 };
+// The sort temporaries (two 64-bit key arrays, two id arrays, the radix-sort workspace: 28 B per message) live
+// in a phase-local Scratch and return to the stream-ordered pool before the next view is built, so a
+// 200 M-message graph peaks at one view's temporaries instead of four.
 
 int csr_phase_a(rgcn_graph* g, CsrSide& side, ViewTmp& t, const int32_t* row, int32_t n_rows,
                 const int32_t* nbr, const int32_t* relw, const float* norm, int64_t M,
                 bool count_runs, unsigned long long* d_runs, int32_t* h_totals /* pinned [2] */,
                 cudaStream_t st, int64_t& bytes) {
-  Scratch& sc = t.sc;
+  Scratch sc(st);
   int rc;
   if ((rc = dalloc(&side.d_rowptr, (int64_t)n_rows + 1, st, &bytes))) return rc;
   int32_t* perm;
@@ -302,8 +305,8 @@ int csr_phase_a(rgcn_graph* g, CsrSide& side, ViewTmp& t, const int32_t* row, in
   int32_t *nitems, *issplit;
   if ((rc = sc.get(&nitems, (int64_t)n_rows + 1))) return rc;
   if ((rc = sc.get(&issplit, (int64_t)n_rows + 1))) return rc;
-  if ((rc = sc.get(&t.item_off, (int64_t)n_rows + 1))) return rc;
-  if ((rc = sc.get(&t.split_off, (int64_t)n_rows + 1))) return rc;
+  if ((rc = t.sc.get(&t.item_off, (int64_t)n_rows + 1))) return rc;
+  if ((rc = t.sc.get(&t.split_off, (int64_t)n_rows + 1))) return rc;
   DCK(cudaMemsetAsync(nitems, 0, ((size_t)n_rows + 1) * 4, st));
   DCK(cudaMemsetAsync(issplit, 0, ((size_t)n_rows + 1) * 4, st));
   if (n_rows > 0) {
@@ -338,7 +341,7 @@ int csr_phase_b(rgcn_graph* g, CsrSide& side, ViewTmp& t, int32_t n_rows, const 
 int rel_phase_a(rgcn_graph* g, RelSide& side, ViewTmp& t, const int32_t* row, int32_t n_rows,
                 const int32_t* nbr, const int32_t* relw, const float* norm, int64_t M,
                 int32_t* h_total /* pinned [1] */, cudaStream_t st, int64_t& bytes) {
-  Scratch& sc = t.sc;
+  Scratch sc(st);
   int rc;
   const int32_t n_super = std::max(1, (n_rows + g->supertile_rows - 1) / g->supertile_rows);
   side.n_super = n_super;
@@ -364,7 +367,7 @@ int rel_phase_a(rgcn_graph* g, RelSide& side, ViewTmp& t, const int32_t* row, in
   }
   int32_t* nitems;
   if ((rc = sc.get(&nitems, nkeys + 1))) return rc;
-  if ((rc = sc.get(&t.item_off, nkeys + 1))) return rc;
+  if ((rc = t.sc.get(&t.item_off, nkeys + 1))) return rc;
   DCK(cudaMemsetAsync(nitems, 0, ((size_t)nkeys + 1) * 4, st));
   k_rel_item_counts<<<grid_for(nkeys), 256, 0, st>>>(side.d_ptr, (int32_t)nkeys, g->item_max, nitems);
   ++g_rgcn_launches;
@@ -431,11 +434,17 @@ int rgcn_build_on_device_checked(rgcn_graph* g, const int32_t* d_dst, const int3
     DCK(cudaMemcpyAsync(g->d_msg_norm, d_norm, (size_t)M * 4, cudaMemcpyDeviceToDevice, st));
   }
   ViewTmp t0(st), t1(st), t2(st), t3(st);
-  hs.p[6] = 0;
-  rc = csr_phase_a(g, g->by_dst, t0, d_dst, g->V_dst, d_src, d_relw, d_norm, M, true, d_runs, hs.p + 0, st, bytes);
-  if (!rc) rc = csr_phase_a(g, g->by_src, t1, d_src, g->V_src, d_dst, d_relw, d_norm, M, false, nullptr, hs.p + 2, st, bytes);
-  if (!rc) rc = rel_phase_a(g, g->by_rel, t2, d_dst, g->V_dst, d_src, d_relw, d_norm, M, hs.p + 4, st, bytes);
-  if (!rc) rc = rel_phase_a(g, g->by_rel_src, t3, d_src, g->V_src, d_dst, d_relw, d_norm, M, hs.p + 5, st, bytes);
+  for (int i = 0; i < 8; ++i) hs.p[i] = 0;
+  *hs.runs = 0;
+  rc = RGCN_OK;
+  if (g->has_csr) {
+    rc = csr_phase_a(g, g->by_dst, t0, d_dst, g->V_dst, d_src, d_relw, d_norm, M, true, d_runs, hs.p + 0, st, bytes);
+    if (!rc) rc = csr_phase_a(g, g->by_src, t1, d_src, g->V_src, d_dst, d_relw, d_norm, M, false, nullptr, hs.p + 2, st, bytes);
+  }
+  if (!rc && g->has_rel) {
+    rc = rel_phase_a(g, g->by_rel, t2, d_dst, g->V_dst, d_src, d_relw, d_norm, M, hs.p + 4, st, bytes);
+    if (!rc) rc = rel_phase_a(g, g->by_rel_src, t3, d_src, g->V_src, d_dst, d_relw, d_norm, M, hs.p + 5, st, bytes);
+  }
   if (!rc) rc = rgcn_check_cuda(cudaMemcpyAsync(hs.runs, d_runs, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "copy runs");
   if (!rc && d_bad) rc = rgcn_check_cuda(cudaMemcpyAsync(hs.p + 6, d_bad, 4, cudaMemcpyDeviceToHost, st), "copy flag");
   if (!rc) rc = rgcn_check_cuda(cudaStreamSynchronize(st), "sync(graph prep)");
@@ -444,13 +453,24 @@ int rgcn_build_on_device_checked(rgcn_graph* g, const int32_t* d_dst, const int3
     rgcn_set_error("rgcn_graph_create: index out of range");
     rc = RGCN_ERR_INVALID;
   }
-  if (!rc) rc = csr_phase_b(g, g->by_dst, t0, g->V_dst, hs.p + 0, st, bytes);
-  if (!rc) rc = csr_phase_b(g, g->by_src, t1, g->V_src, hs.p + 2, st, bytes);
-  if (!rc) rc = rel_phase_b(g, g->by_rel, t2, hs.p + 4, st, bytes);
-  if (!rc) rc = rel_phase_b(g, g->by_rel_src, t3, hs.p + 5, st, bytes);
+  if (!rc && g->has_csr) {
+    rc = csr_phase_b(g, g->by_dst, t0, g->V_dst, hs.p + 0, st, bytes);
+    if (!rc) rc = csr_phase_b(g, g->by_src, t1, g->V_src, hs.p + 2, st, bytes);
+  }
+  if (!rc && g->has_rel) {
+    rc = rel_phase_b(g, g->by_rel, t2, hs.p + 4, st, bytes);
+    if (!rc) rc = rel_phase_b(g, g->by_rel_src, t3, hs.p + 5, st, bytes);
+  }
   g->n_groups = (int64_t)*hs.runs;
   g->device_bytes = bytes;
   g->built_on_device = true;
+  if (!rc && M >= (int64_t)(32 << 20)) {
+    // a very large build leaves gigabytes of freed temporaries cached in the stream-ordered pool (release
+    // threshold = max): hand them back to the driver so the caller's own allocator can use the memory
+    rc = rgcn_check_cuda(cudaStreamSynchronize(st), "sync(graph prep end)");
+    cudaMemPool_t pool;
+    if (!rc && cudaDeviceGetDefaultMemPool(&pool, g->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+  }
   return rc;
 }
 

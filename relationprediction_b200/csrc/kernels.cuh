@@ -40,6 +40,13 @@ int launch_block_rel(const WorkItem* items, int n_items, const int32_t* r_row, c
                      const float* r_norm, const float* X, int ldx, int d, int s, const float* Wt,
                      float* out, const float* Hrow, int ldh, float* dWt, cudaStream_t st);
 
+// Same contract as launch_block_rel with the gathered rows staged through shared memory by TMA bulk copies
+// (block_staged.cu); block sizes 4, 8, 16.
+bool block_stg_supported(int d, int s);
+int launch_block_stg(const WorkItem* items, int n_items, const int32_t* r_row, const int32_t* r_nbr,
+                     const float* r_norm, const float* X, int ldx, int d, int s, const float* Wt, float* out,
+                     const float* Hrow, int ldh, float* dWt, cudaStream_t st);
+
 // Block-diagonal weight gradient, weight-id major:
 //   dWt[w][j][b*s+i] += sum_{m: relw_m = w} norm_m * G[dst_m, b*s+i] * H[src_m, b*s+j]
 int launch_block_dw(const WorkItem* items, int n_items, const int32_t* r_dst, const int32_t* r_src,

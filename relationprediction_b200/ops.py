@@ -81,6 +81,50 @@ class Graph:
         _lib.check(rc, "rgcn_graph_create_messages")
         return cls(None, 0, 0, device=device, _handle=h)
 
+    @staticmethod
+    def _dev_i32(name, t, n=None):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.int32 and t.is_contiguous()):
+            raise _lib.RgcnError("%s must be a contiguous CUDA int32 tensor" % name)
+        if n is not None and t.numel() != n:
+            raise _lib.RgcnError("%s has %d elements, expected %d" % (name, t.numel(), n))
+        return t
+
+    @classmethod
+    def from_device_triples(cls, triples, n_entities, n_relations, norm_mode="canonical", norm_f=None, norm_b=None):
+        """Graph from an int32 [E,3] (s,r,o) tensor that already lives on the GPU (rgcn_graph_create_device):
+        the edge list never visits the host."""
+        lib = _lib.load()
+        tri = cls._dev_i32("triples", triples)
+        if tri.dim() != 2 or tri.shape[1] != 3:
+            raise _lib.RgcnError("triples must be [E,3]")
+        for nm, t in (("norm_f", norm_f), ("norm_b", norm_b)):
+            if t is not None:
+                _check_cuda_f32(nm, t, (tri.shape[0],))
+        dev = tri.device.index if tri.device.index is not None else torch.cuda.current_device()
+        h = ctypes.c_void_p(0)
+        rc = lib.rgcn_graph_create_device(_ptr(tri), tri.shape[0], int(n_entities), int(n_relations),
+                                          _NORM[norm_mode], _ptr(norm_f), _ptr(norm_b), dev, _stream(tri.device),
+                                          ctypes.byref(h))
+        _lib.check(rc, "rgcn_graph_create_device")
+        return cls(None, 0, 0, device=dev, _handle=h)
+
+    @classmethod
+    def from_device_messages(cls, dst, src, relw, norm, V_dst, V_src, n_relw):
+        """Graph from message arrays resident on the GPU (rgcn_graph_create_messages_device)."""
+        lib = _lib.load()
+        M = dst.numel()
+        cls._dev_i32("dst", dst)
+        cls._dev_i32("src", src, M)
+        cls._dev_i32("relw", relw, M)
+        _check_cuda_f32("norm", norm, (M,))
+        dev = dst.device.index if dst.device.index is not None else torch.cuda.current_device()
+        h = ctypes.c_void_p(0)
+        rc = lib.rgcn_graph_create_messages_device(_ptr(dst), _ptr(src), _ptr(relw), _ptr(norm), M, int(V_dst),
+                                                   int(V_src), int(n_relw), dev, _stream(dst.device),
+                                                   ctypes.byref(h))
+        _lib.check(rc, "rgcn_graph_create_messages_device")
+        return cls(None, 0, 0, device=dev, _handle=h)
+
     def info(self):
         arr = (ctypes.c_int64 * 16)()
         _lib.check(self._lib.rgcn_graph_info(self._h, arr), "rgcn_graph_info")

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <vector>
+#include <algorithm>
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -53,11 +54,11 @@ __global__ void __launch_bounds__(256) k_ldg_red(const float4* __restrict__ T, f
                                                   const int* __restrict__ dst, int n, float4* sink) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nw = (gridDim.x * blockDim.x) >> 5;
-  // contiguous message range per warp (like a work item): the dst window slides with the message index
-  const int per = (n + nw - 1) / nw;
-  const int beg = warp * per, end = min(n, beg + per);
+  // items of 64 consecutive messages dealt round-robin to the warps (like the product's work items): concurrently
+  // running warps sit in the same 16 MB window of the output
   float4 acc = make_float4(0, 0, 0, 0);
-  for (int i = beg; i + U <= end; i += U) {
+  for (int item = warp; item * 64 < n; item += nw)
+  for (int i = item * 64; i + U <= min(n, item * 64 + 64); i += U) {
     float4 v[U][4];
     int dr[U];
 #pragma unroll
@@ -95,27 +96,37 @@ __global__ void __launch_bounds__(256, 1) k_bulk_red(const float4* __restrict__ 
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full[B_SLOTS], empty[B_SLOTS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per = (n + gridDim.x - 1) / gridDim.x;
-  const int beg = blockIdx.x * per, end = min(n, beg + per);
+  // CTA b owns chunks b, b + grid, ... of CH consecutive messages (window locality like the product)
+  constexpr int CH = 224;  // multiple of 32 and of B_CONS
+  const int n_chunks = n / CH;
+  int my_chunks = 0;
+  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) ++my_chunks;
+  const int total = my_chunks * CH;  // messages this CTA handles; message k lives at chunk (k / CH), offset k % CH
+  auto gidx = [&](int k) { return (blockIdx.x + (k / CH) * gridDim.x) * CH + (k % CH); };
   if (threadIdx.x == 0) {
     for (int s = 0; s < B_SLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (warp == B_CONS) {
-    if (lane == 0) {
-      for (int i = beg; i < end; ++i) {
-        const int k = i - beg, s = k % B_SLOTS;
-        if (k >= B_SLOTS) mbar_wait(&empty[s], ((k / B_SLOTS) - 1) & 1);
-        mbar_expect_tx(&full[s], 2048);
-        bulk_g2s(smem_u32(smem + s * 2048), T + (size_t)__ldg(src + i) * 128, 2048, &full[s]);
+    for (int k0 = 0; k0 < total; k0 += 32) {   // CH % 32 == 0: a batch never straddles chunks
+      const int mine = __ldg(src + gidx(k0 + lane));
+      for (int u = 0; u < 32; ++u) {
+        const int k = k0 + u, s = k % B_SLOTS;
+        const int row = __shfl_sync(0xffffffffu, mine, u);
+        if (lane == 0) {
+          if (k >= B_SLOTS) mbar_wait(&empty[s], ((k / B_SLOTS) - 1) & 1);
+          mbar_expect_tx(&full[s], 2048);
+          bulk_g2s(smem_u32(smem + s * 2048), T + (size_t)row * 128, 2048, &full[s]);
+        }
+        __syncwarp();
       }
     }
   } else {
     float4 acc = make_float4(0, 0, 0, 0);
-    for (int i = beg + warp; i < end; i += B_CONS) {
-      const int k = i - beg, s = k % B_SLOTS;
-      const int dr = __ldg(dst + i);
+    for (int k = warp; k < total; k += B_CONS) {
+      const int s = k % B_SLOTS;
+      const int dr = __ldg(dst + gidx(k));
       mbar_wait(&full[s], (k / B_SLOTS) & 1);
       const float4* row = reinterpret_cast<const float4*>(smem + s * 2048);
       float4 v[4];
@@ -145,8 +156,12 @@ __global__ void __launch_bounds__(32 * D_RINGS, 1) k_bulk_bulk(const float4* __r
   __shared__ __align__(8) uint64_t full[D_RINGS][D_SLOTS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nr = gridDim.x * D_RINGS, ring = blockIdx.x * D_RINGS + warp;
-  const int per = (n + nr - 1) / nr;
-  const int beg = ring * per, end = min(n, beg + per);
+  constexpr int CH = 64;
+  const int n_chunks = n / CH;
+  int my_chunks = 0;
+  for (int c = ring; c < n_chunks; c += nr) ++my_chunks;
+  const int cnt = my_chunks * CH;
+  auto gidx = [&](int k) { return (ring + (k / CH) * nr) * CH + (k % CH); };
   uint8_t* my = smem + warp * D_SLOTS * 2048;
   if (lane == 0) {
     for (int s = 0; s < D_SLOTS; ++s) mbar_init(&full[warp][s], 1);
@@ -158,28 +173,40 @@ __global__ void __launch_bounds__(32 * D_RINGS, 1) k_bulk_bulk(const float4* __r
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
   }
-  if (lane != 0) return;
-  const int cnt = end - beg;
-  for (int k = 0; k < cnt + D_AHEAD; ++k) {
-    if (k < cnt) {
-      const int s = k % D_SLOTS;
-      if (RED && k >= D_SLOTS) bulk_wait_read<D_SLOTS - 1 - D_AHEAD>();  // the reduce that last used slot s has read it
-      if (GATHER) {
-        mbar_expect_tx(&full[warp][s], 2048);
-        bulk_g2s(smem_u32(my + s * 2048), T + (size_t)__ldg(src + beg + k) * 128, 2048, &full[warp][s]);
+  // the whole warp walks the stream (indices are loaded 32 at a time and broadcast); lane 0 issues the copies
+  int src_cur = 0, dst_cur = 0, dst_prev = 0;
+  for (int k0 = 0; k0 < cnt + 32; k0 += 32) {
+    dst_prev = dst_cur;
+    if (k0 < cnt) { src_cur = __ldg(src + gidx(k0 + lane)); dst_cur = __ldg(dst + gidx(k0 + lane)); }
+    for (int u = 0; u < 32; ++u) {
+      const int k = k0 + u;
+      const int srow = __shfl_sync(0xffffffffu, src_cur, u);
+      const int j = k - D_AHEAD;  // D_AHEAD < 32: j lies in this batch or the previous one
+      const int drow = (u >= D_AHEAD) ? __shfl_sync(0xffffffffu, dst_cur, (u - D_AHEAD) & 31)
+                                      : __shfl_sync(0xffffffffu, dst_prev, (u + 32 - D_AHEAD) & 31);
+      if (lane == 0) {
+        if (k < cnt) {
+          const int s = k % D_SLOTS;
+          if (RED && k >= D_SLOTS) bulk_wait_read<D_SLOTS - 1 - D_AHEAD>();  // the reduce that last used slot s has read it
+          if (GATHER) {
+            mbar_expect_tx(&full[warp][s], 2048);
+            bulk_g2s(smem_u32(my + s * 2048), T + (size_t)srow * 128, 2048, &full[warp][s]);
+          }
+        }
+        if (j >= 0 && j < cnt) {
+          const int s = j % D_SLOTS;
+          if (GATHER) mbar_wait(&full[warp][s], (j / D_SLOTS) & 1);
+          if (RED) {
+            bulk_red_s2g(O + (size_t)drow * 512, smem_u32(my + s * 2048), 2048);
+            bulk_commit();
+          }
+        }
       }
-    }
-    const int j = k - D_AHEAD;
-    if (j >= 0) {
-      const int s = j % D_SLOTS;
-      if (GATHER) mbar_wait(&full[warp][s], (j / D_SLOTS) & 1);
-      if (RED) {
-        bulk_red_s2g(O + (size_t)__ldg(dst + beg + j) * 512, smem_u32(my + s * 2048), 2048);
-        bulk_commit();
-      }
+      __syncwarp();
     }
   }
-  if (RED) bulk_wait_read<0>();
+  if (RED && lane == 0) bulk_wait_read<0>();
+  __syncwarp();
 }
 
 template <typename F> float timeit(F f, int reps = 5) {
@@ -190,9 +217,12 @@ template <typename F> float timeit(F f, int reps = 5) {
   return best;
 }
 
-int main() {
-  const int n = 4 << 20;              // 4M messages = 8.6 GB gathered + 8.6 GB reduced
-  const size_t rows = 2000000;        // 4 GB table, 4 GB output
+int main(int argc, char** argv) {
+  // usage: microbench2 [n_messages] [rows] [tests: any of A B D]   (small sizes for compute-sanitizer)
+  const int n = argc > 1 ? atoi(argv[1]) : (4 << 20);   // 4M messages = 8.6 GB gathered + 8.6 GB reduced
+  const size_t rows = argc > 2 ? (size_t)atol(argv[2]) : 2000000;  // 4 GB table, 4 GB output
+  const char* tests = argc > 3 ? argv[3] : "ABD";
+  auto want = [&](char c) { for (const char* p = tests; *p; ++p) if (*p == c) return true; return false; };
   std::vector<int> hs(n), hd(n);
   uint64_t x = 88172645463325252ull;
   auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
@@ -208,7 +238,7 @@ int main() {
   CK(cudaMalloc(&O, rows * 2048)); CK(cudaMemset(O, 0, rows * 2048));
   const double gb = n * 2048.0 / 1e9;
   auto rep = [&](const char* name, float ms, double bytes_gb) { printf("%-34s %8.3f ms  %8.1f GB/s (per stream %.1f GB)\n", name, ms, bytes_gb / ms * 1e3, gb); };
-  for (int bps : {2, 4, 8}) {
+  if (want('A')) for (int bps : {2, 4, 8}) {
     char nm[96];
     float ms = timeit([&] { k_ldg_red<4, true, false><<<148 * bps, 256>>>((const float4*)T, O, src, dst, n, sink); });
     snprintf(nm, 96, "G ldg gather only   U=4 bps=%d", bps); rep(nm, ms, gb);
@@ -221,7 +251,7 @@ int main() {
     ms = timeit([&] { k_ldg_red<8, true, true><<<148 * bps, 256>>>((const float4*)T, O, src, dst, n, sink); });
     snprintf(nm, 96, "A ldg + red.v4      U=8 bps=%d", bps); rep(nm, ms, 2 * gb);
   }
-  {
+  if (want('B')) {
     const int smemB = B_SLOTS * 2048;
     CK(cudaFuncSetAttribute(k_bulk_red, cudaFuncAttributeMaxDynamicSharedMemorySize, smemB));
     float ms = timeit([&] { k_bulk_red<<<148, 256, smemB>>>((const float4*)T, O, src, dst, n, 1, sink); });
@@ -231,7 +261,7 @@ int main() {
     ms = timeit([&] { k_bulk_red<<<296, 256, smemB>>>((const float4*)T, O, src, dst, n, 0, sink); });
     rep("B (2 CTAs/SM)", ms, 2 * gb);
   }
-  {
+  if (want('D')) {
     const int smemD = D_RINGS * D_SLOTS * 2048;
     CK(cudaFuncSetAttribute(k_bulk_bulk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemD));
     CK(cudaFuncSetAttribute(k_bulk_bulk<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemD));
