@@ -49,11 +49,27 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 // TMA bulk copy global -> shared (1-D, 16 B granular); completion is signalled on `bar` as transaction bytes
-__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {  // gathered rows stream through L2 once: do not let them
+  uint64_t p;                                               // evict the accumulation window the reductions live in
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+// Ampere-style asynchronous copy, 16 B per lane (LDGSTS): one instruction moves a 512 B row slab; src_bytes = 0
+// zero-fills the destination (lanes past the row end)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes, uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(src_bytes),
+               "l"(policy)
                : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ float4 lds4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -87,14 +103,19 @@ __device__ __forceinline__ float comp(const float4& v, int c) {  // c is a compi
 //      the issue and wait overheads are paid once per 8 messages; group i + NG - 1 is requested when group i starts
 //      to be consumed, i.e. 8 (NG - 2) .. 8 (NG - 1) rows per warp are in flight.
 // TAIL : the last slab is narrower than NV*128 columns (d % (NV*128) != 0): lanes past the row end read zeros
-constexpr int GS = 8;
-template <int S, int NV, bool FUSE_DW, bool TAIL, int NW, int NG>
+// GS : messages per group (8 or 4)
+// MODE : 0 = TMA bulk copies (cp.async.bulk, one per row, issued by the group's lanes through the uniform datapath:
+//            ~10 issue slots per copy), 1 = cp.async (LDGSTS.128: the whole warp copies a row slab with ONE
+//            instruction per 512 B; completion by commit/wait groups).  The fused backward is issue-bound
+//            (profiles/r2_ncu_staged.md: 69 % issue-active), where the cheaper request path of mode 1 pays.
+template <int S, int NV, bool FUSE_DW, bool TAIL, int NW, int NG, int GS, int MODE>
 __global__ void __launch_bounds__(NW * 32, 1)
     k_block_stg(const WorkItem* __restrict__ items, int n_items, int n_slabs, const int32_t* __restrict__ r_row,
                 const int32_t* __restrict__ r_nbr, const float* __restrict__ r_norm, const float* __restrict__ X, int ldx,
                 int d, const float* __restrict__ Wt, float* __restrict__ out, const float* __restrict__ Hrow, int ldh,
                 float* __restrict__ dWt) {
   static_assert(S == 4 || S == 8 || S == 16, "block size");
+  static_assert(GS == 4 || GS == 8, "group size");
   static_assert(NG >= 2 && (NG - 1) * GS <= 32, "the fetch cursor must stay within the next index batch");
   constexpr int G = S / 4;                      // lanes per block
   constexpr int SLAB_B = NV * 512;              // bytes of one row slab
@@ -111,6 +132,7 @@ __global__ void __launch_bounds__(NW * 32, 1)
   }
   __syncwarp();
 
+  const uint64_t pol = policy_evict_first();
   const int rel = lane & (G - 1);  // position of this lane's quad inside its block
   uint32_t gcnt = 0;               // groups requested so far by this warp (buffer = gcnt % NG, phase = gcnt / NG)
   uint32_t ccnt = 0;               // groups consumed so far
@@ -158,33 +180,64 @@ __global__ void __launch_bounds__(NW * 32, 1)
     uint32_t cur_start = start_bits(cur_row, -1);
     uint32_t nxt_start = start_bits(nxt_row, __shfl_sync(FULL, cur_row, 31));
 
-    // request group gi (0 <= gi < ng, warp-uniform): lane g < cnt issues the copy of message gi*8 + g
+    // request group gi (0 <= gi < ng, warp-uniform)
     auto request = [&](int gi) {
       const int q_rel = gi * GS - b0;           // first message of the group relative to the current batch: 0 .. 56
-      const bool in_cur = q_rel < 32;           // a group never straddles batches (8 | 32)
-      const int sl = (q_rel + (lane & (GS - 1))) & 31;
-      const int src = __shfl_sync(FULL, in_cur ? cur_nbr : nxt_nbr, sl);
+      const bool in_cur = q_rel < 32;           // a group never straddles batches (GS | 32)
       const int cnt = min(GS, n - gi * GS);
       const uint32_t buf = gcnt % NG;
-      uint32_t tx = (uint32_t)cnt * vb;
-      int hrow = 0;
-      bool st = false;
-      if (FUSE_DW) {
-        hrow = __shfl_sync(FULL, in_cur ? cur_row : nxt_row, sl);
-        const uint32_t sb = ((in_cur ? cur_start : nxt_start) >> (q_rel & 31)) & ((1u << cnt) - 1u);
-        st = (sb >> (lane & (GS - 1))) & 1u;
-        tx += (uint32_t)__popc(sb) * vb;
-      }
-      if (lane == 0) mbar_expect_tx_a(full_a + buf * 8, tx);
-      __syncwarp();
-      if (lane < cnt) {
-        const uint32_t off = (buf * GS + lane) * SLAB_B;
-        bulk_g2s_a(gring_a + off, Xc + (size_t)(uint32_t)src * (uint32_t)ldx, vb, full_a + buf * 8);
-        if (FUSE_DW && st) bulk_g2s_a(hring_a + off, Hc + (size_t)(uint32_t)hrow * (uint32_t)ldh, vb, full_a + buf * 8);
+      const uint32_t sb = ((in_cur ? cur_start : nxt_start) >> (q_rel & 31)) & ((1u << cnt) - 1u);  // run starts
+      if (MODE == 0) {  // TMA: lane g < cnt issues the bulk copy of message gi*GS + g; all land on one mbarrier
+        const int sl = (q_rel + (lane & (GS - 1))) & 31;
+        const int src = __shfl_sync(FULL, in_cur ? cur_nbr : nxt_nbr, sl);
+        uint32_t tx = (uint32_t)cnt * vb;
+        int hrow = 0;
+        bool st = false;
+        if (FUSE_DW) {
+          hrow = __shfl_sync(FULL, in_cur ? cur_row : nxt_row, sl);
+          st = (sb >> (lane & (GS - 1))) & 1u;
+          tx += (uint32_t)__popc(sb) * vb;
+        }
+        if (lane == 0) mbar_expect_tx_a(full_a + buf * 8, tx);
+        __syncwarp();
+        if (lane < cnt) {
+          const uint32_t off = (buf * GS + lane) * SLAB_B;
+          bulk_g2s_a(gring_a + off, Xc + (size_t)(uint32_t)src * (uint32_t)ldx, vb, full_a + buf * 8, pol);
+          if (FUSE_DW && st)
+            bulk_g2s_a(hring_a + off, Hc + (size_t)(uint32_t)hrow * (uint32_t)ldh, vb, full_a + buf * 8, pol);
+        }
+      } else {          // cp.async: every lane copies its own quads of every row of the group
+        const int nbr_sel = in_cur ? cur_nbr : nxt_nbr;
+        const int row_sel = in_cur ? cur_row : nxt_row;
+#pragma unroll
+        for (int j = 0; j < GS; ++j) {
+          if (j < cnt) {
+            const int src = __shfl_sync(FULL, nbr_sel, (q_rel + j) & 31);
+            const float* xr = X + (size_t)(uint32_t)src * (uint32_t)ldx;
+            const uint32_t off = (buf * GS + j) * SLAB_B + lane * 16;
+#pragma unroll
+            for (int k = 0; k < NV; ++k)
+              cp_async16(gring_a + off + k * 512, xr + (ok[k] ? col[k] : c0), ok[k] ? 16u : 0u, pol);
+            if (FUSE_DW && ((sb >> j) & 1u)) {
+              const int hrow = __shfl_sync(FULL, row_sel, (q_rel + j) & 31);
+              const float* hr = Hrow + (size_t)(uint32_t)hrow * (uint32_t)ldh;
+#pragma unroll
+              for (int k = 0; k < NV; ++k)
+                cp_async16(hring_a + off + k * 512, hr + (ok[k] ? col[k] : c0), ok[k] ? 16u : 0u, pol);
+            }
+          }
+        }
+        cp_async_commit();
       }
       ++gcnt;
     };
-    for (int gi = 0; gi < min(NG - 1, ng); ++gi) request(gi);
+    // prologue: NG - 1 groups in flight (mode 1 keeps the commit-group count uniform with empty groups)
+    for (int gi = 0; gi < NG - 1; ++gi) {
+      if (gi < ng)
+        request(gi);
+      else if (MODE == 1)
+        cp_async_commit();
+    }
 
     // ---- weights of this (weight id, slab) -> registers, pre-arranged by exchange distance r = lane ^ source lane
     float4 wsel[G][4][NV];
@@ -237,9 +290,18 @@ __global__ void __launch_bounds__(NW * 32, 1)
     make_ends();
 
     for (int gi = 0; gi < ng; ++gi) {
-      if (gi + NG - 1 < ng) request(gi + NG - 1);  // its buffer held group gi - 1, fully consumed
+      __syncwarp();                                // every lane is done reading the buffer of group gi - 1 ...
+      if (gi + NG - 1 < ng)
+        request(gi + NG - 1);                      // ... which the group requested now reuses
+      else if (MODE == 1)
+        cp_async_commit();
       const uint32_t buf = ccnt % NG;
-      mbar_wait_a(full_a + buf * 8, (ccnt / NG) & 1u);
+      if (MODE == 0) {
+        mbar_wait_a(full_a + buf * 8, (ccnt / NG) & 1u);
+      } else {
+        cp_async_wait<NG - 1>();                   // this lane's copies of group gi have landed ...
+        __syncwarp();                              // ... and so have everyone else's
+      }
       ++ccnt;
       const uint32_t gbase = gring_a + buf * GS * SLAB_B + lane * 16;
       const uint32_t hbase = hring_a + buf * GS * SLAB_B + lane * 16;
@@ -253,7 +315,7 @@ __global__ void __launch_bounds__(NW * 32, 1)
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
           x[k] = lds4(gbase + t * SLAB_B + k * 512);
-          if (TAIL && !ok[k]) x[k] = zero4();  // bytes past the row end were not copied
+          if (MODE == 0 && TAIL && !ok[k]) x[k] = zero4();  // TMA copies stop at the row end (cp.async zero-fills)
         }
         if (st) {
 #pragma unroll
@@ -262,7 +324,7 @@ __global__ void __launch_bounds__(NW * 32, 1)
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
               hq[k] = lds4(hbase + t * SLAB_B + k * 512);
-              if (TAIL && !ok[k]) hq[k] = zero4();
+              if (MODE == 0 && TAIL && !ok[k]) hq[k] = zero4();
             }
           }
         } else {
@@ -302,14 +364,14 @@ __global__ void __launch_bounds__(NW * 32, 1)
   }
 }
 
-template <int S, int NV, bool FUSE, bool TAIL, int NW, int NG>
+template <int S, int NV, bool FUSE, bool TAIL, int NW, int NG, int GS, int MODE>
 int launch_stg_t(const WorkItem* items, int n_items, const int32_t* r_row, const int32_t* r_nbr, const float* r_norm,
                  const float* X, int ldx, int d, const float* Wt, float* out, const float* Hrow, int ldh, float* dWt,
                  cudaStream_t st) {
   constexpr int SLAB_B = NV * 512;
   constexpr int smem = NW * NG * GS * SLAB_B * (FUSE ? 2 : 1) + NW * NG * 8;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  auto kern = k_block_stg<S, NV, FUSE, TAIL, NW, NG>;
+  auto kern = k_block_stg<S, NV, FUSE, TAIL, NW, NG, GS, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     int rc = rgcn_check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
@@ -343,36 +405,41 @@ int launch_block_stg(const WorkItem* items, int n_items, const int32_t* r_row, c
   }
   const bool fuse = dWt != nullptr;
 #define ARGS items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt, st
-#define STG(S_, NV_, FUSE_, NW_, NG_)                                                    \
-  do {                                                                                   \
-    if (d % ((NV_)*128) != 0) return launch_stg_t<S_, NV_, FUSE_, true, NW_, NG_>(ARGS); \
-    return launch_stg_t<S_, NV_, FUSE_, false, NW_, NG_>(ARGS);                          \
+#define STG(S_, NV_, FUSE_, NW_, NG_, GS_, MODE_)                                                  \
+  do {                                                                                             \
+    if (d % ((NV_)*128) != 0) return launch_stg_t<S_, NV_, FUSE_, true, NW_, NG_, GS_, MODE_>(ARGS); \
+    return launch_stg_t<S_, NV_, FUSE_, false, NW_, NG_, GS_, MODE_>(ARGS);                         \
   } while (0)
-  // Configurations (one persistent CTA per SM; registers from -Xptxas -v, ptxas budgets them for the block rounded
-  // up to 4 warps; shared memory = warps x groups x 8 rows x slab bytes, twice that for the fused backward):
-  //   forward        : 2 quads per lane (1 KB slabs), 12 warps x 2 groups = 192 KB   (RGCN_STG_FWD=1: 14 warps;
-  //                    =2: 1 quad per lane, 16 warps x 3 groups)
-  //   fused backward : weights + gradient accumulators in registers (1 quad per lane: ~147), 12 warps x 2 groups x
-  //                    (gathered-row ring + input-row ring) = 192 KB;  s = 16: 8 warps (230 registers)
-  int fwd_cfg = 0;
+  // Configurations (one persistent CTA per SM; registers from -Xptxas -v, budgeted by ptxas for the block rounded up
+  // to 4 warps; shared memory = warps x groups x GS rows x slab bytes, twice that for the fused backward).
+  // RGCN_STG_FWD / RGCN_STG_BWD pick among the measured variants of the s = 8 kernels (A/B knobs):
+  //   forward  0: 2 quads/lane, 12 warps x 2 groups of 8, TMA     2: 1 quad/lane, 16 warps x 3 groups, TMA
+  //            3: as 2 with cp.async                              4: as 0 with cp.async
+  //   backward 0: 1 quad/lane, 12 warps x 2 groups of 8, TMA      1: as 0 with cp.async
+  //            2: 2 quads/lane, 8 warps x 2 groups of 4, cp.async 3: as 2 with TMA
+  int fwd_cfg = -1, bwd_cfg = -1;
   if (const char* e = std::getenv("RGCN_STG_FWD")) fwd_cfg = std::atoi(e);
+  if (const char* e = std::getenv("RGCN_STG_BWD")) bwd_cfg = std::atoi(e);
   if (s == 4) {
     if (!fuse) {
-      if (d <= 128 || fwd_cfg == 2) STG(4, 1, false, 16, 3);
-      if (fwd_cfg == 1) STG(4, 2, false, 14, 2);
-      STG(4, 2, false, 12, 2);
+      if (d <= 128) STG(4, 1, false, 16, 3, 8, 1);
+      STG(4, 2, false, 12, 2, 8, 1);
     }
-    STG(4, 1, true, 12, 2);
+    STG(4, 1, true, 12, 2, 8, 1);
   } else if (s == 8) {
     if (!fuse) {
-      if (d <= 128 || fwd_cfg == 2) STG(8, 1, false, 16, 3);
-      if (fwd_cfg == 1) STG(8, 2, false, 14, 2);
-      STG(8, 2, false, 12, 2);
+      if (d <= 128 || fwd_cfg == 2) STG(8, 1, false, 16, 3, 8, 0);
+      if (fwd_cfg == 0) STG(8, 2, false, 12, 2, 8, 0);
+      if (fwd_cfg == 4) STG(8, 2, false, 12, 2, 8, 1);
+      STG(8, 1, false, 16, 3, 8, 1);
     }
-    STG(8, 1, true, 12, 2);
+    if (d > 128 && bwd_cfg == 2) STG(8, 2, true, 8, 2, 4, 1);
+    if (d > 128 && bwd_cfg == 3) STG(8, 2, true, 8, 2, 4, 0);
+    if (bwd_cfg == 0) STG(8, 1, true, 12, 2, 8, 0);
+    STG(8, 1, true, 12, 2, 8, 1);
   } else {
-    if (!fuse) STG(16, 1, false, 16, 3);
-    STG(16, 1, true, 8, 2);
+    if (!fuse) STG(16, 1, false, 16, 3, 8, 1);
+    STG(16, 1, true, 8, 2, 8, 1);
   }
 #undef ARGS
 #undef STG

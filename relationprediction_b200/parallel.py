@@ -81,6 +81,77 @@ class ShardPlan(object):
         self.send_rows = (pairs[:, 1] - lo).astype(np.int64)  # grouped by peer, ascending id inside
 
 
+class ShardPlanDevice(object):
+    """The same partition computed with torch ops ON THE DEVICE that holds the edge list (a CUDA tensor of triples):
+    no per-rank pass of numpy over the global 2E-message list, so a 100 M-edge graph is planned in well under a
+    second per rank and never visits the host.  Attributes mirror ShardPlan; the per-message / per-row arrays are
+    device tensors (int32 / float32 / int64 for send_rows), the per-peer counts small host arrays.  Element for
+    element identical to ShardPlan (tests/test_gpu_parallel.py compares them)."""
+
+    def __init__(self, triples, n_nodes, n_relations, rank, world, norm_mode="canonical", norm_f=None, norm_b=None,
+                 keep_global_ids=False):
+        t = triples
+        if not (isinstance(t, torch.Tensor) and t.dtype == torch.int32 and t.dim() == 2 and t.shape[1] == 3):
+            raise ValueError("ShardPlanDevice: triples must be an int32 [E,3] tensor")
+        dev = t.device
+        self.rank, self.world = rank, world
+        self.n_nodes, self.n_relations = n_nodes, n_relations
+        self.bounds = node_bounds(n_nodes, world)
+        lo, hi = self.bounds[rank], self.bounds[rank + 1]
+        self.lo, self.hi, self.n_local = lo, hi, hi - lo
+        E = t.shape[0]
+        s, r, o = t[:, 0], t[:, 1], t[:, 2]
+        if norm_mode == "canonical":
+            cf = torch.bincount(o.long(), minlength=n_nodes).to(torch.float32)
+            cb = torch.bincount(s.long(), minlength=n_nodes).to(torch.float32)
+            one = torch.ones((), dtype=torch.float32, device=dev)
+            inv_f, inv_b = one / cf, one / cb      # fp32 division, as in ShardPlan / rgcn_graph_create
+        inner = torch.as_tensor(self.bounds[1:], dtype=torch.int32, device=dev)
+
+        def owner(nodes):
+            return torch.bucketize(nodes, inner, out_int32=True, right=True)
+
+        parts = {k: [] for k in ("dst", "src", "relw", "norm", "gid")}
+        need_keys = []
+        # forward messages (dst = o, src = s, weight id r), then backward (dst = s, src = o, weight id r + R):
+        # the global message order of ShardPlan, handled per direction to keep the temporaries at E elements
+        for direction, (dn, sn) in enumerate(((o, s), (s, o))):
+            od, os_ = owner(dn), owner(sn)
+            mine = (od == rank).nonzero(as_tuple=True)[0]
+            parts["dst"].append((dn[mine] - lo).to(torch.int32))
+            parts["src"].append(sn[mine])
+            parts["relw"].append((r[mine] + direction * n_relations).to(torch.int32))
+            if norm_mode == "canonical":
+                parts["norm"].append((inv_f if direction == 0 else inv_b)[dn[mine].long()])
+            elif norm_mode == "explicit":
+                parts["norm"].append((norm_f if direction == 0 else norm_b)[mine].to(torch.float32))
+            else:
+                parts["norm"].append(torch.ones(mine.shape[0], dtype=torch.float32, device=dev))
+            if keep_global_ids:
+                parts["gid"].append(mine + direction * E)
+            need = ((os_ == rank) & (od != rank)).nonzero(as_tuple=True)[0]
+            need_keys.append(od[need].long() * n_nodes + sn[need].long())
+            del od, os_, mine, need
+        self.msg_dst = torch.cat(parts["dst"])
+        src_g = torch.cat(parts["src"])
+        self.msg_relw = torch.cat(parts["relw"])
+        self.msg_norm = torch.cat(parts["norm"])
+        self.msg_global_id = torch.cat(parts["gid"]) if keep_global_ids else None
+        del parts
+        remote = (src_g < lo) | (src_g >= hi)
+        self.halo_nodes = torch.unique(src_g[remote])          # ascending global id, hence grouped by owner
+        self.n_halo = int(self.halo_nodes.shape[0])
+        pos = torch.searchsorted(self.halo_nodes, src_g, out_int32=True) if self.n_halo else torch.zeros_like(src_g)
+        self.msg_src = torch.where(remote, pos + self.n_local, src_g - lo).to(torch.int32)
+        del src_g, remote, pos
+        self.recv_counts = torch.bincount(owner(self.halo_nodes).long(), minlength=world).cpu().numpy().astype(np.int64)
+        keys = torch.unique(torch.cat(need_keys))               # (peer, source) pairs, sorted by peer then id
+        del need_keys
+        self.send_counts = torch.bincount(torch.div(keys, n_nodes, rounding_mode="floor"),
+                                          minlength=world).cpu().numpy().astype(np.int64)
+        self.send_rows = (keys % n_nodes) - lo                  # int64, grouped by peer, ascending id inside
+
+
 class _HaloExchange(torch.autograd.Function):
     """H_local [n_local,d] -> H_ext [n_local+n_halo,d]; backward returns halo gradients to their owners."""
 
@@ -282,16 +353,28 @@ class _PipelinedBlockLayer(torch.autograd.Function):
 class ShardedGraph(object):
     def __init__(self, triples, n_nodes, n_relations, rank, world, device, norm_mode="canonical",
                  norm_f=None, norm_b=None, group=None, overlap=True, pipelined=None):
-        self.plan = ShardPlan(triples, n_nodes, n_relations, rank, world, norm_mode, norm_f, norm_b)
         self.device = torch.device(device)
+        on_device = isinstance(triples, torch.Tensor) and triples.is_cuda
+        if on_device:   # edge list already on the GPU: plan + graph preparation never leave it
+            self.plan = ShardPlanDevice(triples, n_nodes, n_relations, rank, world, norm_mode, norm_f, norm_b)
+        else:
+            self.plan = ShardPlan(triples, n_nodes, n_relations, rank, world, norm_mode, norm_f, norm_b)
         self.group = group
         p = self.plan
         self.n_local, self.n_halo = p.n_local, p.n_halo
         index = None
         if self.device.type == "cuda":
             index = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        self.graph = ops.Graph.from_messages(p.msg_dst, p.msg_src, p.msg_relw, p.msg_norm, p.n_local,
-                                             p.n_local + p.n_halo, 2 * n_relations, device=index)
+
+        def make_graph(dst, src, relw, norm, v_dst, v_src):
+            if on_device:
+                return ops.Graph.from_device_messages(dst.contiguous(), src.contiguous(), relw.contiguous(),
+                                                      norm.contiguous(), v_dst, v_src, 2 * n_relations)
+            return ops.Graph.from_messages(dst, src, relw, norm, v_dst, v_src, 2 * n_relations, device=index)
+
+        self.graph = None
+        if not (overlap and world > 1) or not on_device:   # the un-split graph (basis layers, non-overlapped path)
+            self.graph = make_graph(p.msg_dst, p.msg_src, p.msg_relw, p.msg_norm, p.n_local, p.n_local + p.n_halo)
         self.send_rows = torch.as_tensor(p.send_rows, device=self.device)
         self.send_off = np.concatenate([[0], np.cumsum(p.send_counts)]).astype(np.int64).tolist()
         self.halo_off = np.concatenate([[0], np.cumsum(p.recv_counts)]).astype(np.int64).tolist()
@@ -303,13 +386,11 @@ class ShardedGraph(object):
         self.pipelined = self.overlap and bool(pipelined)
         if self.overlap:
             loc = p.msg_src < p.n_local
-            self.graph_local = ops.Graph.from_messages(p.msg_dst[loc], p.msg_src[loc], p.msg_relw[loc],
-                                                       p.msg_norm[loc], p.n_local, p.n_local,
-                                                       2 * n_relations, device=index)
+            self.graph_local = make_graph(p.msg_dst[loc], p.msg_src[loc], p.msg_relw[loc], p.msg_norm[loc],
+                                          p.n_local, p.n_local)
             rem = ~loc
-            self.graph_halo = ops.Graph.from_messages(p.msg_dst[rem], p.msg_src[rem] - p.n_local, p.msg_relw[rem],
-                                                      p.msg_norm[rem], p.n_local, max(p.n_halo, 0),
-                                                      2 * n_relations, device=index)
+            self.graph_halo = make_graph(p.msg_dst[rem], p.msg_src[rem] - p.n_local, p.msg_relw[rem],
+                                         p.msg_norm[rem], p.n_local, max(p.n_halo, 0))
             self.graph_halo_peer = {}
             if self.pipelined:
                 hsrc = p.msg_src - p.n_local  # halo-row index of every remote-source message
@@ -318,9 +399,10 @@ class ShardedGraph(object):
                     if q == rank or hi_q == lo_q:
                         continue
                     sel = rem & (hsrc >= lo_q) & (hsrc < hi_q)
-                    self.graph_halo_peer[q] = ops.Graph.from_messages(
-                        p.msg_dst[sel], hsrc[sel] - lo_q, p.msg_relw[sel], p.msg_norm[sel], p.n_local,
-                        hi_q - lo_q, 2 * n_relations, device=index)
+                    self.graph_halo_peer[q] = make_graph(p.msg_dst[sel], hsrc[sel] - lo_q, p.msg_relw[sel],
+                                                         p.msg_norm[sel], p.n_local, hi_q - lo_q)
+            if on_device:   # the plan's per-message arrays are no longer needed: free the device memory
+                p.msg_dst = p.msg_src = p.msg_relw = p.msg_norm = None
 
     def halo_exchange(self, H_local):
         return _HaloExchange.apply(H_local, self.plan, self.send_rows, self.group)
@@ -338,6 +420,9 @@ class ShardedGraph(object):
 
     def basis_layer(self, H_local, W_forward, W_backward, C_forward, C_backward, W_self, drop_mask=None,
                     keep=1.0, relu=True):
+        if self.graph is None:
+            raise ValueError("this ShardedGraph was planned on the device for the overlapped block path only "
+                             "(pass overlap=False to also build the un-split graph the basis layer walks)")
         return ops.basis_layer(self.halo_exchange(H_local), W_forward, W_backward, C_forward, C_backward,
                                W_self, self.graph, drop_mask, keep, relu)
 

@@ -14,8 +14,18 @@ from test_gpu_parity import assert_close, cu, run_block
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True)
-def staged_algo():
+# (RGCN_STG_FWD, RGCN_STG_BWD): default = cp.async staging; the others select the TMA-bulk-copy and the
+# two-quads-per-lane variants of the s = 8 kernels (csrc/block_staged.cu launch_block_stg)
+VARIANTS = [("", ""), ("2", "0"), ("0", "3"), ("4", "2")]
+
+
+@pytest.fixture(autouse=True, params=VARIANTS, ids=["default", "tma-nv1", "tma-nv2", "cpasync-nv2"])
+def staged_algo(request, monkeypatch):
+    fwd, bwd = request.param
+    if fwd:
+        monkeypatch.setenv("RGCN_STG_FWD", fwd)
+    if bwd:
+        monkeypatch.setenv("RGCN_STG_BWD", bwd)
     _lib.set_option("block_algo", 3)
     yield
     _lib.set_option("block_algo", -1)

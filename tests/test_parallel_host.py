@@ -266,3 +266,25 @@ def test_block_bounds_keep_rows_float4_aligned():
         parallel.block_bounds(10, 5, 2)      # 10 blocks of 5 cannot be dealt in groups of 4 blocks
     with pytest.raises(ValueError):
         parallel.block_bounds(4, 8, 8)       # fewer column groups than ranks
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_device_plan_equals_host_plan(world):
+    """ShardPlanDevice (torch ops; runs on whatever device holds the edge list -- here CPU tensors) reproduces the
+    numpy ShardPlan element for element, explicit norms included."""
+    V, R, E = 900, 6, 7000
+    tr = synthetic_kg(V, R, E, seed=9, skewed=True)
+    rng = np.random.RandomState(1)
+    nf, nb = rng.uniform(0.1, 1, E).astype(np.float32), rng.uniform(0.1, 1, E).astype(np.float32)
+    t = torch.from_numpy(tr)
+    for mode, kw_h, kw_d in (("canonical", {}, {}),
+                             ("explicit", dict(norm_f=nf, norm_b=nb), dict(norm_f=torch.from_numpy(nf), norm_b=torch.from_numpy(nb))),
+                             ("none", {}, {})):
+        for rank in range(world):
+            h = parallel.ShardPlan(tr, V, R, rank, world, norm_mode=mode, **kw_h)
+            dv = parallel.ShardPlanDevice(t, V, R, rank, world, norm_mode=mode, keep_global_ids=True, **kw_d)
+            assert (dv.lo, dv.hi, dv.n_local, dv.n_halo) == (h.lo, h.hi, h.n_local, h.n_halo)
+            for name in ("msg_dst", "msg_src", "msg_relw", "msg_norm", "msg_global_id", "halo_nodes", "send_rows"):
+                np.testing.assert_array_equal(getattr(dv, name).numpy(), getattr(h, name), err_msg=name)
+            np.testing.assert_array_equal(dv.recv_counts, h.recv_counts)
+            np.testing.assert_array_equal(dv.send_counts, h.send_counts)
