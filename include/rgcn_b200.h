@@ -282,6 +282,44 @@ int distmult_backward(const float* codes, const float* rel, int32_t V, int32_t V
                       float g_loss, float g_reg, const float* g_scale_dev, const float* g_energy,
                       float* dcodes, float* drel, void* stream);
 
+/* Same as distmult_backward, additionally accumulating (+=) into the device float rel_slice_sumsq (may be NULL) the
+ * sum over triples of |gradient slice of the gathered relation row|^2 -- the contribution of the relation table to
+ * tf.clip_by_global_norm, which sees that gradient as un-aggregated IndexedSlices (bilinear_diag.py:18,
+ * optimization/tensorflow_backend/algorithms.py:65-68). */
+int distmult_backward_slices(const float* codes, const float* rel, int32_t V, int32_t Vrel, int32_t d,
+                             const int32_t* X, int64_t N, const float* Y, const float* energies, float g_loss,
+                             float g_reg, const float* g_scale_dev, const float* g_energy, float* dcodes,
+                             float* drel, float* rel_slice_sumsq, void* stream);
+
+/* IndexedSlices norm of the block tables' gradients: sumsq2[0] (W_forward) and sumsq2[1] (W_backward), overwritten,
+ * receive  sum_messages norm_m^2 * sum_b |G[dst_m]_b|^2 |H[src_m]_b|^2  -- the squared norm of the per-edge gradient
+ * slices tf.gradients hands to tf.clip_by_global_norm for variables read through tf.nn.embedding_lookup
+ * (gcn_basis_concat.py:38-39).  H [V_src,d] layer input, G [V_dst,d] = dOut * relu'(out). */
+int64_t rgcn_block_slice_sumsq_workspace_bytes(const rgcn_graph_t* g, int32_t d, int32_t B);
+int rgcn_block_slice_sumsq(const rgcn_graph_t* g, int32_t d, int32_t B, const float* H, const float* G,
+                           float* sumsq2, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DistMult all-entity scoring + ranking, fused (next row N3): decoders/bilinear_diag.py:51-61
+ * (predict_all_subject_scores / predict_all_object_scores) feeding the rank counts of
+ * common/evaluation.py:148-159 and :355-367.  For every triple t of X and the corrupted side,
+ *   score(t, v)      = sigmoid( sum_k q[t,k] * codes[v,k] ),  q = rel[r]*codes[o] (side 0: subjects) or
+ *                      codes[s]*rel[r] (side 1: objects)
+ *   raw_rank[t]      = #{ v : score(t, v) >= score(t, gold_t) }               (the gold entity counts itself)
+ *   filtered_rank[t] = raw_rank[t] - #{ v in known(t) : score(t, v) >= score(t, gold_t) } + 1
+ * The [n, V] score matrix the reference materialises per 1000-triple chunk is never written: the energies come
+ * out of the tcgen05 3xTF32 GEMM tile by tile and are compared in its epilogue.
+ * known_mask : uint32 [n, ceil(V/32)] device, bit v of row t = v is a known true answer of t (the reference's
+ *              known sets contain the evaluated triple itself, train.py:103-105), or NULL (then filtered_rank
+ *              must be NULL).  raw_rank / filtered_rank : int32 [n] device.
+ * workspace  : distmult_rank_workspace_bytes(V, d, n); its head holds the hi/lo split of `codes`:
+ *              reuse_split != 0 skips re-splitting when the same workspace is passed again with unchanged codes.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t distmult_rank_workspace_bytes(int32_t V, int32_t d, int64_t n);
+int distmult_rank(const float* codes, const float* rel, int32_t V, int32_t Vrel, int32_t d, const int32_t* X,
+                  int64_t n, int side, const uint32_t* known_mask, int reuse_split, int32_t* raw_rank,
+                  int32_t* filtered_rank, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

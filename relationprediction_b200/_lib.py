@@ -20,7 +20,8 @@ EXPORTED_SYMBOLS = [
     "rgcn_block_workspace_bytes", "rgcn_block_forward", "rgcn_block_backward",
     "rgcn_block_aggregate_workspace_bytes", "rgcn_block_aggregate", "rgcn_block_aggregate_backward",
     "rgcn_basis_workspace_bytes", "rgcn_basis_forward", "rgcn_basis_backward",
-    "distmult_forward", "distmult_backward",
+    "distmult_forward", "distmult_backward", "distmult_rank_workspace_bytes", "distmult_rank",
+    "distmult_backward_slices", "rgcn_block_slice_sumsq_workspace_bytes", "rgcn_block_slice_sumsq",
 ]
 
 RGCN_NORM_CANONICAL, RGCN_NORM_EXPLICIT, RGCN_NORM_NONE = 0, 1, 2
@@ -111,6 +112,17 @@ def _declare(lib):
                                         c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, c_int64, vp]
     lib.distmult_forward.restype = c_int
     lib.distmult_forward.argtypes = [vp, vp, c_int32, c_int32, c_int32, vp, c_int64, vp, vp, vp, vp]
+    lib.distmult_backward_slices.restype = c_int
+    lib.distmult_backward_slices.argtypes = [vp, vp, c_int32, c_int32, c_int32, vp, c_int64, vp, vp,
+                                             c_float, c_float, vp, vp, vp, vp, vp, vp]
+    lib.rgcn_block_slice_sumsq_workspace_bytes.restype = c_int64
+    lib.rgcn_block_slice_sumsq_workspace_bytes.argtypes = [vp, c_int32, c_int32]
+    lib.rgcn_block_slice_sumsq.restype = c_int
+    lib.rgcn_block_slice_sumsq.argtypes = [vp, c_int32, c_int32, vp, vp, vp, vp, c_int64, vp]
+    lib.distmult_rank_workspace_bytes.restype = c_int64
+    lib.distmult_rank_workspace_bytes.argtypes = [c_int32, c_int32, c_int64]
+    lib.distmult_rank.restype = c_int
+    lib.distmult_rank.argtypes = [vp, vp, c_int32, c_int32, c_int32, vp, c_int64, c_int, vp, c_int, vp, vp, vp, c_int64, vp]
     lib.distmult_backward.restype = c_int
     lib.distmult_backward.argtypes = [vp, vp, c_int32, c_int32, c_int32, vp, c_int64, vp, vp,
                                       c_float, c_float, vp, vp, vp, vp, vp]

@@ -79,6 +79,20 @@ class Scorer(object):
     def compute_mrr_scores(self, triples, verbose=False):
         triples = np.asarray(triples).reshape(-1, 3)
         score = MrrScore()
+        # GPU models rank inside the scoring GEMM (distmult_rank): same counting rules, no [chunk, V] matrices, one
+        # encoder pass.  The interleaving of the reference (subjects then objects per triple chunk) only orders the
+        # rank lists; every summary statistic is a mean over them.
+        fused = getattr(self.model, 'rank_all_entities', None)
+        if fused is not None and getattr(self.model, 'supports_fused_ranking', lambda: False)():
+            tl = triples.tolist()
+            ks = [self.known_subject_triples.get((t[2], t[1]), []) for t in tl]
+            ko = [self.known_object_triples.get((t[0], t[1]), []) for t in tl]
+            res = fused(triples, ks, ko)
+            if res is not None:
+                raw_s, filt_s, raw_o, filt_o = res
+                score.raw_ranks.extend(raw_s.tolist() + raw_o.tolist())
+                score.filtered_ranks.extend(filt_s.tolist() + filt_o.tolist())
+                return score
         chunk = 1000
         for c in range(math.ceil(len(triples) / chunk)):
             part = triples[c * chunk:(c + 1) * chunk]

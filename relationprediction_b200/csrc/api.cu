@@ -855,5 +855,105 @@ extern "C" int distmult_backward(const float* codes, const float* rel, int32_t V
     return RGCN_ERR_INVALID;
   }
   return launch_distmult_backward(codes, rel, d, X, N, Y, energies, g_loss, g_reg, g_scale_dev,
-                                  g_energy, dcodes, drel, (cudaStream_t)stream);
+                                  g_energy, dcodes, drel, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int distmult_backward_slices(const float* codes, const float* rel, int32_t V, int32_t Vrel, int32_t d,
+                                        const int32_t* X, int64_t N, const float* Y, const float* energies,
+                                        float g_loss, float g_reg, const float* g_scale_dev, const float* g_energy,
+                                        float* dcodes, float* drel, float* rel_slice_sumsq, void* stream) {
+  if (!codes || !rel || (N > 0 && !X) || !dcodes || !drel || d <= 0 || d % 4 != 0 || V <= 0 ||
+      Vrel <= 0 || N < 0 || (Y && !energies)) {
+    rgcn_set_error("distmult_backward_slices: bad arguments");
+    return RGCN_ERR_INVALID;
+  }
+  return launch_distmult_backward(codes, rel, d, X, N, Y, energies, g_loss, g_reg, g_scale_dev,
+                                  g_energy, dcodes, drel, rel_slice_sumsq, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// IndexedSlices norm of the block tables' gradients (see slice_norm.cu)
+// ------------------------------------------------------------------------------------------------
+extern "C" int64_t rgcn_block_slice_sumsq_workspace_bytes(const rgcn_graph_t* g, int32_t d, int32_t B) {
+  if (!g || d <= 0 || B <= 0 || d % B != 0) {
+    rgcn_set_error("rgcn_block_slice_sumsq_workspace_bytes: bad arguments");
+    return RGCN_ERR_INVALID;
+  }
+  return align_up((int64_t)g->V_src * B * 4) + align_up((int64_t)g->V_dst * B * 4) + 256;
+}
+
+extern "C" int rgcn_block_slice_sumsq(const rgcn_graph_t* g, int32_t d, int32_t B, const float* H, const float* G,
+                                      float* sumsq2, void* workspace, int64_t workspace_bytes, void* stream) {
+  int rc = common_checks(g, d, B, "rgcn_block_slice_sumsq");
+  if (rc) return rc;
+  if (d % B != 0 || !H || !G || !sumsq2 || !workspace) {
+    rgcn_set_error("rgcn_block_slice_sumsq: bad arguments");
+    return RGCN_ERR_INVALID;
+  }
+  rc = need_views(g, false, true, "rgcn_block_slice_sumsq");
+  if (rc) return rc;
+  if (workspace_bytes < rgcn_block_slice_sumsq_workspace_bytes(g, d, B)) {
+    rgcn_set_error("rgcn_block_slice_sumsq: workspace too small");
+    return RGCN_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = rgcn_check_cuda(cudaSetDevice(g->device), "cudaSetDevice");
+  if (rc) return rc;
+  Carver ws(workspace, workspace_bytes);
+  float* HB = ws.take<float>((int64_t)g->V_src * B);
+  float* GB = ws.take<float>((int64_t)g->V_dst * B);
+  const int s = d / B;
+  rc = launch_block_sqnorm(H, g->V_src, d, B, s, HB, st);
+  if (!rc) rc = launch_block_sqnorm(G, g->V_dst, d, B, s, GB, st);
+  if (!rc) rc = rgcn_check_cuda(cudaMemsetAsync(sumsq2, 0, 2 * sizeof(float), st), "memset(sumsq2)");
+  if (!rc)
+    rc = launch_block_slice_sumsq(g->by_rel.d_items, (int)g->by_rel.n_items, g->by_rel.d_row, g->by_rel.d_nbr,
+                                  g->by_rel.d_norm, GB, HB, B, g->n_relw / 2, sumsq2, st);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// DistMult all-entity scoring + ranking, fused (next row N3)
+// ------------------------------------------------------------------------------------------------
+extern "C" int64_t distmult_rank_workspace_bytes(int32_t V, int32_t d, int64_t n) {
+  if (V <= 0 || d <= 0 || n < 0) {
+    rgcn_set_error("distmult_rank_workspace_bytes: bad arguments");
+    return RGCN_ERR_INVALID;
+  }
+  return 2 * align_up((int64_t)V * d * 4) + align_up(n * d * 4) + 4 * align_up(n * 4) + 256;
+}
+
+extern "C" int distmult_rank(const float* codes, const float* rel, int32_t V, int32_t Vrel, int32_t d,
+                             const int32_t* X, int64_t n, int side, const uint32_t* known_mask, int reuse_split,
+                             int32_t* raw_rank, int32_t* filtered_rank, void* workspace, int64_t workspace_bytes,
+                             void* stream) {
+  if (!codes || !rel || (n > 0 && (!X || !raw_rank)) || !workspace || V <= 0 || Vrel <= 0 || d <= 0 || d % 4 != 0 ||
+      n < 0 || n > 0x7fffffffLL || (side != 0 && side != 1) || (filtered_rank && !known_mask)) {
+    rgcn_set_error("distmult_rank: bad arguments (need d % 4 == 0, side in {0,1}, a known mask when filtered ranks are requested)");
+    return RGCN_ERR_INVALID;
+  }
+  if (workspace_bytes < distmult_rank_workspace_bytes(V, d, n)) {
+    rgcn_set_error("distmult_rank: workspace too small");
+    return RGCN_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver ws(workspace, workspace_bytes);
+  float* hi = ws.take<float>((int64_t)V * d);
+  float* lo = ws.take<float>((int64_t)V * d);
+  float* Q = ws.take<float>(n * d);
+  float* gold_sig = ws.take<float>(n);
+  int32_t* gold_col = ws.take<int32_t>(n);
+  int32_t* raw_cnt = ws.take<int32_t>(n);
+  int32_t* known_cnt = ws.take<int32_t>(n);
+  int rc = RGCN_OK;
+  if (!reuse_split) rc = launch_gemm_split_b(codes, d, V, d, /*transposed=*/0, hi, lo, st);
+  if (rc || n == 0) return rc;
+  rc = rgcn_check_cuda(cudaMemsetAsync(raw_cnt, 0, (char*)(known_cnt + n) - (char*)raw_cnt, st), "memset(rank counts)");
+  if (rc) return rc;
+  rc = launch_distmult_rank_prepare(codes, rel, d, X, n, side, Q, gold_sig, gold_col, st);
+  if (rc) return rc;
+  rc = launch_gemm_rank_tf32x3(Q, d, hi, lo, d, (int)n, V, d, gold_sig, gold_col, known_mask, (V + 31) / 32, raw_cnt,
+                               known_cnt, st);
+  if (rc) return rc;
+  return launch_distmult_rank_finalize(raw_cnt, known_cnt, n, raw_rank, filtered_rank, st);
 }

@@ -364,6 +364,261 @@ __global__ void __launch_bounds__(NW * 32, 1)
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// TEAM variant: the T = n_slabs warps that own the column slabs of one work item share ONE staged copy of every
+// gathered row.  At the full benchmark size (10 M nodes: H is 20 GB) the per-warp kernel above slowed down 1.9x
+// against its small-graph rate: every 512 B slab request is its own random access into a 20 GB table, i.e. its
+// own address translation, and 4 warps request the 4 slabs of a row at different times.  Here the team's leader
+// warp requests each row ONCE (one 2 KB TMA bulk copy: one translation, one descriptor, a quarter of the request
+// instructions) into a ring all T warps read; a group's buffer returns to the leader through an `empty` mbarrier
+// the T warps arrive on (the classic multi-consumer TMA pipeline: full = transaction barrier, empty = count T).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int S, int NV, bool FUSE_DW, bool TAIL, int T, int NTEAMS, int NG, int GS>
+__global__ void __launch_bounds__(NTEAMS * T * 32, 1)
+    k_block_team(const WorkItem* __restrict__ items, int n_items, const int32_t* __restrict__ r_row,
+                 const int32_t* __restrict__ r_nbr, const float* __restrict__ r_norm, const float* __restrict__ X, int ldx,
+                 int d, const float* __restrict__ Wt, float* __restrict__ out, const float* __restrict__ Hrow, int ldh,
+                 float* __restrict__ dWt) {
+  static_assert(S == 4 || S == 8 || S == 16, "block size");
+  static_assert(GS == 4 || GS == 8, "group size");
+  static_assert(NG >= 2 && (NG - 1) * GS <= 32, "the fetch cursor must stay within the next index batch");
+  constexpr int G = S / 4;                      // lanes per block
+  constexpr int ROW_B = T * NV * 512;           // bytes of one staged row slot (>= d * 4)
+  constexpr int RING_B = NG * GS * ROW_B;
+  constexpr int TEAM_B = RING_B * (FUSE_DW ? 2 : 1);
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int team = warp / T, sw = warp % T;     // sw = this warp's column slab; the sw == 0 warp is the team's leader
+  const uint32_t gring_a = smem_u32(smem) + (uint32_t)team * TEAM_B;
+  const uint32_t hring_a = gring_a + RING_B;
+  const uint32_t full_a = smem_u32(smem) + (uint32_t)NTEAMS * TEAM_B + (uint32_t)team * NG * 16;
+  const uint32_t empty_a = full_a + NG * 8;
+  if (sw == 0 && lane == 0) {
+    for (int s = 0; s < NG; ++s) {
+      mbar_init_a(full_a + s * 8, 1);
+      mbar_init_a(empty_a + s * 8, T);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const uint64_t pol = policy_evict_first();
+  const int rel = lane & (G - 1);
+  const int c0 = sw * (NV * 128);
+  const uint32_t rowb = (uint32_t)d * 4u;       // bytes of one gathered row
+  uint32_t gcnt = 0;                            // groups requested so far by this team (leader's counter)
+  uint32_t ccnt = 0;                            // groups consumed so far by this warp
+
+  bool ok[NV];
+  int col[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    col[k] = c0 + 4 * (lane + 32 * k);
+    ok[k] = col[k] < d;
+  }
+
+  for (int item = blockIdx.x * NTEAMS + team; item < n_items; item += gridDim.x * NTEAMS) {
+    const int4 itv = __ldg(reinterpret_cast<const int4*>(items) + item);
+    const int beg = itv.x, n = itv.y - itv.x, w = itv.z;
+    const int ng = (n + GS - 1) / GS;
+
+    int b0 = 0;
+    int cur_row = 0, cur_nbr = 0, nxt_row = 0, nxt_nbr = 0;
+    float cur_nm = 0.f, nxt_nm = 0.f;
+    if (lane < n) {
+      cur_row = __ldg(r_row + beg + lane);
+      cur_nbr = __ldg(r_nbr + beg + lane);
+      cur_nm = __ldg(r_norm + beg + lane);
+    }
+    if (32 + lane < n) {
+      nxt_row = __ldg(r_row + beg + 32 + lane);
+      nxt_nbr = __ldg(r_nbr + beg + 32 + lane);
+      nxt_nm = __ldg(r_norm + beg + 32 + lane);
+    }
+    auto start_bits = [&](int row_reg, int prev_row_last) {
+      int p = __shfl_up_sync(FULL, row_reg, 1);
+      if (lane == 0) p = prev_row_last;
+      return __ballot_sync(FULL, row_reg != p);
+    };
+    uint32_t cur_start = start_bits(cur_row, -1);
+    uint32_t nxt_start = start_bits(nxt_row, __shfl_sync(FULL, cur_row, 31));
+
+    // leader only: request group gi -- lane g < cnt issues ONE bulk copy of the whole row of message gi*GS + g
+    auto request = [&](int gi) {
+      const int q_rel = gi * GS - b0;
+      const bool in_cur = q_rel < 32;
+      const int cnt = min(GS, n - gi * GS);
+      const uint32_t buf = gcnt % NG;
+      const uint32_t sb = ((in_cur ? cur_start : nxt_start) >> (q_rel & 31)) & ((1u << cnt) - 1u);
+      const int sl = (q_rel + (lane & (GS - 1))) & 31;
+      const int src = __shfl_sync(FULL, in_cur ? cur_nbr : nxt_nbr, sl);
+      uint32_t tx = (uint32_t)cnt * rowb;
+      int hrow = 0;
+      bool st = false;
+      if (FUSE_DW) {
+        hrow = __shfl_sync(FULL, in_cur ? cur_row : nxt_row, sl);
+        st = (sb >> (lane & (GS - 1))) & 1u;
+        tx += (uint32_t)__popc(sb) * rowb;
+      }
+      if (gcnt >= NG) mbar_wait_a(empty_a + buf * 8, ((gcnt / NG) - 1u) & 1u);  // all T warps left the buffer
+      if (lane == 0) mbar_expect_tx_a(full_a + buf * 8, tx);
+      __syncwarp();
+      if (lane < cnt) {
+        const uint32_t off = (buf * GS + lane) * ROW_B;
+        bulk_g2s_a(gring_a + off, X + (size_t)(uint32_t)src * (uint32_t)ldx, rowb, full_a + buf * 8, pol);
+        if (FUSE_DW && st)
+          bulk_g2s_a(hring_a + off, Hrow + (size_t)(uint32_t)hrow * (uint32_t)ldh, rowb, full_a + buf * 8, pol);
+      }
+      ++gcnt;
+    };
+    if (sw == 0)
+      for (int gi = 0; gi < min(NG - 1, ng); ++gi) request(gi);
+
+    float4 wsel[G][4][NV];
+    float4 acc[FUSE_DW ? G : 1][4][NV];
+    const float* wr = Wt + (size_t)w * S * d;
+#pragma unroll
+    for (int r = 0; r < G; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          wsel[r][j][k] = ok[k] ? ldg4(wr + (size_t)(4 * (rel ^ r) + j) * d + col[k]) : zero4();
+          if (FUSE_DW) acc[FUSE_DW ? r : 0][j][k] = zero4();
+        }
+
+    float4 xs[NV], hq[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) xs[k] = hq[k] = zero4();
+
+    auto flush = [&](int row) {
+      float4 y[NV];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) y[k] = zero4();
+#pragma unroll
+      for (int r = 0; r < G; ++r) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const float4 v = (r == 0) ? xs[k] : shfl_xor4(xs[k], r);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float xv = comp(v, j);
+            fma4(y[k], xv, wsel[r][j][k]);
+            if (FUSE_DW) fma4(acc[FUSE_DW ? r : 0][j][k], xv, hq[k]);
+          }
+        }
+      }
+      float* po = out + (size_t)(uint32_t)row * (uint32_t)d;
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+        if (!TAIL || ok[k]) red4(po + col[k], y[k]);
+    };
+
+    uint32_t ends_mask = 0;
+    auto make_ends = [&]() {
+      const int nb = min(32, n - b0);
+      ends_mask = (cur_start >> 1) | ((b0 + nb < n) ? ((nxt_start & 1u) << 31) : (1u << (nb - 1)));
+    };
+    make_ends();
+
+    for (int gi = 0; gi < ng; ++gi) {
+      if (sw == 0 && gi + NG - 1 < ng) request(gi + NG - 1);
+      const uint32_t buf = ccnt % NG;
+      mbar_wait_a(full_a + buf * 8, (ccnt / NG) & 1u);
+      ++ccnt;
+      const uint32_t gbase = gring_a + buf * GS * ROW_B + (uint32_t)c0 * 4u + lane * 16;
+      const uint32_t hbase = hring_a + buf * GS * ROW_B + (uint32_t)c0 * 4u + lane * 16;
+      const int cnt = min(GS, n - gi * GS);
+      const int tb0 = gi * GS - b0;
+      for (int t = 0; t < cnt; ++t) {
+        const int tb = tb0 + t;
+        const float nm = __shfl_sync(FULL, cur_nm, tb);
+        const bool st = (cur_start >> tb) & 1u;
+        float4 x[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          x[k] = lds4(gbase + t * ROW_B + k * 512);
+          if (TAIL && !ok[k]) x[k] = zero4();  // bytes past the row end were not copied
+        }
+        if (st) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) xs[k] = make_float4(nm * x[k].x, nm * x[k].y, nm * x[k].z, nm * x[k].w);
+          if (FUSE_DW) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+              hq[k] = lds4(hbase + t * ROW_B + k * 512);
+              if (TAIL && !ok[k]) hq[k] = zero4();
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) fma4(xs[k], nm, x[k]);
+        }
+        if ((ends_mask >> tb) & 1u) flush(__shfl_sync(FULL, cur_row, tb));
+      }
+      __syncwarp();                                   // every lane has consumed its loads of this buffer
+      if (lane == 0) mbar_arrive_a(empty_a + buf * 8);
+      if (tb0 + GS == 32 && gi + 1 < ng) {
+        b0 += 32;
+        cur_row = nxt_row;
+        cur_nbr = nxt_nbr;
+        cur_nm = nxt_nm;
+        cur_start = nxt_start;
+        nxt_row = nxt_nbr = 0;
+        nxt_nm = 0.f;
+        if (b0 + 32 + lane < n) {
+          nxt_row = __ldg(r_row + beg + b0 + 32 + lane);
+          nxt_nbr = __ldg(r_nbr + beg + b0 + 32 + lane);
+          nxt_nm = __ldg(r_norm + beg + b0 + 32 + lane);
+        }
+        nxt_start = start_bits(nxt_row, __shfl_sync(FULL, cur_row, 31));
+        make_ends();
+      }
+    }
+    if (FUSE_DW) {
+#pragma unroll
+      for (int r = 0; r < G; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float* pw = dWt + ((size_t)w * S + 4 * (rel ^ r) + j) * d;
+#pragma unroll
+          for (int k = 0; k < NV; ++k)
+            if (!TAIL || ok[k]) red4(pw + col[k], acc[FUSE_DW ? r : 0][j][k]);
+        }
+    }
+  }
+}
+
+template <int S, int NV, bool FUSE, bool TAIL, int T, int NTEAMS, int NG, int GS>
+int launch_team_t(const WorkItem* items, int n_items, const int32_t* r_row, const int32_t* r_nbr, const float* r_norm,
+                  const float* X, int ldx, int d, const float* Wt, float* out, const float* Hrow, int ldh, float* dWt,
+                  cudaStream_t st) {
+  constexpr int ROW_B = T * NV * 512;
+  constexpr int smem = NTEAMS * NG * GS * ROW_B * (FUSE ? 2 : 1) + NTEAMS * NG * 16;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  auto kern = k_block_team<S, NV, FUSE, TAIL, T, NTEAMS, NG, GS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = rgcn_check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                             "cudaFuncSetAttribute(team smem)");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = std::min((n_items + NTEAMS - 1) / NTEAMS, sms);  // persistent: one CTA per SM
+  if (grid < 1) grid = 1;
+  kern<<<grid, NTEAMS * T * 32, smem, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt);
+  ++g_rgcn_launches;
+  return rgcn_check_cuda(cudaGetLastError(), "k_block_team");
+}
+
 template <int S, int NV, bool FUSE, bool TAIL, int NW, int NG, int GS, int MODE>
 int launch_stg_t(const WorkItem* items, int n_items, const int32_t* r_row, const int32_t* r_nbr, const float* r_norm,
                  const float* X, int ldx, int d, const float* Wt, float* out, const float* Hrow, int ldh, float* dWt,
@@ -420,6 +675,25 @@ int launch_block_stg(const WorkItem* items, int n_items, const int32_t* r_row, c
   int fwd_cfg = -1, bwd_cfg = -1;
   if (const char* e = std::getenv("RGCN_STG_FWD")) fwd_cfg = std::atoi(e);
   if (const char* e = std::getenv("RGCN_STG_BWD")) bwd_cfg = std::atoi(e);
+  // TEAM kernels (one staged copy of a row shared by the 4 slab warps of an item): rows of 4 x 128 columns.
+  // Default for those widths; RGCN_STG_TEAM=0 falls back to the per-warp rings (A/B knob).
+  bool team = d > 384 && d <= 512 && (s == 4 || s == 8) && ldx % 4 == 0;
+  if (const char* e = std::getenv("RGCN_STG_TEAM")) team = team && std::atoi(e) != 0;
+  if (team && !(fuse ? bwd_cfg >= 0 : fwd_cfg >= 0)) {
+#define TEAM(S_, FUSE_, NTEAMS_, NG_)                                                                   \
+  do {                                                                                                  \
+    if (d % 128 != 0) return launch_team_t<S_, 1, FUSE_, true, 4, NTEAMS_, NG_, 8>(ARGS);                \
+    return launch_team_t<S_, 1, FUSE_, false, 4, NTEAMS_, NG_, 8>(ARGS);                                 \
+  } while (0)
+    if (s == 8) {
+      if (!fuse) TEAM(8, false, 4, 3);   // 16 warps, 4 teams x 3 groups x 8 rows x 2 KB = 192 KB
+      TEAM(8, true, 3, 2);               // 12 warps, 3 teams x 2 rings x 2 groups x 8 rows x 2 KB = 192 KB
+    } else {
+      if (!fuse) TEAM(4, false, 4, 3);
+      TEAM(4, true, 3, 2);
+    }
+#undef TEAM
+  }
   if (s == 4) {
     if (!fuse) {
       if (d <= 128) STG(4, 1, false, 16, 3, 8, 1);

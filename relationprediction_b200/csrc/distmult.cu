@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256)
                    const int32_t* __restrict__ X, int64_t N, const float* __restrict__ Y,
                    const float* __restrict__ energies, float g_loss_over_n, float c_reg,
                    const float* __restrict__ g_scale, const float* __restrict__ g_energy,
-                   float* __restrict__ dcodes, float* __restrict__ drel) {
+                   float* __restrict__ dcodes, float* __restrict__ drel, float* __restrict__ rel_slice_sumsq) {
   if (g_scale) {
     g_loss_over_n *= __ldg(g_scale + 0);
     c_reg *= __ldg(g_scale + 1);
@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(256)
   const int64_t wid0 = (int64_t)blockIdx.x * 8 + warp;
   const int64_t wstride = (int64_t)gridDim.x * 8;
   const int d4 = d >> 2;
+  float slice_sq = 0.f;  // sum over this warp's triples of |gradient slice of the relation row|^2 (IndexedSlices norm)
   for (int64_t n = wid0; n < N; n += wstride) {
     const int s = __ldg(X + 3 * n), r = __ldg(X + 3 * n + 1), o = __ldg(X + 3 * n + 2);
     float gx = g_energy ? __ldg(g_energy + n) : 0.f;
@@ -130,7 +131,52 @@ __global__ void __launch_bounds__(256)
       red4(g1 + 4 * i, da);
       red4(gr + 4 * i, db);
       red4(g2 + 4 * i, dc);
+      slice_sq += db.x * db.x + db.y * db.y + db.z * db.z + db.w * db.w;
     }
+  }
+  if (rel_slice_sumsq) {  // warp-uniform
+    slice_sq = warp_sum(slice_sq);
+    if (lane == 0 && slice_sq != 0.f) atomicAdd(rel_slice_sumsq, slice_sq);
+  }
+}
+
+// ---- fused all-entity scoring + ranking (next row N3): query rows and gold scores --------------------------------
+__global__ void __launch_bounds__(256)
+    k_rank_prepare(const float* __restrict__ codes, const float* __restrict__ rel, int d, const int32_t* __restrict__ X,
+                   int64_t n, int side, float* __restrict__ Q, float* __restrict__ gold_sig, int32_t* __restrict__ gold_col) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d4 = d >> 2;
+  for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < n; t += (int64_t)gridDim.x * 8) {
+    const int s = __ldg(X + 3 * t), r = __ldg(X + 3 * t + 1), o = __ldg(X + 3 * t + 2);
+    const int kept = side == 0 ? o : s, gold = side == 0 ? s : o;
+    const float4* ek = reinterpret_cast<const float4*>(codes + (size_t)kept * d);
+    const float4* rr = reinterpret_cast<const float4*>(rel + (size_t)r * d);
+    const float4* eg = reinterpret_cast<const float4*>(codes + (size_t)gold * d);
+    float4* q = reinterpret_cast<float4*>(Q + (size_t)t * d);
+    float e = 0.f;
+    for (int i = lane; i < d4; i += 32) {
+      const float4 a = __ldg(ek + i), b = __ldg(rr + i), c = __ldg(eg + i);
+      const float4 p = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+      q[i] = p;
+      e = fmaf(p.x, c.x, e);
+      e = fmaf(p.y, c.y, e);
+      e = fmaf(p.z, c.z, e);
+      e = fmaf(p.w, c.w, e);
+    }
+    e = warp_sum(e);
+    if (lane == 0) {
+      gold_sig[t] = 1.0f / (1.0f + expf(-e));
+      gold_col[t] = gold;
+    }
+  }
+}
+
+// raw rank = #{score >= gold}; filtered rank = raw - #{known with score >= gold} + 1 (common/evaluation.py:148-152)
+__global__ void k_rank_finalize(const int32_t* __restrict__ raw_cnt, const int32_t* __restrict__ known_cnt, int64_t n,
+                                int32_t* __restrict__ raw_rank, int32_t* __restrict__ filtered_rank) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    raw_rank[t] = raw_cnt[t];
+    if (filtered_rank) filtered_rank[t] = raw_cnt[t] - known_cnt[t] + 1;
   }
 }
 
@@ -164,12 +210,28 @@ int launch_distmult_forward(const float* codes, const float* rel, int d, const i
 int launch_distmult_backward(const float* codes, const float* rel, int d, const int32_t* X,
                              int64_t N, const float* Y, const float* energies, float g_loss,
                              float g_reg, const float* g_scale_dev, const float* g_energy,
-                             float* dcodes, float* drel, cudaStream_t st) {
+                             float* dcodes, float* drel, float* rel_slice_sumsq, cudaStream_t st) {
   if (N == 0) return RGCN_OK;
   const float g_loss_over_n = g_loss / (float)N;
   const float c_reg = g_reg * 2.0f / ((float)N * (float)d);
   k_distmult_bwd<<<blocks_for_triples(N), 256, 0, st>>>(codes, rel, d, X, N, Y, energies,
                                                         g_loss_over_n, c_reg, g_scale_dev, g_energy,
-                                                        dcodes, drel);
+                                                        dcodes, drel, rel_slice_sumsq);
   return check_launch("k_distmult_bwd");
+}
+
+int launch_distmult_rank_prepare(const float* codes, const float* rel, int d, const int32_t* X, int64_t n, int side,
+                                 float* Q, float* gold_sig, int32_t* gold_col, cudaStream_t st) {
+  if (n == 0) return RGCN_OK;
+  k_rank_prepare<<<blocks_for_triples(n), 256, 0, st>>>(codes, rel, d, X, n, side, Q, gold_sig, gold_col);
+  return check_launch("k_rank_prepare");
+}
+
+int launch_distmult_rank_finalize(const int32_t* raw_cnt, const int32_t* known_cnt, int64_t n, int32_t* raw_rank,
+                                  int32_t* filtered_rank, cudaStream_t st) {
+  if (n == 0) return RGCN_OK;
+  int64_t b = (n + 255) / 256;
+  if (b > 148 * 8) b = 148 * 8;
+  k_rank_finalize<<<(int)b, 256, 0, st>>>(raw_cnt, known_cnt, n, raw_rank, filtered_rank);
+  return check_launch("k_rank_finalize");
 }

@@ -108,10 +108,26 @@ __device__ __forceinline__ uint32_t swz(int r, int c) {  // byte offset of 16 B 
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
+// EPI = 1: RANKING epilogue (all-entity scoring of the DistMult decoder, decoders/bilinear_diag.py:51-61, fused with
+// the rank counts of common/evaluation.py:148-159): the C tile is never written.  Row m of A is a query (e1*r or r*e2),
+// row n of Bt an entity code; each energy goes through the reference's float32 sigmoid and is compared with the gold
+// entity's score; a 32-column chunk yields a 32-bit "score >= gold" mask whose popcount is the chunk's contribution to
+// the raw rank, and popcount(mask & known bits) its contribution to the filtered correction.
+struct RankEpi {
+  const float* gold_sig;       // [M] sigmoid(energy of the gold entity)
+  const int32_t* gold_col;     // [M] gold entity id (always counted: score >= itself)
+  const uint32_t* known;       // [M, words] bit v = entity v is a known true answer (or nullptr)
+  int words;                   // ceil(N / 32)
+  int32_t* raw_cnt;            // [M] += #{v : score_v >= gold}
+  int32_t* known_cnt;          // [M] += #{known v : score_v >= gold}
+};
+__device__ __forceinline__ float sigmoid_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int EPI>
 __global__ void __launch_bounds__(N_THREADS, 1)
     k_gemm_tf32x3(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bhi,
                   const float* __restrict__ Blo, int64_t ldb, float* __restrict__ C, int64_t ldc,
-                  int M, int N, int K, int accumulate) {
+                  int M, int N, int K, int accumulate, RankEpi re) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
   __shared__ uint32_t tmem_base_smem;
@@ -221,6 +237,13 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const int cb_begin = (warp >> 2) * (BN / 2);
     const int n_pair = num_kb > 1 ? 2 : 1;  // accumulators actually written: {0,2} or {0,1,2,3}
+    int rank_raw = 0, rank_known = 0;
+    float gold_s = 0.f;
+    int gold_c = -1;
+    if (EPI == 1 && row < M) {
+      gold_s = __ldg(re.gold_sig + row);
+      gold_c = __ldg(re.gold_col + row);
+    }
 #pragma unroll
     for (int cb = cb_begin; cb < cb_begin + BN / 2; cb += 32) {
       uint32_t r[32];
@@ -244,6 +267,19 @@ __global__ void __launch_bounds__(N_THREADS, 1)
 #pragma unroll
         for (int q = 0; q < 32; ++q) sum[q] += __uint_as_float(r[q]);
       }
+      if (EPI == 1) {
+        if (row < M && n0 + cb < N) {
+          uint32_t bits = 0;
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (n0 + cb + q < N && sigmoid_ref(sum[q]) >= gold_s) bits |= 1u << q;
+          const int gq = gold_c - (n0 + cb);
+          if (gq >= 0 && gq < 32) bits |= 1u << gq;   // the gold entity always scores >= itself
+          rank_raw += __popc(bits);
+          if (re.known) rank_known += __popc(bits & __ldg(re.known + (size_t)row * re.words + ((n0 + cb) >> 5)));
+        }
+        continue;
+      }
 #pragma unroll
       for (int q = 0; q < 32; ++q) r[q] = __float_as_uint(sum[q]);
       if (row < M) {
@@ -265,6 +301,10 @@ __global__ void __launch_bounds__(N_THREADS, 1)
           }
         }
       }
+    }
+    if (EPI == 1 && row < M) {
+      if (rank_raw) atomicAdd(re.raw_cnt + row, rank_raw);
+      if (rank_known) atomicAdd(re.known_cnt + row, rank_known);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   } else {
@@ -539,16 +579,42 @@ int launch_gemm_tf32x3(const float* A, int64_t lda, const float* Bt_hi, const fl
   }
   static bool attr_set = false;
   if (!attr_set) {
-    int rc = rgcn_check_cuda(cudaFuncSetAttribute(k_gemm_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    int rc = rgcn_check_cuda(cudaFuncSetAttribute(k_gemm_tf32x3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   SMEM_BYTES),
                              "cudaFuncSetAttribute(gemm smem)");
     if (rc) return rc;
     attr_set = true;
   }
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
-  k_gemm_tf32x3<<<grid, N_THREADS, SMEM_BYTES, st>>>(A, lda, Bt_hi, Bt_lo, ldb, C, ldc, M, N, K, accumulate);
+  k_gemm_tf32x3<0><<<grid, N_THREADS, SMEM_BYTES, st>>>(A, lda, Bt_hi, Bt_lo, ldb, C, ldc, M, N, K, accumulate,
+                                                         RankEpi{});
   ++g_rgcn_launches;
   return rgcn_check_cuda(cudaGetLastError(), "k_gemm_tf32x3");
+}
+
+// Scoring GEMM with the ranking epilogue: queries Q [M,K] against the pre-split entity codes Bt [N,K]; the counts
+// accumulate (+=) into raw_cnt / known_cnt (zeroed by the caller).
+int launch_gemm_rank_tf32x3(const float* Q, int64_t ldq, const float* Bt_hi, const float* Bt_lo, int64_t ldb, int M,
+                            int N, int K, const float* gold_sig, const int32_t* gold_col, const uint32_t* known,
+                            int words, int32_t* raw_cnt, int32_t* known_cnt, cudaStream_t st) {
+  if (M == 0 || N == 0) return RGCN_OK;
+  if (K % 4 != 0 || ldq % 4 != 0 || ldb % 4 != 0) {
+    rgcn_set_error("gemm_rank_tf32x3: K and leading dimensions must be multiples of 4");
+    return RGCN_ERR_INVALID;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = rgcn_check_cuda(cudaFuncSetAttribute(k_gemm_tf32x3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  SMEM_BYTES),
+                             "cudaFuncSetAttribute(gemm rank smem)");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  RankEpi re{gold_sig, gold_col, known, words, raw_cnt, known_cnt};
+  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
+  k_gemm_tf32x3<1><<<grid, N_THREADS, SMEM_BYTES, st>>>(Q, ldq, Bt_hi, Bt_lo, ldb, nullptr, 0, M, N, K, 0, re);
+  ++g_rgcn_launches;
+  return rgcn_check_cuda(cudaGetLastError(), "k_gemm_tf32x3<rank>");
 }
 
 // C[M,N] (+)= A^T B, A [K,M] row-major, B [K,N] row-major (see k_gemm_tn_tf32x3)

@@ -89,6 +89,13 @@ int launch_basis_agg(const AggLaunch& a, const float* C, int B, int n_relw, int 
 int launch_basis_dc(const AggLaunch& a, const float* dAgg, int B, int n_relw, float* dC,
                     cudaStream_t st);
 
+// slice_norm.cu: squared norms of the un-aggregated IndexedSlices gradients (tf.clip_by_global_norm semantics)
+int launch_block_sqnorm(const float* X, int64_t rows, int ld, int B, int s, float* XB, cudaStream_t st);
+// out2[0] += sum over forward-table messages, out2[1] += backward-table messages of norm^2 * <GB[dst], HB[src]>
+int launch_block_slice_sumsq(const WorkItem* items, int n_items, const int32_t* r_row, const int32_t* r_nbr,
+                             const float* r_norm, const float* GB, const float* HB, int B, int half, float* out2,
+                             cudaStream_t st);
+
 // Elementwise helpers
 // G = dOut * (out > 0 if relu);  dS = G * mask * inv_keep (only if mask != null, else dS untouched)
 int launch_grad_prologue(const float* dOut, const float* out, const uint8_t* mask, float inv_keep,
@@ -105,13 +112,23 @@ int launch_gemm_split_b(const float* B, int64_t ldb, int N, int K, int transpose
 int launch_gemm_tf32x3(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, int64_t ldb,
                        float* C, int64_t ldc, int M, int N, int K, int accumulate, cudaStream_t st);
 
+int launch_gemm_rank_tf32x3(const float* Q, int64_t ldq, const float* Bt_hi, const float* Bt_lo, int64_t ldb, int M,
+                            int N, int K, const float* gold_sig, const int32_t* gold_col, const uint32_t* known,
+                            int words, int32_t* raw_cnt, int32_t* known_cnt, cudaStream_t st);
+
 int launch_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                           int M, int N, int K, int accumulate, cudaStream_t st);
 
 // DistMult
+// queries + gold scores of the fused scorer/ranker: side 0 (subjects corrupted): Q[t] = rel[r] * codes[o], gold = s;
+// side 1 (objects corrupted): Q[t] = codes[s] * rel[r], gold = o.  gold_sig[t] = sigmoid(<Q[t], codes[gold]>)
+int launch_distmult_rank_prepare(const float* codes, const float* rel, int d, const int32_t* X, int64_t n, int side,
+                                 float* Q, float* gold_sig, int32_t* gold_col, cudaStream_t st);
+int launch_distmult_rank_finalize(const int32_t* raw_cnt, const int32_t* known_cnt, int64_t n, int32_t* raw_rank,
+                                  int32_t* filtered_rank, cudaStream_t st);
 int launch_distmult_forward(const float* codes, const float* rel, int d, const int32_t* X, int64_t N,
                             const float* Y, float* energies, float* loss_out, cudaStream_t st);
 int launch_distmult_backward(const float* codes, const float* rel, int d, const int32_t* X,
                              int64_t N, const float* Y, const float* energies, float g_loss,
                              float g_reg, const float* g_scale_dev, const float* g_energy,
-                             float* dcodes, float* drel, cudaStream_t st);
+                             float* dcodes, float* drel, float* rel_slice_sumsq, cudaStream_t st);

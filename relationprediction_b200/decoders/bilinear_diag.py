@@ -74,3 +74,38 @@ class BilinearDiag(Model):
         e1s, rs, e2s = self.compute_codes(mode='test')
         all_object_codes = self.next_component.get_all_object_codes(mode='test')
         return torch.sigmoid((e1s * rs) @ all_object_codes.T)
+
+    # ---- fused all-entity scoring + ranking (next row N3; library entry distmult_rank) ----
+    @staticmethod
+    def known_bit_mask(lists, n_entities):
+        """int32 view of the uint32 [n, ceil(V/32)] bit masks the library expects: bit v of row t = v in lists[t]."""
+        words = (n_entities + 31) // 32
+        m = np.zeros((len(lists), words), np.uint32)
+        lens = np.fromiter((len(l) for l in lists), dtype=np.int64, count=len(lists))
+        if lens.sum():
+            rows = np.repeat(np.arange(len(lists)), lens)
+            cols = np.concatenate([np.asarray(l, dtype=np.int64) for l in lists if len(l)])
+            np.bitwise_or.at(m, (rows, cols >> 5), np.left_shift(np.uint32(1), (cols & 31).astype(np.uint32)))
+        return m.view(np.int32)
+
+    def rank_all(self, triplets, known_subject_lists, known_object_lists, chunk=4096):
+        """Raw and filtered ranks of every triple under subject and object corruption with the rules of
+        common/evaluation.py:148-159 / :355-367, without materialising the [n, V] score matrices of
+        predict_all_subject_scores / predict_all_object_scores (bilinear_diag.py:51-61): the encoder runs once,
+        the scoring GEMM counts `score >= gold` in its epilogue.  Returns four int arrays
+        (raw_subjects, filtered_subjects, raw_objects, filtered_objects)."""
+        subject_codes, relation_codes, object_codes = self.next_component.get_all_codes(mode='test')
+        assert subject_codes is object_codes, "DistMult ranking expects one shared entity code matrix"
+        codes, rel = subject_codes.contiguous(), relation_codes.contiguous()
+        ranker = ops.DistMultRanker(codes, rel)
+        V = codes.shape[0]
+        tri = np.ascontiguousarray(np.asarray(triplets, dtype=np.int32).reshape(-1, 3))
+        out = [[], [], [], []]
+        for c0 in range(0, len(tri), chunk):
+            X = torch.as_tensor(tri[c0:c0 + chunk], device=codes.device)
+            for side, lists in ((0, known_subject_lists), (1, known_object_lists)):
+                mask = torch.as_tensor(self.known_bit_mask(lists[c0:c0 + chunk], V), device=codes.device)
+                raw, filt = ranker.rank(X, side, mask)
+                out[2 * side].append(raw)
+                out[2 * side + 1].append(filt)
+        return tuple(torch.cat(o).cpu().numpy().astype(np.int64) if o else np.zeros(0, np.int64) for o in out)

@@ -92,6 +92,19 @@ class Model(object):
         with torch.no_grad():
             return self.predict_all_object_scores().cpu().numpy()
 
+    def supports_fused_ranking(self):
+        """True when the head decoder has a fused scorer/ranker and the model lives on a CUDA device."""
+        return hasattr(self, 'rank_all') and self.get_device().type == 'cuda'
+
+    def rank_all_entities(self, triplets, known_subject_lists, known_object_lists):
+        """Ranks under both corruptions through the decoder's fused scorer/ranker (one encoder pass for the whole
+        set); decoders without one return None and the Scorer falls back to score_all_subjects / score_all_objects."""
+        if not hasattr(self, 'rank_all'):
+            return None
+        self._feed_test(getattr(self, 'test_graph', None), np.asarray(triplets).reshape(-1, 3)[:1])
+        with torch.no_grad():
+            return self.rank_all(triplets, known_subject_lists, known_object_lists)
+
     def register_for_test(self, triplets):
         self.test_graph = triplets
 

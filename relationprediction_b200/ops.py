@@ -160,6 +160,24 @@ class Graph:
         return self._h
 
 
+# ---- tf.clip_by_global_norm sees IndexedSlices -----------------------------------------------------------------
+# Variables the reference reads through tf.nn.embedding_lookup (block tables, relation table) get un-aggregated
+# per-edge / per-triple gradient slices, and the global clipping norm is taken over those slice values.  When enabled,
+# the backward passes below also produce sum |slice|^2 on the device and park it on the parameter tensor as
+# `_slice_sumsq`; optim.ClippedAdam uses it in place of the dense gradient's sum of squares.
+_SLICE_NORMS = False
+
+
+def set_slice_norms(enabled):
+    global _SLICE_NORMS
+    _SLICE_NORMS = bool(enabled)
+
+
+def _add_slice_sumsq(param, value):
+    prev = getattr(param, "_slice_sumsq", None)
+    param._slice_sumsq = value if prev is None else prev + value
+
+
 def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
@@ -197,6 +215,7 @@ class _BlockLayerFn(torch.autograd.Function):
         _lib.check(rc, "rgcn_block_forward")
         ctx.graph, ctx.n_blocks, ctx.keep, ctx.relu = graph, n_blocks, float(keep), bool(relu)
         ctx.mask = mask
+        ctx.params = (Wf, Wb)   # the caller's tensor objects (slice norms are parked on them)
         ctx.save_for_backward(H, Wf, Wb, Wself, out)
         return out
 
@@ -218,6 +237,16 @@ class _BlockLayerFn(torch.autograd.Function):
                                      _ptr(dH), _ptr(dWf), _ptr(dWb), _ptr(dWself), _ptr(ws),
                                      ws.numel(), _stream(dev))
         _lib.check(rc, "rgcn_block_backward")
+        if _SLICE_NORMS:
+            G = (dOut * (out > 0)) if ctx.relu else dOut
+            nb2 = lib.rgcn_block_slice_sumsq_workspace_bytes(graph.handle, d, B)
+            ws2 = _workspace(nb2, dev)
+            ss = torch.empty(2, dtype=torch.float32, device=dev)
+            rc = lib.rgcn_block_slice_sumsq(graph.handle, d, B, _ptr(H), _ptr(G.contiguous()), _ptr(ss), _ptr(ws2),
+                                            ws2.numel(), _stream(dev))
+            _lib.check(rc, "rgcn_block_slice_sumsq")
+            _add_slice_sumsq(ctx.params[0], ss[0])
+            _add_slice_sumsq(ctx.params[1], ss[1])
         return dH, dWf, dWb, dWself, None, None, None, None, None
 
 
@@ -308,6 +337,7 @@ class _DistMultFn(torch.autograd.Function):
                                   _ptr(energies), _ptr(loss2), _stream(dev))
         _lib.check(rc, "distmult_forward")
         ctx.has_y = Y is not None
+        ctx.rel_param = rel
         ctx.save_for_backward(codes, rel, X, Y if Y is not None else torch.empty(0, device=dev),
                               energies)
         return energies, loss2[0], loss2[1]
@@ -330,10 +360,13 @@ class _DistMultFn(torch.autograd.Function):
             gs[0] = g_loss
         if g_reg is not None:
             gs[1] = g_reg
-        rc = lib.distmult_backward(_ptr(codes), _ptr(rel), V, rel.shape[0], d, _ptr(X), X.shape[0],
-                                   _ptr(Y), _ptr(energies), 1.0, 1.0, _ptr(gs), _ptr(ge),
-                                   _ptr(dcodes), _ptr(drel), _stream(dev))
-        _lib.check(rc, "distmult_backward")
+        ss = torch.zeros(1, dtype=torch.float32, device=dev) if _SLICE_NORMS else None
+        rc = lib.distmult_backward_slices(_ptr(codes), _ptr(rel), V, rel.shape[0], d, _ptr(X), X.shape[0],
+                                          _ptr(Y), _ptr(energies), 1.0, 1.0, _ptr(gs), _ptr(ge),
+                                          _ptr(dcodes), _ptr(drel), _ptr(ss), _stream(dev))
+        _lib.check(rc, "distmult_backward_slices")
+        if ss is not None:
+            _add_slice_sumsq(ctx.rel_param, ss[0])
         return dcodes, drel, None, None
 
 
@@ -406,3 +439,41 @@ def block_aggregate_backward(X, W_forward, W_backward, G, graph, n_blocks, dWf=N
                                            ws.numel(), _stream(X.device))
     _lib.check(rc, "rgcn_block_aggregate_backward")
     return dX, dWf, dWb
+
+
+class DistMultRanker(object):
+    """Fused all-entity scoring + ranking over one entity code matrix (distmult_rank, include/rgcn_b200.h): the
+    hi/lo split of `codes` is made once and reused by every chunk / corruption side."""
+
+    def __init__(self, codes, rel):
+        _check_cuda_f32("codes", codes)
+        _check_cuda_f32("relation table", rel)
+        self.codes, self.rel = codes, rel
+        self._ws, self._ws_n, self._split_ready = None, -1, False
+
+    def rank(self, X, side, known_mask=None):
+        """X int32 [n,3] CUDA; side 0 = subjects corrupted, 1 = objects; known_mask uint32 [n, ceil(V/32)] CUDA or None.
+        Returns (raw_rank, filtered_rank or None) int32 CUDA tensors."""
+        lib = _lib.load()
+        V, d = self.codes.shape
+        if not (X.is_cuda and X.dtype == torch.int32 and X.is_contiguous() and X.dim() == 2 and X.shape[1] == 3):
+            raise _lib.RgcnError("X must be a contiguous CUDA int32 [n,3] tensor")
+        n = X.shape[0]
+        words = (V + 31) // 32
+        if known_mask is not None and not (known_mask.is_cuda and known_mask.dtype == torch.int32
+                                           and known_mask.is_contiguous() and tuple(known_mask.shape) == (n, words)):
+            raise _lib.RgcnError("known_mask must be a contiguous CUDA int32 [n, ceil(V/32)] tensor (bit masks)")
+        dev = self.codes.device
+        if self._ws is None or n > self._ws_n:
+            nb = lib.distmult_rank_workspace_bytes(V, d, n)
+            if nb < 0:
+                _lib.check(int(nb), "distmult_rank_workspace_bytes")
+            self._ws, self._ws_n, self._split_ready = _workspace(nb, dev), n, False
+        raw = torch.empty(n, dtype=torch.int32, device=dev)
+        filt = torch.empty(n, dtype=torch.int32, device=dev) if known_mask is not None else None
+        rc = lib.distmult_rank(_ptr(self.codes), _ptr(self.rel), V, self.rel.shape[0], d, _ptr(X), n, int(side),
+                               _ptr(known_mask), int(self._split_ready), _ptr(raw), _ptr(filt), _ptr(self._ws),
+                               self._ws.numel(), _stream(dev))
+        _lib.check(rc, "distmult_rank")
+        self._split_ready = True
+        return raw, filt

@@ -1,6 +1,14 @@
 """Optimizer step of the reference's stack (GradientClipping + Adam, optimization/optimize.py:152-203 wiring,
 tensorflow_backend/algorithms.py:36-42, :65-68) on the library's kernels (csrc/optimizer.cu): TensorFlow-1.x
-clip_by_global_norm and AdamOptimizer formulas, all gradients treated as dense, no host synchronisation."""
+clip_by_global_norm and AdamOptimizer formulas, no host synchronisation.
+
+The clipping norm follows what tf.clip_by_global_norm actually sees in the reference: variables read through
+tf.nn.embedding_lookup (block tables W_forward / W_backward, the decoder's relation table) carry IndexedSlices
+gradients, whose norm is taken over the un-aggregated per-edge / per-triple slice VALUES.  When the backward passes
+were run with ops.set_slice_norms(True) they leave that sum of squares on the parameter (`_slice_sumsq`) and it is
+used here; parameters without it (dense gradients) contribute the sum of squares of their gradient.  The Adam update
+itself is dense in both worlds (TF 1.4 sums duplicate indices before _apply_sparse and decays every row).
+Not covered: the basis coefficients C_forward / C_backward (also embedding_lookup variables) still use the dense norm."""
 import torch
 
 from . import _lib
@@ -33,6 +41,11 @@ class ClippedAdam(object):
         if self.max_norm is not None:
             sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
             for p, _, _ in live:
+                ss = getattr(p, "_slice_sumsq", None)
+                if ss is not None:   # IndexedSlices in the reference: norm over the un-aggregated slices
+                    sumsq += ss.to(dev)
+                    p._slice_sumsq = None
+                    continue
                 g = p.grad.contiguous()
                 _lib.check(lib.rgcn_sumsq_accumulate(_ptr(g), g.numel(), _ptr(sumsq), st), "rgcn_sumsq_accumulate")
         for p, m, v in live:

@@ -197,6 +197,9 @@ def main(argv=None):
     ap.add_argument("--set", action="append", default=[], metavar="Section.Key=Value",
                     help="override one settings entry after the file is read, e.g. "
                          "--set Encoder.NumberOfBasisFunctions=2 (repeatable)")
+    ap.add_argument("--dense-clip-norm", action="store_true",
+                    help="clip by the norm of the summed dense gradients instead of the reference's IndexedSlices norm "
+                         "(tf.clip_by_global_norm over un-aggregated per-edge slices of embedding_lookup variables)")
     ap.add_argument("--no-save", action="store_true", help="do not write checkpoints (default: the reference's "
                     "ModelSaver cadence to General.ExperimentName)")
     ap.add_argument("--save-path", default=None, help="checkpoint path prefix (default: General.ExperimentName)")
@@ -274,6 +277,9 @@ def main(argv=None):
     lr = float(algo['learning_rate'])
     max_norm = float(opt['MaxGradientNorm']) if 'MaxGradientNorm' in opt else None
     optimizer = ClippedAdam(weights, lr=lr, beta1=0.9, beta2=0.999, eps=1e-8, max_norm=max_norm)
+    if str(args.device).startswith("cuda"):
+        from . import ops
+        ops.set_slice_norms(max_norm is not None and not args.dense_clip_norm)
     report_every = int(opt['ReportTrainLossEvery']) if 'ReportTrainLossEvery' in opt else 100
     stopper = None
     if 'EarlyStopping' in opt and not args.no_periodic_eval:

@@ -193,3 +193,16 @@ def test_real_chain_weight_and_feed_order_on_cpu(toy):
     assert [p.name for p in model.get_train_input_variables()] == ['graph_edges', 'X', 'Y']
     assert [p.name for p in model.get_test_input_variables()] == ['graph_edges', 'X']
     assert model.needs_graph()
+
+
+def test_known_bit_mask_layout():
+    """uint32 [n, ceil(V/32)] masks for the fused ranker: bit v of row t set iff v is in lists[t]."""
+    from relationprediction_b200.decoders.bilinear_diag import BilinearDiag
+    lists = [[0, 31, 32, 99], [], [64], [5, 5, 7]]
+    m = BilinearDiag.known_bit_mask(lists, 100).view(np.uint32)
+    assert m.shape == (4, 4) and m.dtype == np.uint32
+    dense = np.zeros((4, 128), bool)
+    for t, l in enumerate(lists):
+        dense[t, l] = True
+    got = ((m[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool).reshape(4, 128)
+    np.testing.assert_array_equal(got, dense)
