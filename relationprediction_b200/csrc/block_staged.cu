@@ -612,6 +612,7 @@ int launch_team_t(const WorkItem* items, int n_items, const int32_t* r_row, cons
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (const char* e = std::getenv("RGCN_STG_SMS")) sms = std::max(1, std::min(sms, std::atoi(e)));  // experiment knob
   int grid = std::min((n_items + NTEAMS - 1) / NTEAMS, sms);  // persistent: one CTA per SM
   if (grid < 1) grid = 1;
   kern<<<grid, NTEAMS * T * 32, smem, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt);
@@ -639,6 +640,7 @@ int launch_stg_t(const WorkItem* items, int n_items, const int32_t* r_row, const
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (const char* e = std::getenv("RGCN_STG_SMS")) sms = std::max(1, std::min(sms, std::atoi(e)));  // experiment knob
   int grid = (int)std::min<int64_t>((units + NW - 1) / NW, sms);  // persistent: one CTA per SM
   if (grid < 1) grid = 1;
   kern<<<grid, NW * 32, smem, st>>>(items, n_items, n_slabs, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt);
