@@ -49,10 +49,10 @@ const char* rgcn_last_error(void);
 int64_t rgcn_launch_count(void);
 
 /* Library options.  "block_algo": 0 = destination-major aggregation (deterministic summation order,
- * epilogue fused), 1 = weight-id-major aggregation (block weights in registers, vector reductions
- * in L2; fastest, fp32 summation order not reproducible run to run), -1 = auto (default),
- * 2 = EXPERIMENTAL component-major path for 5x5 blocks (rgcn_block_forward / rgcn_block_backward only;
- * falls back to 1 for other shapes; not yet validated on hardware -- never selected automatically).
+ * epilogue fused), 1 = weight-id-major aggregation with the gathered rows in registers (block weights in
+ * registers, vector reductions in L2; fp32 summation order not reproducible run to run), 3 = the same walk with the
+ * gathered rows staged through shared memory by TMA bulk copies / cp.async (block sizes 4, 8, 16; fastest),
+ * -1 = auto (default): 3 where the block size allows, else 1, else 0.
  * The environment variable RGCN_BLOCK_ALGO overrides the option.
  * "graph_views": which sorted views GPU-prepared graphs created AFTER the call get: 1 = the two CSR views
  * (deterministic block mode, basis layers), 2 = the two weight-id-major views (default block kernels),

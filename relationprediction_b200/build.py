@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "librgcn_b200.so")
-SOURCES = ["graph.cu", "graph_device.cu", "rgcn_kernels.cu", "gemm_tf32x3.cu", "distmult.cu", "sampler.cu", "optimizer.cu", "block_cm.cu", "block_staged.cu", "slice_norm.cu", "api.cu"]
+SOURCES = ["graph.cu", "graph_device.cu", "rgcn_kernels.cu", "gemm_tf32x3.cu", "distmult.cu", "sampler.cu", "optimizer.cu", "block_staged.cu", "slice_norm.cu", "api.cu"]
 HEADERS = ["graph.h", "kernels.cuh", os.path.join("..", "..", "include", "rgcn_b200.h")]
 
 

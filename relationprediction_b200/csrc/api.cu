@@ -146,22 +146,16 @@ AggLaunch make_agg(const CsrSide& side, const float* X, int ldx, int d, float* s
 
 }  // namespace
 
-// block_algo: 0 = destination-major (deterministic, fused epilogue), 1 = weight-id major (weights in
-// registers + L2 vector reductions), -1 = auto (weight-id major whenever the block size supports it),
-// 2 = EXPERIMENTAL component-major path for 5x5 blocks (block_cm.cu; rgcn_block_forward/backward only)
+// block_algo: 0 = destination-major (deterministic, fused epilogue), 1 = weight-id major with the gathered rows in
+// registers (rgcn_kernels.cu), 3 = weight-id major with TMA-staged rows (block_staged.cu; block sizes 4, 8, 16),
+// -1 = auto: 3 where it applies, else 1 where it applies, else 0
 static int g_block_algo = -1;
-
-static bool use_cm(int d, int s) {
-  int algo = g_block_algo;
-  if (const char* e = std::getenv("RGCN_BLOCK_ALGO")) algo = std::atoi(e);
-  return algo == 2 && block_cm_supported(d, s);
-}
 
 // 3 = weight-id-major with TMA-staged gathers (block_staged.cu) where the block size supports it
 static bool use_staged(int d, int s) {
   int algo = g_block_algo;
   if (const char* e = std::getenv("RGCN_BLOCK_ALGO")) algo = std::atoi(e);
-  return algo == 3 && block_stg_supported(d, s);
+  return (algo == 3 || algo == -1) && block_stg_supported(d, s);
 }
 
 static int launch_block_relmajor(const WorkItem* items, int n_items, const int32_t* r_row, const int32_t* r_nbr,
@@ -271,16 +265,6 @@ extern "C" int64_t rgcn_block_workspace_bytes(const rgcn_graph_t* g, int32_t d, 
   const int64_t wt = (int64_t)g->n_relw * s * d;
   const int slabs = slabs_for(d);
   int64_t bytes = align_up((int64_t)2 * d * d * 4);  // hi/lo split of W_self for the tensor-core GEMM
-  if (use_cm((int)d, (int)s)) {  // component-major copies: Wc (+dWc), Hc, Mc | Gc, dHc
-    bytes += (backward ? 2 : 1) * align_up(wt * 4);
-    bytes += align_up((int64_t)g->V_src * d * 4);                       // Hc
-    bytes += align_up((int64_t)g->V_dst * d * 4);                       // Mc (forward) / Gc (backward)
-    if (backward) {
-      bytes += 2 * align_up((int64_t)g->V_dst * d * 4);                 // G, dS
-      bytes += align_up((int64_t)g->V_src * d * 4);                     // dHc
-    }
-    return bytes + 256;
-  }
   if (!backward) {
     bytes += align_up(wt * 4);
     bytes += align_up(g->by_dst.n_split * d * 4);
@@ -317,7 +301,7 @@ extern "C" int rgcn_block_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
   if (rc) return rc;
   const int s = d / B, R = g->n_relw / 2;
   {
-    const bool relm = use_rel_major(d, s) || use_cm(d, s);
+    const bool relm = use_rel_major(d, s);
     rc = need_views(g, !relm, relm, "rgcn_block_forward");
     if (rc) return rc;
   }
@@ -325,32 +309,6 @@ extern "C" int rgcn_block_forward(const rgcn_graph_t* g, int32_t d, int32_t B, c
   const int64_t n_split = g->by_dst.n_split;
   Carver ws(workspace, workspace_bytes);
   float* split_ws = ws.take<float>((int64_t)2 * d * d);
-  if (use_cm(d, s)) {
-    // component-major path: Hc = cm(H); Mc = 0; Mc[dst] += W_r . sum(norm Hc[src]); out = act(dropout(H W_self) + Mc)
-    float* Wc = ws.take<float>((int64_t)g->n_relw * s * d);
-    float* Hc = ws.take<float>((int64_t)g->V_src * d);
-    float* Mc = ws.take<float>((int64_t)g->V_dst * d);
-    MARK("start");
-    rc = launch_relayout_cm(Wf, Wb, R, B, s, /*transpose=*/0, Wc, st);
-    if (rc) return rc;
-    rc = launch_to_cm(H, g->V_src, B, s, Hc, st);
-    if (rc) return rc;
-    rc = rgcn_check_cuda(cudaMemsetAsync(Mc, 0, (size_t)g->V_dst * d * sizeof(float), st), "memset(Mc)");
-    if (rc) return rc;
-    MARK("block_relayout");
-    rc = gemm_any(st, split_ws, false, false, g->V_dst, d, d, H, d, Wself, d, 0.f, out, d);
-    if (rc) return rc;
-    MARK("gemm_self_loop");
-    rc = launch_mask_relu(out, drop_mask, 1.0f / keep, 0, (int64_t)g->V_dst * d, st);
-    if (rc) return rc;
-    rc = launch_block_cm(g->by_rel.d_items, (int)g->by_rel.n_items, g->by_rel.d_row, g->by_rel.d_nbr,
-                         g->by_rel.d_norm, Hc, d, B, s, Wc, Mc, d, nullptr, 0, nullptr, st);
-    if (rc) return rc;
-    MARK("block_agg_fwd");
-    rc = launch_cm_add(Mc, g->V_dst, B, s, relu, out, st);
-    MARK("relu_epilogue");
-    return rc;
-  }
   float* Wt = ws.take<float>((int64_t)g->n_relw * s * d);
   float* scratch = ws.take<float>(n_split * d);
   int* counters = ws.take<int>(n_split * slabs);
@@ -414,7 +372,7 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   if (rc) return rc;
   const int s = d / B, R = g->n_relw / 2;
   {
-    const bool relm = use_rel_major(d, s) || use_cm(d, s);
+    const bool relm = use_rel_major(d, s);
     rc = need_views(g, !relm, true, "rgcn_block_backward");
     if (rc) return rc;
   }
@@ -423,60 +381,6 @@ extern "C" int rgcn_block_backward(const rgcn_graph_t* g, int32_t d, int32_t B, 
   const int64_t wt = (int64_t)g->n_relw * s * d;
   Carver ws(workspace, workspace_bytes);
   float* split_ws = ws.take<float>((int64_t)2 * d * d);
-  if (use_cm(d, s)) {
-    float* Wct = ws.take<float>(wt);
-    float* dWc = ws.take<float>(wt);
-    float* Hc = ws.take<float>((int64_t)g->V_src * d);
-    float* Gc = ws.take<float>((int64_t)g->V_dst * d);
-    float* Gm = ws.take<float>((int64_t)g->V_dst * d);
-    float* dSm = ws.take<float>((int64_t)g->V_dst * d);
-    float* dHc = ws.take<float>((int64_t)g->V_src * d);
-    if (!drop_mask) dSm = Gm;
-    MARK("start");
-    rc = launch_grad_prologue(dOut, out, drop_mask, 1.0f / keep, relu, (int64_t)g->V_dst * d, Gm, dSm, st);
-    if (rc) return rc;
-    MARK("grad_prologue");
-    rc = gemm_any(st, split_ws, true, false, d, d, g->V_dst, H, d, dSm, d, 0.f, dWself, d);
-    if (rc) return rc;
-    MARK("gemm_dWself");
-    rc = gemm_any(st, split_ws, false, true, g->V_dst, d, d, dSm, d, Wself, d, 0.f, dH, d);
-    if (rc) return rc;
-    if (g->V_src > g->V_dst) {
-      rc = rgcn_check_cuda(cudaMemsetAsync(dH + (size_t)g->V_dst * d, 0,
-                                           (size_t)(g->V_src - g->V_dst) * d * sizeof(float), st),
-                           "memset(dH halo)");
-      if (rc) return rc;
-    }
-    MARK("gemm_dH_self");
-    rc = launch_relayout_cm(Wf, Wb, R, B, s, /*transpose=*/1, Wct, st);
-    if (rc) return rc;
-    rc = launch_to_cm(Gm, g->V_dst, B, s, Gc, st);
-    if (rc) return rc;
-    rc = launch_to_cm(H, g->V_src, B, s, Hc, st);
-    if (rc) return rc;
-    rc = rgcn_check_cuda(cudaMemsetAsync(dHc, 0, (size_t)g->V_src * d * sizeof(float), st), "memset(dHc)");
-    if (rc) return rc;
-    rc = rgcn_check_cuda(cudaMemsetAsync(dWc, 0, wt * sizeof(float), st), "memset(dWc)");
-    if (rc) return rc;
-    MARK("block_relayout_T");
-    // dHc[src] += W_r^T . sum_run(norm Gc[dst])      (rows = sources, gathered rows = destinations)
-    rc = launch_block_cm(g->by_rel_src.d_items, (int)g->by_rel_src.n_items, g->by_rel_src.d_row,
-                         g->by_rel_src.d_nbr, g->by_rel_src.d_norm, Gc, d, B, s, Wct, dHc, d, nullptr, 0,
-                         nullptr, st);
-    if (rc) return rc;
-    MARK("block_agg_dH");
-    // dWc[w][i][j][b] += sum_run(norm Gc[dst])[i][b] * Hc[src][j][b]
-    rc = launch_block_cm(g->by_rel_src.d_items, (int)g->by_rel_src.n_items, g->by_rel_src.d_row,
-                         g->by_rel_src.d_nbr, g->by_rel_src.d_norm, Gc, d, B, s, nullptr, nullptr, d, Hc, d,
-                         dWc, st);
-    if (rc) return rc;
-    MARK("block_dW");
-    rc = launch_cm_add(dHc, g->V_src, B, s, 0, dH, st);
-    if (rc) return rc;
-    rc = launch_unlayout_cm(dWc, R, B, s, dWf, dWb, st);
-    MARK("block_unlayout");
-    return rc;
-  }
   float* Wtt = ws.take<float>(wt);
   float* dWt = ws.take<float>(wt);
   float* G = ws.take<float>((int64_t)g->V_dst * d);
@@ -577,7 +481,7 @@ extern "C" int rgcn_block_aggregate(const rgcn_graph_t* g, int32_t d, int32_t B,
   if (rc) return rc;
   const int s = d / B, R = g->n_relw / 2;
   {
-    const bool relm = use_rel_major(d, s) || use_cm(d, s);
+    const bool relm = use_rel_major(d, s);
     rc = need_views(g, !relm, relm, "rgcn_block_aggregate");
     if (rc) return rc;
   }
@@ -627,7 +531,7 @@ extern "C" int rgcn_block_aggregate_backward(const rgcn_graph_t* g, int32_t d, i
   if (rc) return rc;
   const int s = d / B, R = g->n_relw / 2;
   {
-    const bool relm = use_rel_major(d, s) || use_cm(d, s);
+    const bool relm = use_rel_major(d, s);
     rc = need_views(g, !relm, true, "rgcn_block_aggregate_backward");
     if (rc) return rc;
   }

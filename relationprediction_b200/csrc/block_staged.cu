@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(NW * 32, 1)
     k_block_stg(const WorkItem* __restrict__ items, int n_items, int n_slabs, const int32_t* __restrict__ r_row,
                 const int32_t* __restrict__ r_nbr, const float* __restrict__ r_norm, const float* __restrict__ X, int ldx,
                 int d, const float* __restrict__ Wt, float* __restrict__ out, const float* __restrict__ Hrow, int ldh,
-                float* __restrict__ dWt) {
+                float* __restrict__ dWt, int* __restrict__ next_unit) {
   static_assert(S == 4 || S == 8 || S == 16, "block size");
   static_assert(GS == 4 || GS == 8, "group size");
   static_assert(NG >= 2 && (NG - 1) * GS <= 32, "the fetch cursor must stay within the next index batch");
@@ -137,8 +137,18 @@ __global__ void __launch_bounds__(NW * 32, 1)
   uint32_t gcnt = 0;               // groups requested so far by this warp (buffer = gcnt % NG, phase = gcnt / NG)
   uint32_t ccnt = 0;               // groups consumed so far
 
+  // DYNAMIC work distribution: a warp takes the next (item, slab) unit from a global counter when it is done with
+  // its current one.  The units are ordered by (supertile, weight id), and the vector reductions only resolve in L2
+  // while all warps of the chip work inside the same few supertiles.  A static round-robin keeps them together on a
+  // small graph, but at the full benchmark size (2.4 M items, 170 ms) per-SM speed differences let the warps drift
+  // hundreds of supertiles apart and the reduction window falls out of L2 (measured: 0.85 ns instead of 0.46 ns per
+  // message, and FASTER on 110 SMs than on 148).
   const int64_t n_units = (int64_t)n_items * n_slabs;
-  for (int64_t unit = (int64_t)blockIdx.x * NW + warp; unit < n_units; unit += (int64_t)gridDim.x * NW) {
+  for (;;) {
+    int unit_l = 0;
+    if (lane == 0) unit_l = atomicAdd(next_unit, 1);
+    const int64_t unit = __shfl_sync(FULL, unit_l, 0);
+    if (unit >= n_units) break;
     const int item = (int)(unit / n_slabs);
     const int c0 = (int)(unit % n_slabs) * (NV * 128);
     const int4 itv = __ldg(reinterpret_cast<const int4*>(items) + item);
@@ -383,12 +393,13 @@ __global__ void __launch_bounds__(NTEAMS * T * 32, 1)
     k_block_team(const WorkItem* __restrict__ items, int n_items, const int32_t* __restrict__ r_row,
                  const int32_t* __restrict__ r_nbr, const float* __restrict__ r_norm, const float* __restrict__ X, int ldx,
                  int d, const float* __restrict__ Wt, float* __restrict__ out, const float* __restrict__ Hrow, int ldh,
-                 float* __restrict__ dWt) {
+                 float* __restrict__ dWt, int* __restrict__ next_unit) {
   static_assert(S == 4 || S == 8 || S == 16, "block size");
   static_assert(GS == 4 || GS == 8, "group size");
   static_assert(NG >= 2 && (NG - 1) * GS <= 32, "the fetch cursor must stay within the next index batch");
   constexpr int G = S / 4;                      // lanes per block
   constexpr int ROW_B = T * NV * 512;           // bytes of one staged row slot (>= d * 4)
+  __shared__ int next_item[NTEAMS][2];          // the team's current item, double-buffered across iterations
   constexpr int RING_B = NG * GS * ROW_B;
   constexpr int TEAM_B = RING_B * (FUSE_DW ? 2 : 1);
   extern __shared__ __align__(128) uint8_t smem[];
@@ -422,7 +433,14 @@ __global__ void __launch_bounds__(NTEAMS * T * 32, 1)
     ok[k] = col[k] < d;
   }
 
-  for (int item = blockIdx.x * NTEAMS + team; item < n_items; item += gridDim.x * NTEAMS) {
+  // dynamic work distribution (see k_block_stg): the leader takes the team's next item from the global counter, the
+  // T warps meet at one named barrier per item (slot it & 1 cannot be overwritten before every warp has passed the
+  // following barrier)
+  for (int it = 0;; ++it) {
+    if (sw == 0 && lane == 0) next_item[team][it & 1] = atomicAdd(next_unit, 1);
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(T * 32) : "memory");
+    const int item = next_item[team][it & 1];
+    if (item >= n_items) break;
     const int4 itv = __ldg(reinterpret_cast<const int4*>(items) + item);
     const int beg = itv.x, n = itv.y - itv.x, w = itv.z;
     const int ng = (n + GS - 1) / GS;
@@ -594,6 +612,23 @@ __global__ void __launch_bounds__(NTEAMS * T * 32, 1)
   }
 }
 
+// One zeroed int per launch for the dynamic work distribution: a ring of 256 counters per device, the launch takes the
+// next slot and clears it on its own stream (stream-ordered before the kernel).  Launches of this library that are
+// concurrently in flight on different streams therefore never share a counter unless more than 256 are pending.
+int* next_counter_slot(cudaStream_t st) {
+  static int* ring[64] = {nullptr};
+  static unsigned cursor[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!ring[dev] && cudaMalloc((void**)&ring[dev], 256 * sizeof(int)) != cudaSuccess) {
+    ring[dev] = nullptr;
+    return nullptr;
+  }
+  int* slot = ring[dev] + (cursor[dev]++ & 255u);
+  if (cudaMemsetAsync(slot, 0, sizeof(int), st) != cudaSuccess) return nullptr;
+  return slot;
+}
+
 template <int S, int NV, bool FUSE, bool TAIL, int T, int NTEAMS, int NG, int GS>
 int launch_team_t(const WorkItem* items, int n_items, const int32_t* r_row, const int32_t* r_nbr, const float* r_norm,
                   const float* X, int ldx, int d, const float* Wt, float* out, const float* Hrow, int ldh, float* dWt,
@@ -615,7 +650,13 @@ int launch_team_t(const WorkItem* items, int n_items, const int32_t* r_row, cons
   if (const char* e = std::getenv("RGCN_STG_SMS")) sms = std::max(1, std::min(sms, std::atoi(e)));  // experiment knob
   int grid = std::min((n_items + NTEAMS - 1) / NTEAMS, sms);  // persistent: one CTA per SM
   if (grid < 1) grid = 1;
-  kern<<<grid, NTEAMS * T * 32, smem, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt);
+  int* counter = next_counter_slot(st);
+  if (!counter) {
+    rgcn_set_error("staged block kernel: cannot allocate the work counter");
+    return RGCN_ERR_CUDA;
+  }
+  kern<<<grid, NTEAMS * T * 32, smem, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt,
+                                            counter);
   ++g_rgcn_launches;
   return rgcn_check_cuda(cudaGetLastError(), "k_block_team");
 }
@@ -643,7 +684,13 @@ int launch_stg_t(const WorkItem* items, int n_items, const int32_t* r_row, const
   if (const char* e = std::getenv("RGCN_STG_SMS")) sms = std::max(1, std::min(sms, std::atoi(e)));  // experiment knob
   int grid = (int)std::min<int64_t>((units + NW - 1) / NW, sms);  // persistent: one CTA per SM
   if (grid < 1) grid = 1;
-  kern<<<grid, NW * 32, smem, st>>>(items, n_items, n_slabs, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt);
+  int* counter = next_counter_slot(st);
+  if (!counter) {
+    rgcn_set_error("staged block kernel: cannot allocate the work counter");
+    return RGCN_ERR_CUDA;
+  }
+  kern<<<grid, NW * 32, smem, st>>>(items, n_items, n_slabs, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt,
+                                    counter);
   ++g_rgcn_launches;
   return rgcn_check_cuda(cudaGetLastError(), "k_block_stg");
 }

@@ -62,21 +62,6 @@ int launch_block_relayout(const float* Wf, const float* Wb, int R, int B, int s,
 int launch_block_unlayout(const float* dWt, int R, int B, int s, float* dWf, float* dWb,
                           int accumulate, int table_t, cudaStream_t st);
 
-// EXPERIMENTAL component-major path for 5x5 blocks (block_cm.cu; block_algo = 2, not yet validated on a GPU).
-// Rows in the component-major layout store element (block b, component i) at position i*B + b.
-bool block_cm_supported(int d, int s);
-int launch_to_cm(const float* X, int64_t rows, int B, int s, float* Xc, cudaStream_t st);
-// out[row][b*s+i] = act(out[row][b*s+i] + Mc[row][i*B+b])
-int launch_cm_add(const float* Mc, int64_t rows, int B, int s, int relu, float* out, cudaStream_t st);
-// Wc[w][a][c][b] = W[w][b][a][c] (transpose = 0) or W[w][b][c][a] (transpose = 1)
-int launch_relayout_cm(const float* Wf, const float* Wb, int R, int B, int s, int transpose, float* Wc,
-                       cudaStream_t st);
-int launch_unlayout_cm(const float* dWc, int R, int B, int s, float* dWf, float* dWb, cudaStream_t st);
-// dWc == nullptr: outc[row] += Wc[w] . sum_run(norm * Xc[nbr]);  else: dWc[w] += sum_run(norm * Xc[nbr]) (x) Hc[row]
-int launch_block_cm(const WorkItem* items, int n_items, const int32_t* r_row, const int32_t* r_nbr,
-                    const float* r_norm, const float* Xc, int ldx, int B, int s, const float* Wc, float* outc,
-                    int ldo, const float* Hc, int ldh, float* dWc, cudaStream_t st);
-
 // Basis aggregation: Agg[row][dir][...] = sum_m norm_m * C[relw_m, b] * X[nbr_m, k]
 //   layout 0 (interleaved): index k*B + b      (matches V.reshape(d_in*B, d_out) rows)
 //   layout 1 (planar):      index b*d + k      (matches V.reshape(d_in, B*d_out) columns)

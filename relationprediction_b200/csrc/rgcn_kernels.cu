@@ -377,10 +377,7 @@ __global__ void __launch_bounds__(RGCN_THREADS, 1)
 // by L2-sized supertiles of rows, graph.cu).  Weight traffic drops from d*s*4 bytes per run to
 // d*s*4 bytes per item; the price is a non-deterministic fp32 summation order across items.
 // ------------------------------------------------------------------------------------------------
-// LEAN = true (opt-in, RGCN_LEAN=1; not yet validated on a GPU): lanes past the row end gather a clamped
-// column instead of being predicated off (their weights are zero and they never store) -- the predicated form
-// costs ~4 moves + a zero-init per 128-bit load in SASS.
-template <int S, int NV, bool FUSE_DW, bool LEAN = false>
+template <int S, int NV, bool FUSE_DW>
 __global__ void __launch_bounds__(RGCN_THREADS, (FUSE_DW || S * NV > 16) ? 1 : (S * NV > 8 ? 2 : 3))
     k_block_rel(const WorkItem* __restrict__ items, int n_items, const int32_t* __restrict__ r_row,
                 const int32_t* __restrict__ r_nbr, const float* __restrict__ r_norm,
@@ -493,8 +490,8 @@ __global__ void __launch_bounds__(RGCN_THREADS, (FUSE_DW || S * NV > 16) ? 1 : (
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
           const int lc0 = 4 * (lane + 32 * k);
-          const bool ok = LEAN ? true : c0 + lc0 < d;
-          const int lc = LEAN ? min(lc0, d - 4 - c0) : lc0;
+          const bool ok = c0 + lc0 < d;
+          const int lc = lc0;
           x[u][k] = ok ? ldg4(xr + lc) : zero4();
           if (FUSE_DW)  // the run's own H row travels with the run's first gathered row
             hx[FUSE_DW ? u : 0][k] = (ok && starts[u]) ? ldg4(Hrow + (size_t)rv[u] * ldh + c0 + lc) : zero4();
@@ -541,10 +538,7 @@ __global__ void __launch_bounds__(RGCN_THREADS, (FUSE_DW || S * NV > 16) ? 1 : (
 // row is exchanged through a double-buffered shared-memory row per group and ONE named barrier
 // (bar.sync id, 32*G) per run.
 // ------------------------------------------------------------------------------------------------
-// SEL = true (opt-in, RGCN_LEAN=1; not yet validated on a GPU): a quad's four output columns lie in at most
-// two consecutive blocks, so the S inputs of each of those two blocks are read from shared memory ONCE
-// (2*S LDS instead of 4*S) and routed to the columns with selects -- the kernel is L1-wavefront bound.
-template <int S, int G, bool FUSE_DW, bool SEL = false>
+template <int S, int G, bool FUSE_DW>
 __global__ void __launch_bounds__(RGCN_THREADS, FUSE_DW ? 2 : 3)
     k_block_relg(const WorkItem* __restrict__ items, int n_items, const int32_t* __restrict__ r_row,
                  const int32_t* __restrict__ r_nbr, const float* __restrict__ r_norm,
@@ -578,12 +572,6 @@ __global__ void __launch_bounds__(RGCN_THREADS, FUSE_DW ? 2 : 3)
 #pragma unroll
     for (int c = 0; c < 4; ++c) xo[k][c] = ((colq[k] + c) / S) * S;
   }
-  bool hi[NV][4];  // column c of quad k belongs to the SECOND of the (at most two) blocks the quad touches
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) hi[k][c] = xo[k][c] != xo[k][0];
-  }
   float4 xs[NV], hcur[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) xs[k] = hcur[k] = zero4();
@@ -601,26 +589,10 @@ __global__ void __launch_bounds__(RGCN_THREADS, FUSE_DW ? 2 : 3)
     for (int k = 0; k < NV; ++k) {
       if (colq[k] < d) {
         float4 y = zero4();
-        float xa[S], xh[S];
-        if (SEL) {
-#pragma unroll
-          for (int j = 0; j < S; ++j) {
-            xa[j] = xb[xo[k][0] + j];
-            xh[j] = xb[xo[k][0] + S + j];  // unconditional: stays inside the 512-float buffer (d <= 512 - S), unused unless hi
-          }
-        }
 #pragma unroll
         for (int j = 0; j < S; ++j) {
-          float x0, x1, x2, x3;
-          if (SEL) {
-            x0 = xa[j];
-            x1 = hi[k][1] ? xh[j] : xa[j];
-            x2 = hi[k][2] ? xh[j] : xa[j];
-            x3 = hi[k][3] ? xh[j] : xa[j];
-          } else {
-            x0 = xb[xo[k][0] + j], x1 = xb[xo[k][1] + j];
-            x2 = xb[xo[k][2] + j], x3 = xb[xo[k][3] + j];
-          }
+          const float x0 = xb[xo[k][0] + j], x1 = xb[xo[k][1] + j];
+          const float x2 = xb[xo[k][2] + j], x3 = xb[xo[k][3] + j];
           y.x = fmaf(wreg[j][k].x, x0, y.x);
           y.y = fmaf(wreg[j][k].y, x1, y.y);
           y.z = fmaf(wreg[j][k].z, x2, y.z);
@@ -665,10 +637,8 @@ __global__ void __launch_bounds__(RGCN_THREADS, FUSE_DW ? 2 : 3)
         const float* xr = X + (size_t)src * ldx;
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-          // SEL: lanes past the row end load the row's last quad instead of nothing (their weights are zero and
-          // they never store), which removes the predicated-move scaffolding around every gather
-          const bool ok = SEL ? true : colq[k] < d;
-          const int cq = SEL ? min(colq[k], d - 4) : colq[k];
+          const bool ok = colq[k] < d;
+          const int cq = colq[k];
           x[u][k] = ok ? ldg4(xr + cq) : zero4();
           if (FUSE_DW)
             hx[FUSE_DW ? u : 0][k] = (ok && starts[u]) ? ldg4(Hrow + (size_t)rv[u] * ldh + cq) : zero4();
@@ -1138,21 +1108,16 @@ int launch_block_dw(const WorkItem* items, int n_items, const int32_t* r_dst, co
 }
 
 
-template <int S, int NV, bool FUSE, bool LEAN = false>
+template <int S, int NV, bool FUSE>
 static int launch_block_rel_t(const WorkItem* items, int n_items, const int32_t* r_row,
                               const int32_t* r_nbr, const float* r_norm, const float* X, int ldx,
                               int d, const float* Wt, float* out, const float* Hrow, int ldh,
                               float* dWt, cudaStream_t st) {
   const int slabs = (d + NV * 128 - 1) / (NV * 128);
   dim3 grid((n_items + RGCN_WARPS_PER_BLOCK - 1) / RGCN_WARPS_PER_BLOCK, slabs);
-  k_block_rel<S, NV, FUSE, LEAN><<<grid, RGCN_THREADS, 0, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx,
+  k_block_rel<S, NV, FUSE><<<grid, RGCN_THREADS, 0, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx,
                                                                  d, Wt, out, Hrow, ldh, dWt);
   return check_launch("k_block_rel");
-}
-
-static bool lean_kernels_requested() {  // read per launch so tests can toggle it
-  const char* e = std::getenv("RGCN_LEAN");
-  return e && std::atoi(e) == 1;
 }
 
 bool block_rel_supported(int d, int s) {
@@ -1200,13 +1165,7 @@ int launch_block_rel(const WorkItem* items, int n_items, const int32_t* r_row, c
     if (G == 4 || G == 2) {
       const int groups = RGCN_WARPS_PER_BLOCK / G;
       dim3 grid((n_items + groups - 1) / groups);
-      const bool sel = lean_kernels_requested();
-      if (G == 4 && sel) {
-        if (fuse)
-          k_block_relg<5, 4, true, true><<<grid, RGCN_THREADS, 0, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt);
-        else
-          k_block_relg<5, 4, false, true><<<grid, RGCN_THREADS, 0, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt);
-      } else if (G == 4) {
+      if (G == 4) {
         if (fuse)
           k_block_relg<5, 4, true><<<grid, RGCN_THREADS, 0, st>>>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt);
         else
@@ -1223,13 +1182,6 @@ int launch_block_rel(const WorkItem* items, int n_items, const int32_t* r_row, c
   } else if (s == 4) {
     switch (nv) { case 1: RL(4, 1); case 2: RL(4, 2); case 3: RL(4, 3); default: RL(4, 4); }
   } else if (s == 8) {
-    if (lean_kernels_requested()) {
-      if (nv == 1)
-        return fuse ? launch_block_rel_t<8, 1, true, true>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt, st)
-                    : launch_block_rel_t<8, 1, false, true>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt, st);
-      return fuse ? launch_block_rel_t<8, 2, true, true>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt, st)
-                  : launch_block_rel_t<8, 2, false, true>(items, n_items, r_row, r_nbr, r_norm, X, ldx, d, Wt, out, Hrow, ldh, dWt, st);
-    }
     if (nv == 1) RL(8, 1);
     RL(8, 2);
   } else if (s == 16) {

@@ -34,6 +34,10 @@ def _worker(rank, world, port, V, R, E, d, B, out_dir, mode):
         tr = synthetic_kg(V, R, E, seed=5, skewed=True)
         if mode == "feature":
             sg = p = parallel.FeatureShardedGraph(tr, V, R, rank, world, dev, B, d // B)
+        elif mode == "device-plan":   # edge list on the GPU: ShardPlanDevice + rgcn_graph_create_messages_device
+            sg = parallel.ShardedGraph(torch.from_numpy(tr).to(dev), V, R, rank, world, dev)
+            assert isinstance(sg.plan, parallel.ShardPlanDevice) and sg.graph is None
+            p = sg.plan
         else:
             sg = parallel.ShardedGraph(tr, V, R, rank, world, dev, overlap=(mode != "plain"),
                                        pipelined=(mode == "pipelined"))
@@ -57,7 +61,7 @@ def _worker(rank, world, port, V, R, E, d, B, out_dir, mode):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["pipelined", "overlapped", "plain", "feature"])
+@pytest.mark.parametrize("mode", ["device-plan", "pipelined", "overlapped", "plain", "feature"])
 @pytest.mark.parametrize("world", [2, 4])
 def test_sharded_block_layer_equals_single_gpu(tmp_path, world, mode):
     if torch.cuda.device_count() < world:

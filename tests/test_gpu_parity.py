@@ -14,17 +14,15 @@ from conftest import synthetic_kg
 
 pytestmark = pytest.mark.gpu
 
-# kernels written without GPU access run only on request (scripts/gpu_ab_lean.sh): a faulting kernel would poison
-# the CUDA context for every later test of the process
-experimental = pytest.mark.skipif(os.environ.get("RGCN_RUN_EXPERIMENTAL") != "1",
-                                  reason="set RGCN_RUN_EXPERIMENTAL=1 to run the not-yet-validated kernels")
 TOL = 1e-4
 DEV = "cuda:0"
 
 
-@pytest.fixture(params=[0, 1], ids=["dst-major", "rel-major"], autouse=True)
+@pytest.fixture(params=[0, 1, 3], ids=["dst-major", "rel-major", "staged"], autouse=True)
 def block_algo(request):
-    """Every test runs under both aggregation algorithms (rgcn_set_option "block_algo")."""
+    """Every test runs under the three aggregation algorithms (rgcn_set_option "block_algo"): deterministic
+    destination-major, weight-id-major with rows in registers, weight-id-major with TMA-staged rows (falls back to the
+    register path for block sizes the staged kernels do not cover)."""
     _lib.set_option("block_algo", request.param)
     yield request.param
     _lib.set_option("block_algo", -1)
@@ -113,48 +111,6 @@ BLOCK_CASES = [
 @pytest.mark.parametrize("V,R,E,d,B,skewed,drop", BLOCK_CASES)
 def test_block_layer_fwd_bwd_vs_oracle(V, R, E, d, B, skewed, drop):
     tr = synthetic_kg(V, R, E, seed=11, skewed=skewed)
-    rng = np.random.RandomState(5)
-    H = rng.normal(0, 1, (V, d)).astype(np.float32)
-    dOut = rng.normal(0, 1, (V, d)).astype(np.float32)
-    w = oracle.init_block_layer(rng, R, d, B)
-    mask = (rng.uniform(size=(V, d)) < 0.8).astype(np.uint8) if drop else None
-    keep = 0.8 if drop else 1.0
-    nf, nb = oracle.graph_norms(tr, V)
-    ref_out, ref_g = oracle.layer_fwd_bwd("block", H, tr, w, nf, nb, dOut, mask, keep, True, torch.float64)
-    out, grads = run_block(tr, V, R, d, B, H, w, dOut, mask, keep, True)
-    assert_close("out", out, ref_out.numpy())
-    for k in ("H", "W_forward", "W_backward", "W_self"):
-        assert_close("d" + k, grads[k], ref_g[k].numpy())
-
-
-@experimental
-@pytest.mark.xfail(reason="opt-in lean kernels (RGCN_LEAN=1; s=5 group kernel, s=8 rel-major) written without GPU access: "
-                          "reports XPASS once it is validated, never blocks the suite", strict=False)
-@pytest.mark.parametrize("d,B", [(500, 100), (40, 8), (260, 52), (512, 64), (200, 25)])
-def test_lean_group_kernel_opt_in(monkeypatch, d, B):
-    monkeypatch.setenv("RGCN_LEAN", "1")
-    V, R, E = 1500, 23, 12000
-    tr = synthetic_kg(V, R, E, seed=11, skewed=True)
-    rng = np.random.RandomState(5)
-    H = rng.normal(0, 1, (V, d)).astype(np.float32)
-    dOut = rng.normal(0, 1, (V, d)).astype(np.float32)
-    w = oracle.init_block_layer(rng, R, d, B)
-    nf, nb = oracle.graph_norms(tr, V)
-    ref_out, ref_g = oracle.layer_fwd_bwd("block", H, tr, w, nf, nb, dOut, None, 1.0, True, torch.float64)
-    out, grads = run_block(tr, V, R, d, B, H, w, dOut, None, 1.0, True)
-    assert_close("out", out, ref_out.numpy())
-    for k in ("H", "W_forward", "W_backward", "W_self"):
-        assert_close("d" + k, grads[k], ref_g[k].numpy())
-
-
-@experimental
-@pytest.mark.xfail(reason="experimental component-major path (RGCN_BLOCK_ALGO=2, csrc/block_cm.cu) written without "
-                          "GPU access: reports XPASS once it is validated, never blocks the suite", strict=False)
-@pytest.mark.parametrize("d,B,drop", [(500, 100, False), (500, 100, True), (40, 8, False), (260, 52, True)])
-def test_component_major_path_opt_in(monkeypatch, d, B, drop):
-    monkeypatch.setenv("RGCN_BLOCK_ALGO", "2")
-    V, R, E = 1500, 23, 12000
-    tr = synthetic_kg(V, R, E, seed=11, skewed=True)
     rng = np.random.RandomState(5)
     H = rng.normal(0, 1, (V, d)).astype(np.float32)
     dOut = rng.normal(0, 1, (V, d)).astype(np.float32)
