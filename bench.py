@@ -326,6 +326,9 @@ def main():
     ap.add_argument("--shard", choices=["node", "feature"], default="node",
                     help="N > 1: 1-D node shard with halo all-to-all (default, north_star) or the experimental "
                          "feature-sharded message passing (replicated graph, two transposes per layer)")
+    ap.add_argument("--halo", choices=["overlapped", "pipelined"], default="overlapped",
+                    help="N > 1, node shard: one all-to-all per layer direction overlapped with the local-source work "
+                         "(default) or the per-peer ring that aggregates peer k's rows while peer k+1's are in flight")
     ap.add_argument("--triples-npz", default=None,
                     help="use the triples of this .npz (arrays: triples [E,3], V, R) instead of the synthetic generator; "
                          "diagnostic only (e.g. the real FB15k-237 graph), the default bench stays synthetic")
@@ -385,7 +388,7 @@ def main():
             layer = parallel.FeatureShardedGraph(tri_dev.cpu().numpy(), V, R, rank, world, dev, B, s)
             graph = layer.graph
         else:
-            layer = parallel.ShardedGraph(tri_dev, V, R, rank, world, dev)
+            layer = parallel.ShardedGraph(tri_dev, V, R, rank, world, dev, pipelined=(args.halo == "pipelined"))
             graph = layer.graph_local
         V_loc = layer.n_local
     torch.cuda.synchronize()
@@ -667,7 +670,7 @@ def main():
                            "l2": "flushed between timed iterations (256 MB memset outside the event pair); inputs are "
                                  "%.0f MB per matrix" % (V_loc * d * 4 / 1e6),
                            "parallelism": ("%s x%d%s" % ("feature-shard (experimental)" if args.shard == "feature"
-                                                         else "1d-node-shard", world,
+                                                         else "1d-node-shard (%s halo exchange)" % args.halo, world,
                                                          " of the same graph" if strong else " (graph grows with N)"))
                            if world > 1 else "single",
                            "messages": info[0], "block_algo": os.environ.get("RGCN_BLOCK_ALGO", "auto")},

@@ -194,45 +194,61 @@ __global__ void __launch_bounds__(N_THREADS, 1)
                    : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    float4 vcur[BM / 32], vnext[BM / 32];
-    mbar_wait(&empty_bar[0], 1u);
-    issue_b(0);
-    load_a(0, vcur);
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % STAGES;
-      const bool more = kb + 1 < num_kb;
-      if (more) {
-        const int s1 = (kb + 1) % STAGES;
-        const uint32_t ph1 = (uint32_t)((kb + 1) / STAGES) & 1u;
-        mbar_wait(&empty_bar[s1], ph1 ^ 1u);
-        issue_b(kb + 1);
-        load_a(kb + 1, vnext);
+    // PF k-blocks of A are in flight in registers (and of B as asynchronous copies) while block kb is converted and
+    // stored.  Round 1 prefetched ONE block: ncu showed the producers parked on their own global loads
+    // (long-scoreboard 4.0 of 9 warps, tensor pipe 31-35 % active) -- 16 KB in flight per SM cannot cover the
+    // HBM/L2 latency at the 40 GB/s per SM the MMAs consume.
+    constexpr int PF = 2;                    // prefetch distance in k-blocks (PF + 1 register buffers)
+    static_assert(PF + 1 <= STAGES, "B copies of block kb + PF land in the stage that block kb - 1 released");
+    float4 vbuf[PF + 1][BM / 32];
+    for (int p = 0; p < PF; ++p) {
+      if (p < num_kb) {
+        mbar_wait(&empty_bar[p % STAGES], 1u);   // first use of every stage: the "previous phase" is complete
+        issue_b(p);
+        load_a(p, vbuf[p]);
       }
-      const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES;
+    }
+    for (int kb0 = 0; kb0 < num_kb; kb0 += PF + 1) {
 #pragma unroll
-      for (int i = 0; i < BM / 32; ++i) {
-        const int r = rbase + 32 * i;
-        float4 hi, lo;
-        split_tf32(vcur[i].x, hi.x, lo.x);
-        split_tf32(vcur[i].y, hi.y, lo.y);
-        split_tf32(vcur[i].z, hi.z, lo.z);
-        split_tf32(vcur[i].w, hi.w, lo.w);
-        const uint32_t o = swz(r, c);
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + o), "f"(hi.x), "f"(hi.y),
-                     "f"(hi.z), "f"(hi.w)
-                     : "memory");
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + o), "f"(lo.x), "f"(lo.y),
-                     "f"(lo.z), "f"(lo.w)
-                     : "memory");
+      for (int u = 0; u <= PF; ++u) {
+        const int kb = kb0 + u;
+        if (kb >= num_kb) break;
+        const int s = kb % STAGES;
+        if (kb + PF < num_kb) {
+          const int s1 = (kb + PF) % STAGES;
+          const uint32_t ph1 = (uint32_t)((kb + PF) / STAGES) & 1u;
+          mbar_wait(&empty_bar[s1], ph1 ^ 1u);
+          issue_b(kb + PF);
+          load_a(kb + PF, vbuf[(u + PF) % (PF + 1)]);
+        }
+        const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES;
+#pragma unroll
+        for (int i = 0; i < BM / 32; ++i) {
+          const int r = rbase + 32 * i;
+          float4 hi, lo;
+          split_tf32(vbuf[u][i].x, hi.x, lo.x);
+          split_tf32(vbuf[u][i].y, hi.y, lo.y);
+          split_tf32(vbuf[u][i].z, hi.z, lo.z);
+          split_tf32(vbuf[u][i].w, hi.w, lo.w);
+          const uint32_t o = swz(r, c);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + o), "f"(hi.x), "f"(hi.y),
+                       "f"(hi.z), "f"(hi.w)
+                       : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + o), "f"(lo.x), "f"(lo.y),
+                       "f"(lo.z), "f"(lo.w)
+                       : "memory");
+        }
+        // B(kb) has landed; the copies of the (up to PF) later blocks may still fly
+        const int later = min(PF, num_kb - 1 - kb);
+        if (later >= 2)
+          asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (later == 1)
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core
+        mbar_arrive(&full_bar[s]);
       }
-      if (more)
-        asm volatile("cp.async.wait_group 1;" ::: "memory");  // B(kb) has landed, B(kb+1) may still fly
-      else
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core
-      mbar_arrive(&full_bar[s]);
-#pragma unroll
-      for (int i = 0; i < BM / 32; ++i) vcur[i] = vnext[i];
     }
     // ================= epilogue =================
     mbar_wait(&accum_bar, 0);
@@ -429,45 +445,49 @@ __global__ void __launch_bounds__(N_THREADS, 1)
                     : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    float4 va[4], vb[4], van[4], vbn[4];
-    load_ab(0, va, vb);
-    for (int kbi = 0; kbi < num_kb; ++kbi) {
-      const int s = kbi % STAGES;
-      const uint32_t ph = (uint32_t)(kbi / STAGES) & 1u;
-      if (kbi + 1 < num_kb) load_ab(kbi + 1, van, vbn);
-      mbar_wait(&empty_bar[s], ph ^ 1u);
-      const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES;
-      const uint32_t b_hi = a_lo + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
+    // PF k-blocks of both operands in flight in registers (see the NT kernel: one block of prefetch left the
+    // producers latency-bound)
+    constexpr int PF = 2;
+    float4 va[PF + 1][4], vb[PF + 1][4];
+    for (int p = 0; p < PF; ++p)
+      if (p < num_kb) load_ab(p, va[p], vb[p]);
+    for (int kb0 = 0; kb0 < num_kb; kb0 += PF + 1) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int kr = tid >> 3, cm = 8 * i + (tid & 7);
-        const int c8 = cm & 7;  // 16 B chunk within the 128 B row: 32 B chunk (c8 >> 1) is swizzled with k & 3
-        const uint32_t off = (uint32_t)((cm >> 3) * 4096 + (kr >> 2) * 512 + (kr & 3) * 128 +
-                                        ((((c8 >> 1) ^ (kr & 3)) << 5) | ((c8 & 1) << 4)));
-        float4 hi, lo;
-        split_tf32(va[i].x, hi.x, lo.x);
-        split_tf32(va[i].y, hi.y, lo.y);
-        split_tf32(va[i].z, hi.z, lo.z);
-        split_tf32(va[i].w, hi.w, lo.w);
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "f"(hi.x), "f"(hi.y),
-                     "f"(hi.z), "f"(hi.w) : "memory");
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "f"(lo.x), "f"(lo.y),
-                     "f"(lo.z), "f"(lo.w) : "memory");
-        split_tf32(vb[i].x, hi.x, lo.x);
-        split_tf32(vb[i].y, hi.y, lo.y);
-        split_tf32(vb[i].z, hi.z, lo.z);
-        split_tf32(vb[i].w, hi.w, lo.w);
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(b_hi + off), "f"(hi.x), "f"(hi.y),
-                     "f"(hi.z), "f"(hi.w) : "memory");
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(b_lo + off), "f"(lo.x), "f"(lo.y),
-                     "f"(lo.z), "f"(lo.w) : "memory");
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(&full_bar[s]);
+      for (int u = 0; u <= PF; ++u) {
+        const int kbi = kb0 + u;
+        if (kbi >= num_kb) break;
+        const int s = kbi % STAGES;
+        const uint32_t ph = (uint32_t)(kbi / STAGES) & 1u;
+        if (kbi + PF < num_kb) load_ab(kbi + PF, va[(u + PF) % (PF + 1)], vb[(u + PF) % (PF + 1)]);
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES;
+        const uint32_t b_hi = a_lo + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        va[i] = van[i];
-        vb[i] = vbn[i];
+        for (int i = 0; i < 4; ++i) {
+          const int kr = tid >> 3, cm = 8 * i + (tid & 7);
+          const int c8 = cm & 7;  // 16 B chunk within the 128 B row: 32 B chunk (c8 >> 1) is swizzled with k & 3
+          const uint32_t off = (uint32_t)((cm >> 3) * 4096 + (kr >> 2) * 512 + (kr & 3) * 128 +
+                                          ((((c8 >> 1) ^ (kr & 3)) << 5) | ((c8 & 1) << 4)));
+          float4 hi, lo;
+          split_tf32(va[u][i].x, hi.x, lo.x);
+          split_tf32(va[u][i].y, hi.y, lo.y);
+          split_tf32(va[u][i].z, hi.z, lo.z);
+          split_tf32(va[u][i].w, hi.w, lo.w);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "f"(hi.x), "f"(hi.y),
+                       "f"(hi.z), "f"(hi.w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "f"(lo.x), "f"(lo.y),
+                       "f"(lo.z), "f"(lo.w) : "memory");
+          split_tf32(vb[u][i].x, hi.x, lo.x);
+          split_tf32(vb[u][i].y, hi.y, lo.y);
+          split_tf32(vb[u][i].z, hi.z, lo.z);
+          split_tf32(vb[u][i].w, hi.w, lo.w);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(b_hi + off), "f"(hi.x), "f"(hi.y),
+                       "f"(hi.z), "f"(hi.w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(b_lo + off), "f"(lo.x), "f"(lo.y),
+                       "f"(lo.z), "f"(lo.w) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&full_bar[s]);
       }
     }
     // epilogue: add this split's tile into C
