@@ -718,9 +718,13 @@ int launch_block_stg(const WorkItem* items, int n_items, const int32_t* r_row, c
   // to 4 warps; shared memory = warps x groups x GS rows x slab bytes, twice that for the fused backward).
   // RGCN_STG_FWD / RGCN_STG_BWD pick among the measured variants of the s = 8 kernels (A/B knobs):
   //   forward  0: 2 quads/lane, 12 warps x 2 groups of 8, TMA     2: 1 quad/lane, 16 warps x 3 groups, TMA
-  //            3: as 2 with cp.async                              4: as 0 with cp.async
-  //   backward 0: 1 quad/lane, 12 warps x 2 groups of 8, TMA      1: as 0 with cp.async
-  //            2: 2 quads/lane, 8 warps x 2 groups of 4, cp.async 3: as 2 with TMA
+  //            3: as 2 with cp.async (default when the team kernel does not apply)
+  //   backward 0: 1 quad/lane, 12 warps x 2 groups of 8, TMA      1: as 0 with cp.async (default)
+  //            3: 2 quads/lane, 8 warps x 2 groups of 4, TMA
+  // NOT offered: 2 quads/lane with cp.async.  ptxas 12.9 miscompiles those instantiations -- the LDGSTS with an L2
+  // cache hint comes out as `[R0+UR0], desc[UR1]` with UR0/UR1 never written, and faults with "illegal
+  // instruction" (compute-sanitizer, round 2); scripts/check_sass_ur.py and tests/test_cabi_host.py scan the built
+  // library for that pattern.
   int fwd_cfg = -1, bwd_cfg = -1;
   if (const char* e = std::getenv("RGCN_STG_FWD")) fwd_cfg = std::atoi(e);
   if (const char* e = std::getenv("RGCN_STG_BWD")) bwd_cfg = std::atoi(e);
@@ -745,18 +749,15 @@ int launch_block_stg(const WorkItem* items, int n_items, const int32_t* r_row, c
   }
   if (s == 4) {
     if (!fuse) {
-      if (d <= 128) STG(4, 1, false, 16, 3, 8, 1);
-      STG(4, 2, false, 12, 2, 8, 1);
+      STG(4, 1, false, 16, 3, 8, 1);
     }
     STG(4, 1, true, 12, 2, 8, 1);
   } else if (s == 8) {
     if (!fuse) {
       if (d <= 128 || fwd_cfg == 2) STG(8, 1, false, 16, 3, 8, 0);
       if (fwd_cfg == 0) STG(8, 2, false, 12, 2, 8, 0);
-      if (fwd_cfg == 4) STG(8, 2, false, 12, 2, 8, 1);
       STG(8, 1, false, 16, 3, 8, 1);
     }
-    if (d > 128 && bwd_cfg == 2) STG(8, 2, true, 8, 2, 4, 1);
     if (d > 128 && bwd_cfg == 3) STG(8, 2, true, 8, 2, 4, 0);
     if (bwd_cfg == 0) STG(8, 1, true, 12, 2, 8, 0);
     STG(8, 1, true, 12, 2, 8, 1);

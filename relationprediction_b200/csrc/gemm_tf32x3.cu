@@ -198,29 +198,29 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     // stored.  Round 1 prefetched ONE block: ncu showed the producers parked on their own global loads
     // (long-scoreboard 4.0 of 9 warps, tensor pipe 31-35 % active) -- 16 KB in flight per SM cannot cover the
     // HBM/L2 latency at the 40 GB/s per SM the MMAs consume.
-    constexpr int PF = 2;                    // prefetch distance in k-blocks (PF + 1 register buffers)
-    static_assert(PF + 1 <= STAGES, "B copies of block kb + PF land in the stage that block kb - 1 released");
+    // (The asynchronous copies of B stay ONE block ahead: they need the shared-memory stage of block kb + 1, and
+    // asking for the stage of kb + 2 would make the producers wait for the MMAs of block kb - 1 before storing block
+    // kb -- measured 8 % slower.  The A rows only need registers, so they run two blocks ahead.)
+    constexpr int PF = 2;                    // register prefetch distance of A in k-blocks (PF + 1 buffers)
     float4 vbuf[PF + 1][BM / 32];
-    for (int p = 0; p < PF; ++p) {
-      if (p < num_kb) {
-        mbar_wait(&empty_bar[p % STAGES], 1u);   // first use of every stage: the "previous phase" is complete
-        issue_b(p);
-        load_a(p, vbuf[p]);
-      }
-    }
+    mbar_wait(&empty_bar[0], 1u);            // first use of a stage: the "previous phase" is complete
+    issue_b(0);
+    for (int p = 0; p < PF; ++p)
+      if (p < num_kb) load_a(p, vbuf[p]);
     for (int kb0 = 0; kb0 < num_kb; kb0 += PF + 1) {
 #pragma unroll
       for (int u = 0; u <= PF; ++u) {
         const int kb = kb0 + u;
         if (kb >= num_kb) break;
         const int s = kb % STAGES;
-        if (kb + PF < num_kb) {
-          const int s1 = (kb + PF) % STAGES;
-          const uint32_t ph1 = (uint32_t)((kb + PF) / STAGES) & 1u;
+        const bool more = kb + 1 < num_kb;
+        if (more) {
+          const int s1 = (kb + 1) % STAGES;
+          const uint32_t ph1 = (uint32_t)((kb + 1) / STAGES) & 1u;
           mbar_wait(&empty_bar[s1], ph1 ^ 1u);
-          issue_b(kb + PF);
-          load_a(kb + PF, vbuf[(u + PF) % (PF + 1)]);
+          issue_b(kb + 1);
         }
+        if (kb + PF < num_kb) load_a(kb + PF, vbuf[(u + PF) % (PF + 1)]);
         const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES;
 #pragma unroll
         for (int i = 0; i < BM / 32; ++i) {
@@ -238,12 +238,8 @@ __global__ void __launch_bounds__(N_THREADS, 1)
                        "f"(lo.z), "f"(lo.w)
                        : "memory");
         }
-        // B(kb) has landed; the copies of the (up to PF) later blocks may still fly
-        const int later = min(PF, num_kb - 1 - kb);
-        if (later >= 2)
-          asm volatile("cp.async.wait_group 2;" ::: "memory");
-        else if (later == 1)
-          asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (more)
+          asm volatile("cp.async.wait_group 1;" ::: "memory");  // B(kb) has landed, B(kb+1) may still fly
         else
           asm volatile("cp.async.wait_group 0;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core

@@ -146,3 +146,17 @@ def test_next_row_entry_points_reject_bad_arguments_without_a_gpu():
     assert lib.rgcn_sampler_draw(h, 2, 1, ctypes.c_void_p(out.ctypes.data)) == 0 and sorted(out[:2].tolist()) == [0, 1]
     lib.rgcn_sampler_destroy(h)
     lib.rgcn_sampler_destroy(None)
+
+
+def test_built_library_has_no_async_copy_on_undefined_uniform_registers():
+    """ptxas 12.9 once emitted LDGSTS (cp.async + L2 cache hint) reading uniform registers no instruction writes; the
+    kernel faulted with 'illegal instruction' on the GPU.  scripts/check_sass_ur.py scans the built .so for it."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import check_sass_ur
+    _lib.load()
+    n, bad = check_sass_ur.check(_lib.LIB_PATH)
+    assert n > 50 and not bad, bad
