@@ -197,6 +197,7 @@ def main(argv=None):
     ap.add_argument("--set", action="append", default=[], metavar="Section.Key=Value",
                     help="override one settings entry after the file is read, e.g. "
                          "--set Encoder.NumberOfBasisFunctions=2 (repeatable)")
+    ap.add_argument("--seed", type=int, default=None, help="seed numpy / torch (initial weights, samplers, dropout)")
     ap.add_argument("--dense-clip-norm", action="store_true",
                     help="clip by the norm of the summed dense gradients instead of the reference's IndexedSlices norm "
                          "(tf.clip_by_global_norm over un-aggregated per-edge slices of embedding_lookup variables)")
@@ -208,6 +209,10 @@ def main(argv=None):
     if (args.dataset is None) == (args.dataset_npz is None):
         ap.error("give exactly one of --dataset / --dataset-npz")
 
+    if args.seed is not None:
+        import torch
+        np.random.seed(args.seed)
+        torch.manual_seed(args.seed)
     settings = settings_reader.read(args.settings)
     for item in args.set:
         # dotted path into nested sections: Optimizer.Algorithm.learning_rate=0.005 reaches [Algorithm] inside
