@@ -232,6 +232,11 @@ int rgcn_block_aggregate_backward(const rgcn_graph_t* g, int32_t d, int32_t B, c
                                   float* dWf, float* dWb, int accumulate_dW, void* workspace,
                                   int64_t workspace_bytes, void* stream);
 
+/* dst[rows[i], :] += src[i, :] for i < n, rows (int64, device) UNIQUE within the call -- no atomics.  The
+ * node-sharded path returns halo gradients grouped by peer; a local row gets at most one contribution per peer,
+ * so each peer segment is one call (replaces an atomic index_add over 16 GB per rank at 8 GPUs). */
+int rgcn_rows_add(float* dst, const int64_t* rows, const float* src, int64_t n, int32_t d, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Basis-decomposition R-GCN layer ("BasisGcn", encoders/message_gcns/gcn_basis.py:39-88).
  *

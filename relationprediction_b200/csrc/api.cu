@@ -576,6 +576,15 @@ extern "C" int rgcn_block_aggregate_backward(const rgcn_graph_t* g, int32_t d, i
   return launch_block_unlayout(dWt, R, B, s, dWf, dWb, accumulate_dW, fused ? 1 : 0, st);
 }
 
+// dst[rows[i], :] += src[i, :] (rows unique): unpack of the returned halo gradients, one peer segment per call
+extern "C" int rgcn_rows_add(float* dst, const int64_t* rows, const float* src, int64_t n, int32_t d, void* stream) {
+  if (n < 0 || d <= 0 || d % 4 != 0 || (n > 0 && (!dst || !rows || !src))) {
+    rgcn_set_error("rgcn_rows_add: bad arguments (d % 4 == 0)");
+    return RGCN_ERR_INVALID;
+  }
+  return launch_rows_add(dst, rows, src, n, d, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Basis layer
 // ------------------------------------------------------------------------------------------------

@@ -88,6 +88,8 @@ int launch_grad_prologue(const float* dOut, const float* out, const uint8_t* mas
 // x = x * mask * inv_keep (if mask) ; x = relu(x) (if relu)
 int launch_mask_relu(float* x, const uint8_t* mask, float inv_keep, int relu, int64_t n,
                      cudaStream_t st);
+// dst[rows[i], :] += src[i, :], rows unique within the call
+int launch_rows_add(float* dst, const int64_t* rows, const float* src, int64_t n, int d, cudaStream_t st);
 // zero rows listed in `rows` of a [*, width] matrix
 int launch_zero_rows(float* A, int64_t width, const int32_t* rows, int n_rows, cudaStream_t st);
 

@@ -1007,6 +1007,27 @@ __global__ void k_mask_relu(float* __restrict__ x, const uint8_t* __restrict__ m
   }
 }
 
+// dst[rows[i], :] += src[i, :]  for UNIQUE rows (no atomics): the halo-gradient return of the node-sharded path, one
+// peer segment per call (a row receives at most one contribution per peer)
+__global__ void __launch_bounds__(256)
+    k_rows_add(float* __restrict__ dst, const int64_t* __restrict__ rows, const float* __restrict__ src, int64_t n,
+               int d4) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t i = (int64_t)blockIdx.x * 8 + warp; i < n; i += (int64_t)gridDim.x * 8) {
+    float4* pd = reinterpret_cast<float4*>(dst) + (size_t)__ldg(rows + i) * d4;
+    const float4* ps = reinterpret_cast<const float4*>(src) + (size_t)i * d4;
+    for (int k = lane; k < d4; k += 32) {
+      const float4 a = __ldcs(ps + k);
+      float4 b = pd[k];
+      b.x += a.x;
+      b.y += a.y;
+      b.z += a.z;
+      b.w += a.w;
+      pd[k] = b;
+    }
+  }
+}
+
 __global__ void k_zero_rows(float* __restrict__ A, int64_t width4, const int32_t* __restrict__ rows,
                             int n_rows) {
   const int r = blockIdx.x;
@@ -1285,4 +1306,12 @@ int launch_zero_rows(float* A, int64_t width, const int32_t* rows, int n_rows, c
   if (n_rows == 0) return RGCN_OK;
   k_zero_rows<<<n_rows, 256, 0, st>>>(A, width / 4, rows, n_rows);
   return check_launch("k_zero_rows");
+}
+
+int launch_rows_add(float* dst, const int64_t* rows, const float* src, int64_t n, int d, cudaStream_t st) {
+  if (n == 0) return RGCN_OK;
+  int64_t b = (n + 7) / 8;
+  if (b > 148 * 16) b = 148 * 16;
+  k_rows_add<<<(int)b, 256, 0, st>>>(dst, rows, src, n, d / 4);
+  return check_launch("k_rows_add");
 }

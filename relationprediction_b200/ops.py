@@ -408,6 +408,18 @@ def gemm_tn_tf32x3(A, B, out=None, accumulate=False):
     return out
 
 
+def rows_add_(dst, rows, src):
+    """dst[rows[i]] += src[i] for UNIQUE rows (rgcn_rows_add): the non-atomic unpack of one peer's halo gradients."""
+    lib = _lib.load()
+    _check_cuda_f32("dst", dst)
+    _check_cuda_f32("src", src)
+    if not (rows.is_cuda and rows.dtype == torch.int64 and rows.is_contiguous() and rows.numel() == src.shape[0]):
+        raise _lib.RgcnError("rows must be a contiguous CUDA int64 tensor with one entry per row of src")
+    _lib.check(lib.rgcn_rows_add(_ptr(dst), _ptr(rows), _ptr(src), src.shape[0], dst.shape[1], _stream(dst.device)),
+               "rgcn_rows_add")
+    return dst
+
+
 def block_aggregate_(out, X, W_forward, W_backward, graph, n_blocks):
     """out[dst] += sum_m norm_m W[relw_m] . X[src_m] (messages only, in place; rgcn_block_aggregate)."""
     lib = _lib.load()

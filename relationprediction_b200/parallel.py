@@ -152,6 +152,19 @@ class ShardPlanDevice(object):
         self.send_rows = (keys % n_nodes) - lo                  # int64, grouped by peer, ascending id inside
 
 
+def _unpack_add(dH, sg, back):
+    """dH[send_rows] += back.  `back` is grouped by peer and a peer's rows are unique, so on the GPU each peer segment is
+    one non-atomic row-add kernel (rgcn_rows_add); elsewhere (CPU tests) torch's index_add_."""
+    if dH.is_cuda and back.dtype == torch.float32:
+        for q in range(len(sg.send_off) - 1):
+            a, b = sg.send_off[q], sg.send_off[q + 1]
+            if b > a:
+                ops.rows_add_(dH, sg.send_rows[a:b], back[a:b])
+    else:
+        dH.index_add_(0, sg.send_rows, back)
+    return dH
+
+
 class _HaloExchange(torch.autograd.Function):
     """H_local [n_local,d] -> H_ext [n_local+n_halo,d]; backward returns halo gradients to their owners."""
 
@@ -240,7 +253,7 @@ class _OverlappedBlockLayer(torch.autograd.Function):
         dWf += dWf_l
         dWb += dWb_l
         work.wait()
-        dH.index_add_(0, sg.send_rows, back)
+        _unpack_add(dH, sg, back)
         return dH, dWf, dWb, dWs, None, None, None, None, None
 
 
@@ -346,7 +359,7 @@ class _PipelinedBlockLayer(torch.autograd.Function):
         for wk in works:
             for w in wk:
                 w.wait()
-        dH.index_add_(0, sg.send_rows, back)
+        _unpack_add(dH, sg, back)
         return dH, dWf_l, dWb_l, dWs, None, None, None, None, None
 
 
