@@ -259,7 +259,7 @@ def relerr(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 
-def parity_check_sharded(rank, world, dev, B, d, R):
+def parity_check_sharded(rank, world, dev, B, d, R, transport=None):
     """N > 1: a small graph through the SAME sharded code path (device plan, overlapped halo exchange, gradient
     all-reduce) against the single-GPU layer computed on rank 0.  The driver's GPU test box has one GPU, so this is
     where the 4- and 8-rank equivalence is verified every time the scaling bench runs."""
@@ -276,7 +276,7 @@ def parity_check_sharded(rank, world, dev, B, d, R):
     dOut = torch.randn(V, d, device=dev, generator=gen)
     ws = [torch.randn(R, B, s, s, device=dev, generator=gen) * 0.2, torch.randn(R, B, s, s, device=dev, generator=gen) * 0.2,
           torch.randn(d, d, device=dev, generator=gen) * 0.05]
-    sg = parallel.ShardedGraph(tri, V, R, rank, world, dev)
+    sg = parallel.ShardedGraph(tri, V, R, rank, world, dev, transport=transport)
     p = sg.plan
     Hl = H[p.lo:p.hi].clone().requires_grad_(True)
     wl = [w.clone().requires_grad_(True) for w in ws]
@@ -302,7 +302,8 @@ def parity_check_sharded(rank, world, dev, B, d, R):
         errs = {"out": relerr(out_all, o1.detach()), "dH": relerr(dh_all, H1.grad),
                 "dW_forward": relerr(wl[0].grad, w1[0].grad), "dW_backward": relerr(wl[1].grad, w1[1].grad),
                 "dW_self": relerr(wl[2].grad, w1[2].grad)}
-        res = {"what": "sharded (this N) vs single-GPU layer on rank 0, skewed KG V=%d E=%d d=%d B=%d" % (V, E, d, B),
+        res = {"what": "sharded (this N, %s transport) vs single-GPU layer on rank 0, skewed KG V=%d E=%d d=%d B=%d"
+                       % (sg.halo_transport() or "nccl", V, E, d, B),
                "max_rel_err": max(errs.values()), "rel_err": errs, "tolerance": 1e-5,
                "ok": bool(max(errs.values()) <= 1e-5)}
     dist.barrier()
@@ -329,6 +330,10 @@ def main():
     ap.add_argument("--halo", choices=["overlapped", "pipelined"], default="overlapped",
                     help="N > 1, node shard: one all-to-all per layer direction overlapped with the local-source work "
                          "(default) or the per-peer ring that aggregates peer k's rows while peer k+1's are in flight")
+    ap.add_argument("--transport", choices=["auto", "peer", "nccl"], default="auto",
+                    help="N > 1, overlapped halo exchange: 'peer' = rows pushed into peer-mapped halo buffers by "
+                         "rgcn_rows_gather over NVLink, 'nccl' = packed rows + all-to-all; auto = peer, NCCL when "
+                         "symmetric memory cannot be set up")
     ap.add_argument("--triples-npz", default=None,
                     help="use the triples of this .npz (arrays: triples [E,3], V, R) instead of the synthetic generator; "
                          "diagnostic only (e.g. the real FB15k-237 graph), the default bench stays synthetic")
@@ -388,7 +393,8 @@ def main():
             layer = parallel.FeatureShardedGraph(tri_dev.cpu().numpy(), V, R, rank, world, dev, B, s)
             graph = layer.graph
         else:
-            layer = parallel.ShardedGraph(tri_dev, V, R, rank, world, dev, pipelined=(args.halo == "pipelined"))
+            layer = parallel.ShardedGraph(tri_dev, V, R, rank, world, dev, pipelined=(args.halo == "pipelined"),
+                                          transport=None if args.transport == "auto" else args.transport)
             graph = layer.graph_local
         V_loc = layer.n_local
     torch.cuda.synchronize()
@@ -548,7 +554,8 @@ def main():
     parity = None
     if world > 1 and args.shard == "node" and not args.no_parity_check:
         try:
-            parity = parity_check_sharded(rank, world, dev, B, d, R)
+            parity = parity_check_sharded(rank, world, dev, B, d, R,
+                                          transport=None if args.transport == "auto" else args.transport)
         except Exception as exc:  # noqa: BLE001  (every rank takes the same path: the check has no data-dependent branch)
             parity = {"error": repr(exc)}
         sync_all()
@@ -624,7 +631,7 @@ def main():
                "d2h_bytes_per_step": int(d2h) * world, "ms_per_step": e2e_ms, "steps": n_e2e,
                "what": ("pinned host buffers every step: triples -> GPU graph prep || H2D(H, dOut) -> fwd -> bwd || "
                         "D2H(out) -> D2H(dH, dW*); one device sync at the end") if world == 1 else
-                       ("per rank: pinned host H/dOut shard -> H2D -> sharded fwd+bwd (halo all-to-all, grad all-reduce) "
+                       ("per rank: pinned host H/dOut shard -> H2D -> sharded fwd+bwd (halo exchange, grad all-reduce) "
                         "-> D2H(out, dH shard, dW*); the shard plan + graph handles are built once (graph prep per step is "
                         "measured in the single-GPU e2e)")}
         if prep_times:
@@ -670,7 +677,9 @@ def main():
                            "l2": "flushed between timed iterations (256 MB memset outside the event pair); inputs are "
                                  "%.0f MB per matrix" % (V_loc * d * 4 / 1e6),
                            "parallelism": ("%s x%d%s" % ("feature-shard (experimental)" if args.shard == "feature"
-                                                         else "1d-node-shard (%s halo exchange)" % args.halo, world,
+                                                         else "1d-node-shard (%s halo exchange, %s transport)" %
+                                                         (args.halo, getattr(layer, "halo_transport", lambda: None)()
+                                                          or "nccl"), world,
                                                          " of the same graph" if strong else " (graph grows with N)"))
                            if world > 1 else "single",
                            "messages": info[0], "block_algo": os.environ.get("RGCN_BLOCK_ALGO", "auto")},

@@ -237,6 +237,14 @@ int rgcn_block_aggregate_backward(const rgcn_graph_t* g, int32_t d, int32_t B, c
  * so each peer segment is one call (replaces an atomic index_add over 16 GB per rank at 8 GPUs). */
 int rgcn_rows_add(float* dst, const int64_t* rows, const float* src, int64_t n, int32_t d, void* stream);
 
+/* dst[i, :] = src[rows[i], :] for i < n (rows int64, device).  The halo PUSH of the node-sharded path: `dst` may be
+ * (and in that path is) a PEER GPU's buffer mapped into this process (CUDA symmetric / IPC memory), so the rows a
+ * peer needs go from H straight over NVLink into the buffer its aggregation kernel reads -- no packed send buffer,
+ * no all-to-all (the reference has no multi-device path at all: model.py builds one tf.Session graph).
+ * max_ctas > 0 bounds the grid so the push shares the GPU with the layer's local work; 0 = library default. */
+int rgcn_rows_gather(float* dst, const float* src, const int64_t* rows, int64_t n, int32_t d, int32_t max_ctas,
+                     void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Basis-decomposition R-GCN layer ("BasisGcn", encoders/message_gcns/gcn_basis.py:39-88).
  *

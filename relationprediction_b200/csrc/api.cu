@@ -585,6 +585,16 @@ extern "C" int rgcn_rows_add(float* dst, const int64_t* rows, const float* src, 
   return launch_rows_add(dst, rows, src, n, d, (cudaStream_t)stream);
 }
 
+// dst[i, :] = src[rows[i], :]; dst may be peer-mapped memory (halo push over NVLink)
+extern "C" int rgcn_rows_gather(float* dst, const float* src, const int64_t* rows, int64_t n, int32_t d,
+                                int32_t max_ctas, void* stream) {
+  if (n < 0 || d <= 0 || d % 4 != 0 || max_ctas < 0 || (n > 0 && (!dst || !rows || !src))) {
+    rgcn_set_error("rgcn_rows_gather: bad arguments (d % 4 == 0)");
+    return RGCN_ERR_INVALID;
+  }
+  return launch_rows_gather(dst, src, rows, n, d, max_ctas, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Basis layer
 // ------------------------------------------------------------------------------------------------

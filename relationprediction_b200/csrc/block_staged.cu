@@ -63,9 +63,11 @@ __device__ __forceinline__ uint64_t policy_evict_first() {  // gathered rows str
 // Ampere-style asynchronous copy, 16 B per lane (LDGSTS): one instruction moves a 512 B row slab; src_bytes = 0
 // zero-fills the destination (lanes past the row end)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes, uint64_t policy) {
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(src_bytes),
-               "l"(policy)
-               : "memory");
+  // No L2::cache_hint operand here.  ptxas 12.9 either drops it for this zero-fill form (identical LDGSTS encoding with
+  // and without) or, when the shared address is partly uniform, emits `LDGSTS [R+UR0], desc[UR1]` with UR0/UR1 never
+  // written -- an illegal instruction at run time (compute-sanitizer; scripts/check_sass_ur.py scans for it).
+  (void)policy;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -122,7 +124,9 @@ __global__ void __launch_bounds__(NW * 32, 1)
   constexpr int RING_B = NG * GS * SLAB_B;      // bytes of one ring (gathered rows; FUSE_DW: a second one for H rows)
   constexpr int WARP_B = RING_B * (FUSE_DW ? 2 : 1);
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // shfl from lane 0 / __reduce_*_sync results are provably warp-uniform for the compiler: without them every
+  // shuffle and vote of the row loop is wrapped in divergence guards (BRA.DIV / BSSY / WARPSYNC, ~20 % of the loop)
+  const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t gring_a = smem_u32(smem) + (uint32_t)warp * WARP_B;
   const uint32_t hring_a = gring_a + RING_B;
   const uint32_t full_a = smem_u32(smem) + (uint32_t)NW * WARP_B + (uint32_t)warp * NG * 8;
@@ -152,7 +156,8 @@ __global__ void __launch_bounds__(NW * 32, 1)
     const int item = (int)(unit / n_slabs);
     const int c0 = (int)(unit % n_slabs) * (NV * 128);
     const int4 itv = __ldg(reinterpret_cast<const int4*>(items) + item);
-    const int beg = itv.x, n = itv.y - itv.x, w = itv.z;
+    const int beg = __reduce_max_sync(FULL, itv.x), n = __reduce_max_sync(FULL, itv.y - itv.x),
+              w = __reduce_max_sync(FULL, itv.z);
     const int ng = (n + GS - 1) / GS;
     const uint32_t vb = (uint32_t)min(NV * 128, d - c0) * 4u;  // valid bytes of this slab (d % 4 == 0)
     const float* Xc = X + c0;
@@ -219,21 +224,21 @@ __global__ void __launch_bounds__(NW * 32, 1)
       } else {          // cp.async: every lane copies its own quads of every row of the group
         const int nbr_sel = in_cur ? cur_nbr : nxt_nbr;
         const int row_sel = in_cur ? cur_row : nxt_row;
+        const uint32_t gdst = gring_a + buf * GS * SLAB_B + lane * 16, hdst = hring_a + buf * GS * SLAB_B + lane * 16;
 #pragma unroll
         for (int j = 0; j < GS; ++j) {
           if (j < cnt) {
             const int src = __shfl_sync(FULL, nbr_sel, (q_rel + j) & 31);
             const float* xr = X + (size_t)(uint32_t)src * (uint32_t)ldx;
-            const uint32_t off = (buf * GS + j) * SLAB_B + lane * 16;
 #pragma unroll
             for (int k = 0; k < NV; ++k)
-              cp_async16(gring_a + off + k * 512, xr + (ok[k] ? col[k] : c0), ok[k] ? 16u : 0u, pol);
+              cp_async16(gdst + j * SLAB_B + k * 512, xr + (ok[k] ? col[k] : c0), ok[k] ? 16u : 0u, pol);
             if (FUSE_DW && ((sb >> j) & 1u)) {
               const int hrow = __shfl_sync(FULL, row_sel, (q_rel + j) & 31);
               const float* hr = Hrow + (size_t)(uint32_t)hrow * (uint32_t)ldh;
 #pragma unroll
               for (int k = 0; k < NV; ++k)
-                cp_async16(hring_a + off + k * 512, hr + (ok[k] ? col[k] : c0), ok[k] ? 16u : 0u, pol);
+                cp_async16(hdst + j * SLAB_B + k * 512, hr + (ok[k] ? col[k] : c0), ok[k] ? 16u : 0u, pol);
             }
           }
         }
@@ -288,8 +293,10 @@ __global__ void __launch_bounds__(NW * 32, 1)
       }
       float* po = out + (size_t)(uint32_t)row * (uint32_t)d;
 #pragma unroll
-      for (int k = 0; k < NV; ++k)
+      for (int k = 0; k < NV; ++k) {
         if (!TAIL || ok[k]) red4(po + col[k], y[k]);
+        xs[k] = zero4();                             // the next run accumulates from zero
+      }
     };
 
     uint32_t ends_mask = 0;
@@ -327,19 +334,14 @@ __global__ void __launch_bounds__(NW * 32, 1)
           x[k] = lds4(gbase + t * SLAB_B + k * 512);
           if (MODE == 0 && TAIL && !ok[k]) x[k] = zero4();  // TMA copies stop at the row end (cp.async zero-fills)
         }
-        if (st) {
 #pragma unroll
-          for (int k = 0; k < NV; ++k) xs[k] = make_float4(nm * x[k].x, nm * x[k].y, nm * x[k].z, nm * x[k].w);
-          if (FUSE_DW) {  // the run's own input row
+        for (int k = 0; k < NV; ++k) fma4(xs[k], nm, x[k]);   // xs is zero at the start of a run (flush clears it)
+        if (FUSE_DW && st) {  // the run's own input row
 #pragma unroll
-            for (int k = 0; k < NV; ++k) {
-              hq[k] = lds4(hbase + t * SLAB_B + k * 512);
-              if (MODE == 0 && TAIL && !ok[k]) hq[k] = zero4();
-            }
+          for (int k = 0; k < NV; ++k) {
+            hq[k] = lds4(hbase + t * SLAB_B + k * 512);
+            if (MODE == 0 && TAIL && !ok[k]) hq[k] = zero4();
           }
-        } else {
-#pragma unroll
-          for (int k = 0; k < NV; ++k) fma4(xs[k], nm, x[k]);
         }
         if ((ends_mask >> tb) & 1u) flush(__shfl_sync(FULL, cur_row, tb));
       }
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(NTEAMS * T * 32, 1)
   constexpr int RING_B = NG * GS * ROW_B;
   constexpr int TEAM_B = RING_B * (FUSE_DW ? 2 : 1);
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // shfl: provably warp-uniform
   const int team = warp / T, sw = warp % T;     // sw = this warp's column slab; the sw == 0 warp is the team's leader
   const uint32_t gring_a = smem_u32(smem) + (uint32_t)team * TEAM_B;
   const uint32_t hring_a = gring_a + RING_B;
@@ -427,10 +429,12 @@ __global__ void __launch_bounds__(NTEAMS * T * 32, 1)
 
   bool ok[NV];
   int col[NV];
+  char* outb[NV];                               // this lane's column of row 0 of `out`: row r is outb + r * rowb
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     col[k] = c0 + 4 * (lane + 32 * k);
     ok[k] = col[k] < d;
+    outb[k] = reinterpret_cast<char*>(out) + (size_t)(ok[k] ? col[k] : 0) * 4u;
   }
 
   // dynamic work distribution (see k_block_stg): the leader takes the team's next item from the global counter, the
@@ -439,10 +443,13 @@ __global__ void __launch_bounds__(NTEAMS * T * 32, 1)
   for (int it = 0;; ++it) {
     if (sw == 0 && lane == 0) next_item[team][it & 1] = atomicAdd(next_unit, 1);
     asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(T * 32) : "memory");
-    const int item = next_item[team][it & 1];
+    // __reduce_*_sync returns in a uniform register: the compiler then knows the item loop and everything keyed on
+    // (beg, n, w) is warp-convergent and drops the divergence guards around every shuffle / vote of the row loop
+    const int item = __reduce_max_sync(FULL, next_item[team][it & 1]);
     if (item >= n_items) break;
     const int4 itv = __ldg(reinterpret_cast<const int4*>(items) + item);
-    const int beg = itv.x, n = itv.y - itv.x, w = itv.z;
+    const int beg = __reduce_max_sync(FULL, itv.x), n = __reduce_max_sync(FULL, itv.y - itv.x),
+              w = __reduce_max_sync(FULL, itv.z);
     const int ng = (n + GS - 1) / GS;
 
     int b0 = 0;
@@ -531,10 +538,11 @@ __global__ void __launch_bounds__(NTEAMS * T * 32, 1)
           }
         }
       }
-      float* po = out + (size_t)(uint32_t)row * (uint32_t)d;
 #pragma unroll
-      for (int k = 0; k < NV; ++k)
-        if (!TAIL || ok[k]) red4(po + col[k], y[k]);
+      for (int k = 0; k < NV; ++k) {
+        if (!TAIL || ok[k]) red4(reinterpret_cast<float*>(outb[k] + (size_t)(uint32_t)row * rowb), y[k]);
+        xs[k] = zero4();                              // the next run accumulates from zero
+      }
     };
 
     uint32_t ends_mask = 0;
@@ -563,19 +571,14 @@ __global__ void __launch_bounds__(NTEAMS * T * 32, 1)
           x[k] = lds4(gbase + t * ROW_B + k * 512);
           if (TAIL && !ok[k]) x[k] = zero4();  // bytes past the row end were not copied
         }
-        if (st) {
 #pragma unroll
-          for (int k = 0; k < NV; ++k) xs[k] = make_float4(nm * x[k].x, nm * x[k].y, nm * x[k].z, nm * x[k].w);
-          if (FUSE_DW) {
+        for (int k = 0; k < NV; ++k) fma4(xs[k], nm, x[k]);   // xs is zero at the start of a run (flush clears it)
+        if (FUSE_DW && st) {
 #pragma unroll
-            for (int k = 0; k < NV; ++k) {
-              hq[k] = lds4(hbase + t * ROW_B + k * 512);
-              if (TAIL && !ok[k]) hq[k] = zero4();
-            }
+          for (int k = 0; k < NV; ++k) {
+            hq[k] = lds4(hbase + t * ROW_B + k * 512);
+            if (TAIL && !ok[k]) hq[k] = zero4();
           }
-        } else {
-#pragma unroll
-          for (int k = 0; k < NV; ++k) fma4(xs[k], nm, x[k]);
         }
         if ((ends_mask >> tb) & 1u) flush(__shfl_sync(FULL, cur_row, tb));
       }

@@ -90,6 +90,8 @@ int launch_mask_relu(float* x, const uint8_t* mask, float inv_keep, int relu, in
                      cudaStream_t st);
 // dst[rows[i], :] += src[i, :], rows unique within the call
 int launch_rows_add(float* dst, const int64_t* rows, const float* src, int64_t n, int d, cudaStream_t st);
+int launch_rows_gather(float* dst, const float* src, const int64_t* rows, int64_t n, int d, int max_ctas,
+                       cudaStream_t st);
 // zero rows listed in `rows` of a [*, width] matrix
 int launch_zero_rows(float* A, int64_t width, const int32_t* rows, int n_rows, cudaStream_t st);
 

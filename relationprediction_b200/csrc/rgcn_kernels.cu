@@ -1028,6 +1028,36 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// dst[i, :] = src[rows[i], :]: the halo PUSH of the node-sharded path.  `dst` is normally a peer GPU's halo buffer mapped
+// into this address space (NVLink stores are posted: the kernel is bound by the local row gather and the link, not by
+// store latency), so the rows go straight from H to their consumer without a packed send buffer and an all-to-all.
+// Two rows per warp iteration keep 8 x 16 B loads in flight per lane; the grid is kept small on purpose (the caller
+// passes max_ctas) so that the push overlaps the layer's local work instead of occupying every SM.
+__global__ void __launch_bounds__(256)
+    k_rows_gather(float4* __restrict__ dst, const float4* __restrict__ src, const int64_t* __restrict__ rows, int64_t n,
+                  int d4) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t i = ((int64_t)blockIdx.x * 8 + warp) * 2; i < n; i += (int64_t)gridDim.x * 16) {
+    const bool two = i + 1 < n;
+    const float4* p0 = src + (size_t)__ldg(rows + i) * d4;
+    const float4* p1 = src + (size_t)__ldg(rows + (two ? i + 1 : i)) * d4;
+    float4* q0 = dst + (size_t)i * d4;
+    float4* q1 = q0 + d4;
+    int k = lane;
+    for (; k + 96 < d4; k += 128) {
+      const float4 a0 = __ldg(p0 + k), a1 = __ldg(p0 + k + 32), a2 = __ldg(p0 + k + 64), a3 = __ldg(p0 + k + 96);
+      const float4 b0 = __ldg(p1 + k), b1 = __ldg(p1 + k + 32), b2 = __ldg(p1 + k + 64), b3 = __ldg(p1 + k + 96);
+      q0[k] = a0, q0[k + 32] = a1, q0[k + 64] = a2, q0[k + 96] = a3;
+      if (two) q1[k] = b0, q1[k + 32] = b1, q1[k + 64] = b2, q1[k + 96] = b3;
+    }
+    for (; k < d4; k += 32) {
+      const float4 a = __ldg(p0 + k), b = __ldg(p1 + k);
+      q0[k] = a;
+      if (two) q1[k] = b;
+    }
+  }
+}
+
 __global__ void k_zero_rows(float* __restrict__ A, int64_t width4, const int32_t* __restrict__ rows,
                             int n_rows) {
   const int r = blockIdx.x;
@@ -1306,6 +1336,17 @@ int launch_zero_rows(float* A, int64_t width, const int32_t* rows, int n_rows, c
   if (n_rows == 0) return RGCN_OK;
   k_zero_rows<<<n_rows, 256, 0, st>>>(A, width / 4, rows, n_rows);
   return check_launch("k_zero_rows");
+}
+
+int launch_rows_gather(float* dst, const float* src, const int64_t* rows, int64_t n, int d, int max_ctas,
+                       cudaStream_t st) {
+  if (n == 0) return RGCN_OK;
+  int64_t b = (n + 15) / 16;
+  const int64_t cap = max_ctas > 0 ? max_ctas : 148 * 8;
+  if (b > cap) b = cap;
+  k_rows_gather<<<(int)b, 256, 0, st>>>(reinterpret_cast<float4*>(dst), reinterpret_cast<const float4*>(src), rows, n,
+                                        d / 4);
+  return check_launch("k_rows_gather");
 }
 
 int launch_rows_add(float* dst, const int64_t* rows, const float* src, int64_t n, int d, cudaStream_t st) {

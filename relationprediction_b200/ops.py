@@ -420,6 +420,17 @@ def rows_add_(dst, rows, src):
     return dst
 
 
+def rows_gather_to(dst_ptr, src, rows, max_ctas=0):
+    """memory at dst_ptr [len(rows), d] = src[rows] (rgcn_rows_gather).  dst_ptr is a raw device address, normally a
+    PEER GPU's halo buffer mapped into this process (parallel.PeerHalo): the halo push of the node-sharded path."""
+    lib = _lib.load()
+    _check_cuda_f32("src", src)
+    if not (rows.is_cuda and rows.dtype == torch.int64 and rows.is_contiguous()):
+        raise _lib.RgcnError("rows must be a contiguous CUDA int64 tensor")
+    _lib.check(lib.rgcn_rows_gather(int(dst_ptr), _ptr(src), _ptr(rows), rows.numel(), src.shape[1], int(max_ctas),
+                                    _stream(src.device)), "rgcn_rows_gather")
+
+
 def block_aggregate_(out, X, W_forward, W_backward, graph, n_blocks):
     """out[dst] += sum_m norm_m W[relw_m] . X[src_m] (messages only, in place; rgcn_block_aggregate)."""
     lib = _lib.load()

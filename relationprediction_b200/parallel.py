@@ -11,6 +11,8 @@ The reference has no distributed code at all (single tf.Session, train.py:278); 
 multi-GPU design for the hot path only.
 """
 import math
+import os
+import warnings
 
 import numpy as np
 import torch
@@ -109,7 +111,7 @@ class ShardPlanDevice(object):
         inner = torch.as_tensor(self.bounds[1:], dtype=torch.int32, device=dev)
 
         def owner(nodes):
-            return torch.bucketize(nodes, inner, out_int32=True, right=True)
+            return torch.bucketize(nodes.contiguous(), inner, out_int32=True, right=True)
 
         parts = {k: [] for k in ("dst", "src", "relw", "norm", "gid")}
         need_keys = []
@@ -150,6 +152,53 @@ class ShardPlanDevice(object):
         self.send_counts = torch.bincount(torch.div(keys, n_nodes, rounding_mode="floor"),
                                           minlength=world).cpu().numpy().astype(np.int64)
         self.send_rows = (keys % n_nodes) - lo                  # int64, grouped by peer, ascending id inside
+
+
+class PeerHalo(object):
+    """Peer-mapped (CUDA symmetric memory) buffers for the halo exchange of ONE layer call in flight.
+
+    Every rank owns `halo` [max n_halo, d] -- the rows its aggregation kernels gather from -- and `back` [max rows
+    sent, d] -- the gradients of the rows it sent -- allocated symmetrically and mapped into every peer.  The forward
+    exchange is then rgcn_rows_gather writing each peer's rows from H straight into that peer's `halo` over NVLink
+    (no packed send buffer, no all-to-all), the backward return is one peer-to-peer copy per owner into its `back`
+    (the halo gradients are already grouped by owner), and three stream-ordered cross-GPU barriers per layer step
+    replace the collectives: buffers free -> rows landed -> gradients landed."""
+
+    def __init__(self, sg, d):
+        import torch.distributed._symmetric_memory as symm
+        p = sg.plan
+        dev = sg.device
+        group = sg.group if sg.group is not None else dist.group.WORLD
+        me, P = p.rank, p.world
+        mine = torch.tensor([p.n_halo, int(np.sum(p.send_counts))] + [int(x) for x in sg.halo_off[:P]] +
+                            [int(x) for x in sg.send_off[:P]], dtype=torch.int64, device=dev)
+        table = [torch.empty_like(mine) for _ in range(P)]
+        dist.all_gather(table, mine, group=group)
+        table = torch.stack(table).cpu().numpy()
+        self.halo_rows = max(int(table[:, 0].max()), 1)
+        self.back_rows = max(int(table[:, 1].max()), 1)
+        # where MY rows start inside peer q's halo buffer / where my gradients for q's rows start in q's back buffer
+        self.peer_halo_off = [int(table[q, 2 + me]) for q in range(P)]
+        self.peer_back_off = [int(table[q, 2 + P + me]) for q in range(P)]
+        self.d = int(d)
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:   # newer torch enables every group implicitly
+            pass
+        self.buf = symm.empty((self.halo_rows + self.back_rows, self.d), dtype=torch.float32, device=dev)
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.halo = self.buf[:self.halo_rows]
+        self.back = self.buf[self.halo_rows:]
+        self.busy = False
+
+    def peer_halo_ptr(self, q):
+        return int(self.hdl.buffer_ptrs[q]) + self.peer_halo_off[q] * self.d * 4
+
+    def peer_back_view(self, q, n):
+        return self.hdl.get_buffer(q, (n, self.d), torch.float32, (self.halo_rows + self.peer_back_off[q]) * self.d)
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)
 
 
 def _unpack_add(dH, sg, back):
@@ -209,18 +258,38 @@ class _OverlappedBlockLayer(torch.autograd.Function):
         d = H_local.shape[1]
         dev = H_local.device
         H_local = H_local.contiguous()
-        send = H_local.index_select(0, sg.send_rows)
-        H_halo = torch.empty(p.n_halo, d, dtype=H_local.dtype, device=dev)
-        work = dist.all_to_all_single(H_halo, send, output_split_sizes=p.recv_counts.tolist(),
-                                      input_split_sizes=p.send_counts.tolist(), group=sg.group, async_op=True)
+        slot = sg.peer_slot(d) if H_local.dtype == torch.float32 else None
+        if slot is not None:   # push my rows straight into the peers' halo buffers (rgcn_rows_gather over NVLink)
+            main, side = torch.cuda.current_stream(dev), sg.side_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                slot.barrier()                               # every rank is done with the buffers' previous contents
+                for k in range(1, p.world):                  # ring order: every receiver hears from one sender at a time
+                    q = (p.rank + k) % p.world
+                    a, b = sg.send_off[q], sg.send_off[q + 1]
+                    if b > a:
+                        ops.rows_gather_to(slot.peer_halo_ptr(q), H_local, sg.send_rows[a:b], sg.push_ctas)
+                slot.barrier()                               # every peer's rows have landed in my halo buffer
+            H_halo = slot.halo[:p.n_halo]
+            slot.busy = any(ctx.needs_input_grad)             # held until backward returns
+            work = None
+        else:
+            send = H_local.index_select(0, sg.send_rows)
+            H_halo = torch.empty(p.n_halo, d, dtype=H_local.dtype, device=dev)
+            work = dist.all_to_all_single(H_halo, send, output_split_sizes=p.recv_counts.tolist(),
+                                          input_split_sizes=p.send_counts.tolist(), group=sg.group, async_op=True)
         with torch.no_grad():
             out = ops._BlockLayerFn.apply(H_local, Wf, Wb, Ws, sg.graph_local, n_blocks, drop_mask, keep, False)
-        work.wait()
+        if work is not None:
+            work.wait()
+        else:
+            torch.cuda.current_stream(dev).wait_stream(sg.side_stream)
         if p.n_halo > 0:  # a rank whose messages all have local sources has no halo graph work at all
             ops.block_aggregate_(out, H_halo, Wf, Wb, sg.graph_halo, n_blocks)
         if relu:
             out.relu_()
         ctx.sg, ctx.n_blocks, ctx.keep, ctx.relu, ctx.mask = sg, n_blocks, keep, relu, drop_mask
+        ctx.slot = slot
         ctx.save_for_backward(H_local, Wf, Wb, Ws, H_halo, out)
         return out
 
@@ -229,6 +298,7 @@ class _OverlappedBlockLayer(torch.autograd.Function):
         H_local, Wf, Wb, Ws, H_halo, out = ctx.saved_tensors
         sg, B = ctx.sg, ctx.n_blocks
         p = sg.plan
+        slot = ctx.slot
         G = (dOut * (out > 0)) if ctx.relu else dOut
         G = G.contiguous()
         if p.n_halo > 0:
@@ -236,9 +306,23 @@ class _OverlappedBlockLayer(torch.autograd.Function):
         else:  # empty halo: nothing to send back, no halo contribution to the block weight gradients
             dHalo = torch.empty(0, G.shape[1], dtype=G.dtype, device=G.device)
             dWf, dWb = torch.zeros_like(Wf), torch.zeros_like(Wb)
-        back = torch.empty(int(p.send_counts.sum()), G.shape[1], dtype=G.dtype, device=G.device)
-        work = dist.all_to_all_single(back, dHalo, output_split_sizes=p.send_counts.tolist(),
-                                      input_split_sizes=p.recv_counts.tolist(), group=sg.group, async_op=True)
+        if slot is not None:   # the halo gradients are grouped by owner: one peer-to-peer copy per owner, into its `back`
+            main, side = torch.cuda.current_stream(G.device), sg.side_stream
+            side.wait_stream(main)
+            dHalo.record_stream(side)
+            with torch.cuda.stream(side):
+                for k in range(1, p.world):
+                    q = (p.rank - k) % p.world
+                    a, b = sg.halo_off[q], sg.halo_off[q + 1]
+                    if b > a:
+                        slot.peer_back_view(q, b - a).copy_(dHalo[a:b])
+                slot.barrier()                               # every peer's gradients for my rows have landed
+            back = slot.back[:int(np.sum(p.send_counts))]
+            work = None
+        else:
+            back = torch.empty(int(p.send_counts.sum()), G.shape[1], dtype=G.dtype, device=G.device)
+            work = dist.all_to_all_single(back, dHalo, output_split_sizes=p.send_counts.tolist(),
+                                          input_split_sizes=p.recv_counts.tolist(), group=sg.group, async_op=True)
         lib = ops._lib.load()
         d = H_local.shape[1]
         dH = torch.empty_like(H_local)
@@ -252,8 +336,13 @@ class _OverlappedBlockLayer(torch.autograd.Function):
         ops._lib.check(rc, "rgcn_block_backward")
         dWf += dWf_l
         dWb += dWb_l
-        work.wait()
+        if work is not None:
+            work.wait()
+        else:
+            torch.cuda.current_stream(G.device).wait_stream(sg.side_stream)
         _unpack_add(dH, sg, back)
+        if slot is not None:
+            slot.busy = False   # the next forward's first barrier orders every rank after this unpack
         return dH, dWf, dWb, dWs, None, None, None, None, None
 
 
@@ -365,8 +454,17 @@ class _PipelinedBlockLayer(torch.autograd.Function):
 
 class ShardedGraph(object):
     def __init__(self, triples, n_nodes, n_relations, rank, world, device, norm_mode="canonical",
-                 norm_f=None, norm_b=None, group=None, overlap=True, pipelined=None):
+                 norm_f=None, norm_b=None, group=None, overlap=True, pipelined=None, transport=None):
+        """transport (overlapped block layers on CUDA, world > 1): "peer" = halo rows pushed into peer-mapped buffers by
+        rgcn_rows_gather (PeerHalo), "nccl" = packed rows + all-to-all; None = $RGCN_HALO_TRANSPORT, else "peer" with
+        "nccl" taking over (one warning) when symmetric memory cannot be set up on this system."""
         self.device = torch.device(device)
+        self.transport = transport or os.environ.get("RGCN_HALO_TRANSPORT") or "auto"
+        if self.transport not in ("auto", "peer", "nccl"):
+            raise ValueError("transport must be 'peer', 'nccl' or None")
+        self._peer_slots, self._peer_failed = [], False
+        self.side_stream = None
+        self.push_ctas = int(os.environ.get("RGCN_PUSH_CTAS", "64"))
         on_device = isinstance(triples, torch.Tensor) and triples.is_cuda
         if on_device:   # edge list already on the GPU: plan + graph preparation never leave it
             self.plan = ShardPlanDevice(triples, n_nodes, n_relations, rank, world, norm_mode, norm_f, norm_b)
@@ -416,6 +514,36 @@ class ShardedGraph(object):
                                                          p.msg_norm[sel], p.n_local, hi_q - lo_q)
             if on_device:   # the plan's per-message arrays are no longer needed: free the device memory
                 p.msg_dst = p.msg_src = p.msg_relw = p.msg_norm = None
+
+    def peer_slot(self, d):
+        """A free PeerHalo of width d (created collectively on first use: every rank runs the same layer sequence), or
+        None when the NCCL transport is in force."""
+        if self.transport == "nccl" or self._peer_failed or self.device.type != "cuda" or self.plan.world < 2:
+            return None
+        for slot in self._peer_slots:
+            if slot.d == d and not slot.busy:
+                return slot
+        if len(self._peer_slots) >= 4:   # forwards whose backward never ran hold their slots: do not grow without bound
+            return None
+        try:
+            slot = PeerHalo(self, d)
+        except Exception as e:   # symmetric memory unavailable (no P2P mapping between these GPUs, old driver, ...)
+            if self.transport == "peer":
+                raise
+            warnings.warn("peer-mapped halo buffers unavailable (%s: %s); using the NCCL all-to-all transport"
+                          % (type(e).__name__, e))
+            self._peer_failed = True
+            return None
+        if self.side_stream is None:
+            self.side_stream = torch.cuda.Stream(device=self.device)
+        self._peer_slots.append(slot)
+        return slot
+
+    def halo_transport(self):
+        """Transport the overlapped block layer used so far: "peer", "nccl", or None before the first call."""
+        if self._peer_slots:
+            return "peer"
+        return "nccl" if (self._peer_failed or self.transport == "nccl") else None
 
     def halo_exchange(self, H_local):
         return _HaloExchange.apply(H_local, self.plan, self.send_rows, self.group)

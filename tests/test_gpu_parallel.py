@@ -38,9 +38,10 @@ def _worker(rank, world, port, V, R, E, d, B, out_dir, mode):
             sg = parallel.ShardedGraph(torch.from_numpy(tr).to(dev), V, R, rank, world, dev)
             assert isinstance(sg.plan, parallel.ShardPlanDevice) and sg.graph is None
             p = sg.plan
-        else:
+        else:   # "peer": rows pushed into peer-mapped halo buffers (rgcn_rows_gather); "overlapped": NCCL all-to-all
             sg = parallel.ShardedGraph(tr, V, R, rank, world, dev, overlap=(mode != "plain"),
-                                       pipelined=(mode == "pipelined"))
+                                       pipelined=(mode == "pipelined"),
+                                       transport={"peer": "peer", "overlapped": "nccl"}.get(mode))
             assert sg.pipelined == (mode == "pipelined")
             p = sg.plan
         g = torch.Generator().manual_seed(0)
@@ -51,8 +52,15 @@ def _worker(rank, world, port, V, R, E, d, B, out_dir, mode):
         Wb = (torch.randn(R, B, s, s, generator=g) * 0.3).to(dev).requires_grad_(True)
         Ws = (torch.randn(d, d, generator=g) * 0.05).to(dev).requires_grad_(True)
         Hl = H[p.lo:p.hi].to(dev).requires_grad_(True)
-        out = sg.block_layer(Hl, Wf, Wb, Ws, B, None, 1.0, True)
-        out.backward(dOut[p.lo:p.hi].to(dev))
+        for step in range(2 if mode == "peer" else 1):   # peer: the second step reuses the buffers behind the barriers
+            for t in (Hl, Wf, Wb, Ws):
+                t.grad = None
+            out = sg.block_layer(Hl, Wf, Wb, Ws, B, None, 1.0, True)
+            out.backward(dOut[p.lo:p.hi].to(dev))
+        if mode == "peer":
+            assert sg.halo_transport() == "peer" and len(sg._peer_slots) == 1
+        elif mode == "overlapped":
+            assert sg.halo_transport() == "nccl"
         sg.allreduce_weight_grads([Wf, Wb, Ws])
         torch.cuda.synchronize()
         np.savez(os.path.join(out_dir, "r%d.npz" % rank), out=out.detach().cpu().numpy(), dH=Hl.grad.cpu().numpy(),
@@ -61,7 +69,7 @@ def _worker(rank, world, port, V, R, E, d, B, out_dir, mode):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["device-plan", "pipelined", "overlapped", "plain", "feature"])
+@pytest.mark.parametrize("mode", ["peer", "device-plan", "pipelined", "overlapped", "plain", "feature"])
 @pytest.mark.parametrize("world", [2, 4])
 def test_sharded_block_layer_equals_single_gpu(tmp_path, world, mode):
     if torch.cuda.device_count() < world:
