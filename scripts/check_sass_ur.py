@@ -15,7 +15,7 @@ def check(lib):
         name = fn.split("\n", 1)[0].strip()
         written, need = set(), set()
         for line in fn.splitlines():
-            m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(.*?);", line)
+            m = re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+(.*?);", line)
             if not m:
                 continue
             ins = re.sub(r"^@!?U?P\d+\s+", "", m.group(1).strip())

@@ -23,7 +23,7 @@ def main():
         short = re.sub(r"\(.*", "", dem)
         c, body = collections.Counter(), []
         for line in fn.splitlines():
-            m = re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(.*?)\s*/\* 0x", line)
+            m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/\s+(.*?)\s*/\* 0x", line)
             if not m:
                 continue
             ins = m.group(2)

@@ -15,7 +15,9 @@ def rel(a, b):
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 128), (256, 256, 64), (14541, 500, 500),
                                    (1000, 512, 512), (77, 8, 8), (300, 200, 200), (129, 132, 36),
-                                   (5000, 24, 40)])
+                                   (5000, 24, 40),
+                                   # many tiles per persistent CTA (one / two / sixteen k-blocks per tile)
+                                   (100000, 512, 512), (40000, 132, 32), (30000, 24, 40)])
 @pytest.mark.parametrize("b_is_nk", [False, True])
 def test_gemm_tf32x3_matches_float64(M, N, K, b_is_nk):
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
