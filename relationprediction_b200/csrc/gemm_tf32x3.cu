@@ -19,6 +19,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace {
@@ -96,6 +99,16 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 // a = hi + lo with hi = RN_tf32(a) and lo = RN_tf32(a - hi): both exactly representable in TF32, so
 // the tensor core's own fp32->tf32 conversion is exact and the split error is <= 2^-22 |a|, unbiased.
+// Producer-side split by TRUNCATION: hi = a with the 13 low mantissa bits cleared, lo = (a - hi) (exact in fp32) with
+// its low bits cleared.  Three integer/FP instructions per element instead of two cvt.rna.tf32 (which sm_100 expands
+// to ~5 instructions each: the round-to-nearest split made the producers execute ~360 instructions per thread and
+// k-block and capped the tensor pipe at 35 % active, ncu round 2).  Both parts are exact TF32 values; the split error
+// is |a - hi - lo| < 2^-20 |a| (round-to-nearest: 2^-22), still two orders below the 1e-4 bar of the layer and inside
+// the 1e-5 bar of tests/test_gpu_gemm.py.  The small K-major operand is still split with round-to-nearest (once).
+__device__ __forceinline__ void split_tf32_trunc(float a, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(a) & 0xffffe000u);
+  lo = __uint_as_float(__float_as_uint(a - hi) & 0xffffe000u);
+}
 __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
   uint32_t h, l;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(a));
@@ -123,31 +136,50 @@ struct RankEpi {
 };
 __device__ __forceinline__ float sigmoid_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// PERSISTENT, three roles: 8 producer warps, 1 MMA warp, 4 epilogue warps.  A CTA walks the tiles blockIdx.x,
+// blockIdx.x + gridDim.x, ... (N tiles fastest, see below); the shared-memory stages and their barrier phases run on
+// across tile boundaries, so the producers fill the pipeline of tile t+1 (global-load latency included) while the MMAs
+// of tile t drain and the epilogue warps move its accumulators out of TMEM.  (Round 2 profile of the one-tile-per-CTA
+// version on the 10 M x 512 x 512 self-loop GEMM: tensor pipe 35 % active, producers parked on their first loads --
+// with K = 512 a tile is only 16 k-blocks, and every tile paid pipeline fill + epilogue with the tensor core idle.)
+// TMEM holds TWO accumulator sets (tile parity): a tile uses one big (hi*hi) and one small (cross terms) accumulator,
+// 2 x 128 columns, so the MMAs of tile t+1 run while the epilogue warps move tile t out of the other set; the MMA warp
+// only waits for `drained[set]` of tile t-2.  (A first persistent version kept round 1's four accumulators per tile --
+// even/odd k-blocks separately -- in a single set: the next tile's MMAs then waited for the whole epilogue and the
+// kernel was 12 % SLOWER than one tile per CTA.)
+constexpr int N_EPI = 128;                                  // 4 epilogue warps: one per TMEM lane quarter
+constexpr int N_THREADS_NT = N_PRODUCERS + 32 + N_EPI;      // 416
+constexpr int EPI_WARP0 = MMA_WARP + 1;
+
 template <int EPI>
-__global__ void __launch_bounds__(N_THREADS, 1)
+__global__ void __launch_bounds__(N_THREADS_NT, 1)
     k_gemm_tf32x3(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bhi,
                   const float* __restrict__ Blo, int64_t ldb, float* __restrict__ C, int64_t ldc,
-                  int M, int N, int K, int accumulate, RankEpi re) {
+                  int M, int N, int K, int accumulate, int n_tiles, RankEpi re) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar[2], drained_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B: 1024 B aligned
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // 1-D grid, N tiles fastest: the CTAs that share an A tile (all N tiles of one M tile) are launched back to back,
+  // Tile order, N tiles fastest: the CTAs that share an A tile (all N tiles of one M tile) run at the same time,
   // so the big operand (V x K, 20 GB at the full benchmark size) is read from HBM once and from L2 afterwards; the
   // small K-major operand (<= a few MB of hi/lo planes) lives in L2 throughout.  (Round 1 launched the M tiles
   // fastest: every N tile re-read its A tile from HBM -- ncu: 1.64 GB of DRAM reads for a 0.41 GB operand.)
   const int tn = (N + BN - 1) / BN;
-  const int m0 = (int)(blockIdx.x / tn) * BM, n0 = (int)(blockIdx.x % tn) * BN;
   const int num_kb = (K + BK - 1) / BK;
+  const int n_mine = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA (>= 1)
+  const int total_g = n_mine * num_kb;                                                   // its k-blocks, all tiles
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], N_PRODUCERS);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&accum_bar[b], 1);
+      mbar_init(&drained_bar[b], N_EPI);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {  // TMEM allocation by one full warp; the same warp frees it
@@ -164,190 +196,248 @@ __global__ void __launch_bounds__(N_THREADS, 1)
 
   if (warp < MMA_WARP) {
     // ================= producers =================
-    // Software-pipelined: while block kb is converted and stored, the global loads of A(kb+1) are
-    // already in flight in registers and the async copies of B(kb+1) in the next smem stage.
+    // Software-pipelined over the CTA's whole k-block sequence g = 0 .. total_g-1 (tile g / num_kb, block g % num_kb):
+    // while block g is converted and stored, the global loads of A(g+1), A(g+2) are already in flight in registers
+    // and the async copies of B(g+1) in the next smem stage -- also when g+1 belongs to the NEXT tile.
+    // All addresses are carried incrementally (row pointers advance by BK floats per k-block and are rebuilt once
+    // per tile): recomputing (row * ld + column) with its bounds checks for every request made the producers execute
+    // ~330 instructions per thread and k-block, of which 16 were the loads and copies themselves.
     const int c = tid & 7;        // 16 B chunk within the 128 B K-row
-    const int rbase = tid >> 3;   // 0..31
-    auto issue_b = [&](int kb) {
-      const int s = kb % STAGES;
-      const uint32_t b_hi = smem_base + s * STAGE_BYTES + 2 * TILE_BYTES, b_lo = b_hi + TILE_BYTES;
-      const int col = kb * BK + c * 4;
-      const bool col_ok = col < K;  // K % 4 == 0: a 16 B chunk is entirely valid or entirely padding
+    const int rbase = tid >> 3;   // 0..31; this thread handles tile rows rbase + 32 i
+    const uint32_t soff = swz(rbase, c);  // swizzled offset of (row rbase, chunk c); row rbase + 32 i is 4096 i further
+    constexpr int NR = BM / 32;
+    static_assert(BM == BN, "the producers use one row schedule for both operands");
+
+    // ---- B request stream (async copies, one block ahead)
+    int b_kb = 0, b_tile = (int)blockIdx.x, b_stage = 0;
+    const float* pbh[NR];
+    const float* pbl[NR];
+    bool bok[NR];
+    auto b_set_tile = [&]() {
+      const int n0 = (b_tile % tn) * BN;
 #pragma unroll
-      for (int i = 0; i < BN / 32; ++i) {
-        const int r = rbase + 32 * i;
-        const bool ok = col_ok && (n0 + r < N);
-        const size_t off = ok ? ((size_t)(n0 + r) * ldb + col) : 0;
-        cp_async16(b_hi + swz(r, c), Bhi + off, ok ? 16u : 0u);
-        cp_async16(b_lo + swz(r, c), Blo + off, ok ? 16u : 0u);
+      for (int i = 0; i < NR; ++i) {
+        const int r = n0 + rbase + 32 * i;
+        bok[i] = r < N;
+        const size_t off = bok[i] ? ((size_t)r * ldb + c * 4) : 0;
+        pbh[i] = Bhi + off;
+        pbl[i] = Blo + off;
+      }
+    };
+    b_set_tile();
+    auto issue_b = [&]() {        // requests the stream's current block, then advances it
+      const uint32_t b_hi = smem_base + b_stage * STAGE_BYTES + 2 * TILE_BYTES + soff, b_lo = b_hi + TILE_BYTES;
+      const bool col_ok = b_kb * BK + c * 4 < K;  // K % 4 == 0: a 16 B chunk is entirely valid or entirely padding
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const bool ok = col_ok && bok[i];
+        cp_async16(b_hi + 4096 * i, ok ? pbh[i] : Bhi, ok ? 16u : 0u);
+        cp_async16(b_lo + 4096 * i, ok ? pbl[i] : Blo, ok ? 16u : 0u);
+        pbh[i] += BK;
+        pbl[i] += BK;
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    auto load_a = [&](int kb, float4 (&v)[BM / 32]) {
-      const int col = kb * BK + c * 4;
-      const bool col_ok = col < K;
-#pragma unroll
-      for (int i = 0; i < BM / 32; ++i) {
-        const int r = rbase + 32 * i;
-        v[i] = (col_ok && (m0 + r < M))
-                   ? __ldg(reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + col))
-                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      b_stage = b_stage + 1 == STAGES ? 0 : b_stage + 1;
+      if (++b_kb == num_kb) {
+        b_kb = 0;
+        b_tile += (int)gridDim.x;
+        b_set_tile();
       }
     };
-    // PF k-blocks of A are in flight in registers (and of B as asynchronous copies) while block kb is converted and
-    // stored.  Round 1 prefetched ONE block: ncu showed the producers parked on their own global loads
-    // (long-scoreboard 4.0 of 9 warps, tensor pipe 31-35 % active) -- 16 KB in flight per SM cannot cover the
-    // HBM/L2 latency at the 40 GB/s per SM the MMAs consume.
-    // (The asynchronous copies of B stay ONE block ahead: they need the shared-memory stage of block kb + 1, and
-    // asking for the stage of kb + 2 would make the producers wait for the MMAs of block kb - 1 before storing block
-    // kb -- measured 8 % slower.  The A rows only need registers, so they run two blocks ahead.)
+    // ---- A request stream (register prefetch, PF blocks ahead)
+    int a_kb = 0, a_tile = (int)blockIdx.x;
+    const float* pa[NR];
+    bool aok[NR];
+    auto a_set_tile = [&]() {
+      const int m0 = (a_tile / tn) * BM;
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const int r = m0 + rbase + 32 * i;
+        aok[i] = r < M;
+        pa[i] = A + (aok[i] ? ((size_t)r * lda + c * 4) : 0);
+      }
+    };
+    a_set_tile();
+    auto load_a = [&](float4 (&v)[NR]) {   // requests the stream's current block, then advances it
+      const bool col_ok = a_kb * BK + c * 4 < K;
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        v[i] = (col_ok && aok[i]) ? __ldg(reinterpret_cast<const float4*>(pa[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
+        pa[i] += BK;
+      }
+      if (++a_kb == num_kb) {
+        a_kb = 0;
+        a_tile += (int)gridDim.x;
+        a_set_tile();
+      }
+    };
+    // PF k-blocks of A are in flight in registers (and of B as asynchronous copies) while block g is converted and
+    // stored.  (The asynchronous copies of B stay ONE block ahead: they need the shared-memory stage of block g + 1,
+    // and asking for the stage of g + 2 would make the producers wait for the MMAs of block g - 1 before storing block
+    // g -- measured 8 % slower.  The A rows only need registers, so they run two blocks ahead.)
     constexpr int PF = 2;                    // register prefetch distance of A in k-blocks (PF + 1 buffers)
-    float4 vbuf[PF + 1][BM / 32];
+    float4 vbuf[PF + 1][NR];
     mbar_wait(&empty_bar[0], 1u);            // first use of a stage: the "previous phase" is complete
-    issue_b(0);
+    issue_b();
     for (int p = 0; p < PF; ++p)
-      if (p < num_kb) load_a(p, vbuf[p]);
-    for (int kb0 = 0; kb0 < num_kb; kb0 += PF + 1) {
+      if (p < total_g) load_a(vbuf[p]);
+    int s = 0;                               // stage of block g
+    uint32_t ph_next = 0;                    // phase bit of block g + 1's stage use
+    for (int g0 = 0; g0 < total_g; g0 += PF + 1) {
 #pragma unroll
       for (int u = 0; u <= PF; ++u) {
-        const int kb = kb0 + u;
-        if (kb >= num_kb) break;
-        const int s = kb % STAGES;
-        const bool more = kb + 1 < num_kb;
+        const int g = g0 + u;
+        if (g >= total_g) break;
+        const bool more = g + 1 < total_g;
+        const int s1 = s + 1 == STAGES ? 0 : s + 1;
+        if (s1 == 0) ph_next ^= 1u;          // block g + 1 starts a new round of the stage ring
         if (more) {
-          const int s1 = (kb + 1) % STAGES;
-          const uint32_t ph1 = (uint32_t)((kb + 1) / STAGES) & 1u;
-          mbar_wait(&empty_bar[s1], ph1 ^ 1u);
-          issue_b(kb + 1);
+          mbar_wait(&empty_bar[s1], ph_next ^ 1u);
+          issue_b();
         }
-        if (kb + PF < num_kb) load_a(kb + PF, vbuf[(u + PF) % (PF + 1)]);
-        const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES;
+        if (g + PF < total_g) load_a(vbuf[(u + PF) % (PF + 1)]);
+        const uint32_t a_hi = smem_base + s * STAGE_BYTES + soff, a_lo = a_hi + TILE_BYTES;
 #pragma unroll
-        for (int i = 0; i < BM / 32; ++i) {
-          const int r = rbase + 32 * i;
+        for (int i = 0; i < NR; ++i) {
           float4 hi, lo;
-          split_tf32(vbuf[u][i].x, hi.x, lo.x);
-          split_tf32(vbuf[u][i].y, hi.y, lo.y);
-          split_tf32(vbuf[u][i].z, hi.z, lo.z);
-          split_tf32(vbuf[u][i].w, hi.w, lo.w);
-          const uint32_t o = swz(r, c);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + o), "f"(hi.x), "f"(hi.y),
+          split_tf32_trunc(vbuf[u][i].x, hi.x, lo.x);
+          split_tf32_trunc(vbuf[u][i].y, hi.y, lo.y);
+          split_tf32_trunc(vbuf[u][i].z, hi.z, lo.z);
+          split_tf32_trunc(vbuf[u][i].w, hi.w, lo.w);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + 4096 * i), "f"(hi.x), "f"(hi.y),
                        "f"(hi.z), "f"(hi.w)
                        : "memory");
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + o), "f"(lo.x), "f"(lo.y),
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + 4096 * i), "f"(lo.x), "f"(lo.y),
                        "f"(lo.z), "f"(lo.w)
                        : "memory");
         }
         if (more)
-          asm volatile("cp.async.wait_group 1;" ::: "memory");  // B(kb) has landed, B(kb+1) may still fly
+          asm volatile("cp.async.wait_group 1;" ::: "memory");  // B(g) has landed, B(g+1) may still fly
         else
           asm volatile("cp.async.wait_group 0;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core
         mbar_arrive(&full_bar[s]);
+        s = s1;
       }
     }
-    // ================= epilogue =================
-    mbar_wait(&accum_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // a warp may only touch TMEM lanes 32*(warp % 4)..+31; warps 0-3 take columns 0-63, warps 4-7 64-127
-    const int row = m0 + (warp & 3) * 32 + lane;  // TMEM lane == accumulator row
+  } else if (warp >= EPI_WARP0) {
+    // ================= epilogue warps =================
+    // a warp may only touch TMEM lanes 32*(warp % 4)..+31: the four epilogue warps take one lane quarter each and
+    // all BN columns of it
     const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const int cb_begin = (warp >> 2) * (BN / 2);
-    const int n_pair = num_kb > 1 ? 2 : 1;  // accumulators actually written: {0,2} or {0,1,2,3}
-    int rank_raw = 0, rank_known = 0;
-    float gold_s = 0.f;
-    int gold_c = -1;
-    if (EPI == 1 && row < M) {
-      gold_s = __ldg(re.gold_sig + row);
-      gold_c = __ldg(re.gold_col + row);
-    }
-#pragma unroll
-    for (int cb = cb_begin; cb < cb_begin + BN / 2; cb += 32) {
-      uint32_t r[32];
-      float sum[32];
-#pragma unroll
-      for (int q = 0; q < 32; ++q) sum[q] = 0.f;
-      // small (cross-term) accumulators first, then the big ones
-      for (int a = N_ACC - 1; a >= 0; --a) {
-        if ((a & 1) >= n_pair) continue;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-              "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-              "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
-              "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
-              "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr + (uint32_t)(a * BN + cb)));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int q = 0; q < 32; ++q) sum[q] += __uint_as_float(r[q]);
+    for (int ti = 0; ti < n_mine; ++ti) {
+      const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+      const int m0 = (tile / tn) * BM, n0 = (tile % tn) * BN;
+      const int row = m0 + (warp & 3) * 32 + lane;  // TMEM lane == accumulator row
+      int rank_raw = 0, rank_known = 0;
+      float gold_s = 0.f;
+      int gold_c = -1;
+      if (EPI == 1 && row < M) {
+        gold_s = __ldg(re.gold_sig + row);
+        gold_c = __ldg(re.gold_col + row);
       }
-      if (EPI == 1) {
-        if (row < M && n0 + cb < N) {
-          uint32_t bits = 0;
+      const int set = ti & 1;                       // accumulator set of this tile: columns [set*2*BN, +2*BN)
+      mbar_wait(&accum_bar[set], (uint32_t)(ti >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-          for (int q = 0; q < 32; ++q)
-            if (n0 + cb + q < N && sigmoid_ref(sum[q]) >= gold_s) bits |= 1u << q;
-          const int gq = gold_c - (n0 + cb);
-          if (gq >= 0 && gq < 32) bits |= 1u << gq;   // the gold entity always scores >= itself
-          rank_raw += __popc(bits);
-          if (re.known) rank_known += __popc(bits & __ldg(re.known + (size_t)row * re.words + ((n0 + cb) >> 5)));
+      for (int cb = 0; cb < BN; cb += 32) {
+        uint32_t r[32];
+        float sum[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) sum[q] = 0.f;
+        // small (cross-term) accumulator first, then the big one
+        for (int a = 1; a >= 0; --a) {
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+                "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+                "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+                "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr + (uint32_t)((2 * set + a) * BN + cb)));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int q = 0; q < 32; ++q) sum[q] += __uint_as_float(r[q]);
         }
-        continue;
-      }
+        if (cb == BN - 32) {  // this thread's last read of the accumulators: the MMAs of the next tile may overwrite
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(&drained_bar[set]);
+        }
+        if (EPI == 1) {
+          if (row < M && n0 + cb < N) {
+            uint32_t bits = 0;
 #pragma unroll
-      for (int q = 0; q < 32; ++q) r[q] = __float_as_uint(sum[q]);
-      if (row < M) {
-        float* crow = C + (size_t)row * ldc + n0 + cb;
+            for (int q = 0; q < 32; ++q)
+              if (n0 + cb + q < N && sigmoid_ref(sum[q]) >= gold_s) bits |= 1u << q;
+            const int gq = gold_c - (n0 + cb);
+            if (gq >= 0 && gq < 32) bits |= 1u << gq;   // the gold entity always scores >= itself
+            rank_raw += __popc(bits);
+            if (re.known) rank_known += __popc(bits & __ldg(re.known + (size_t)row * re.words + ((n0 + cb) >> 5)));
+          }
+          continue;
+        }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int ncol = n0 + cb + 4 * q;
-          if (ncol < N) {  // N % 4 == 0
-            float4 o = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-            if (accumulate) {
-              const float4 old = *reinterpret_cast<const float4*>(crow + 4 * q);
-              o.x += old.x;
-              o.y += old.y;
-              o.z += old.z;
-              o.w += old.w;
+        for (int q = 0; q < 32; ++q) r[q] = __float_as_uint(sum[q]);
+        if (row < M) {
+          float* crow = C + (size_t)row * ldc + n0 + cb;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int ncol = n0 + cb + 4 * q;
+            if (ncol < N) {  // N % 4 == 0
+              float4 o = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                     __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+              if (accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(crow + 4 * q);
+                o.x += old.x;
+                o.y += old.y;
+                o.z += old.z;
+                o.w += old.w;
+              }
+              *reinterpret_cast<float4*>(crow + 4 * q) = o;
             }
-            *reinterpret_cast<float4*>(crow + 4 * q) = o;
           }
         }
       }
-    }
-    if (EPI == 1 && row < M) {
-      if (rank_raw) atomicAdd(re.raw_cnt + row, rank_raw);
-      if (rank_known) atomicAdd(re.known_cnt + row, rank_known);
+      if (EPI == 1 && row < M) {
+        if (rank_raw) atomicAdd(re.raw_cnt + row, rank_raw);
+        if (rank_known) atomicAdd(re.known_cnt + row, rank_known);
+      }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   } else {
-    // ================= MMA issuer (warp 4, one elected lane) =================
+    // ================= MMA issuer (one elected lane) =================
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(&full_bar[s], ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES;
-        const uint32_t b_hi = a_lo + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
-#pragma unroll
-        for (int kk = 0; kk < BK / 8; ++kk) {  // UMMA K = 8 tf32 = 32 bytes along the swizzled row
-          const uint64_t dah = make_desc(a_hi + kk * 32), dal = make_desc(a_lo + kk * 32);
-          const uint64_t dbh = make_desc(b_hi + kk * 32), dbl = make_desc(b_lo + kk * 32);
-          const uint32_t acc_big = tmem_base + (uint32_t)((kb & 1) * BN);
-          const uint32_t acc_small = tmem_base + (uint32_t)((2 + (kb & 1)) * BN);
-          const uint32_t first = (kb < 2 && kk == 0) ? 0u : 1u;  // first touch overwrites
-          umma_tf32(acc_small, dal, dbh, first);
-          umma_tf32(acc_small, dah, dbl, 1);
-          umma_tf32(acc_big, dah, dbh, first);
+      int g = 0;
+      for (int ti = 0; ti < n_mine; ++ti) {
+        const int set = ti & 1;
+        if (ti >= 2) {  // the epilogue warps have read tile ti - 2 out of this accumulator set
+          mbar_wait(&drained_bar[set], (uint32_t)((ti >> 1) - 1) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs have read it
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = g % STAGES;
+          const uint32_t ph = (uint32_t)(g / STAGES) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES;
+          const uint32_t b_hi = a_lo + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {  // UMMA K = 8 tf32 = 32 bytes along the swizzled row
+            const uint64_t dah = make_desc(a_hi + kk * 32), dal = make_desc(a_lo + kk * 32);
+            const uint64_t dbh = make_desc(b_hi + kk * 32), dbl = make_desc(b_lo + kk * 32);
+            const uint32_t acc_big = tmem_base + (uint32_t)(2 * set * BN);
+            const uint32_t acc_small = acc_big + (uint32_t)BN;
+            const uint32_t first = (kb == 0 && kk == 0) ? 0u : 1u;  // first touch overwrites
+            umma_tf32(acc_small, dal, dbh, first);
+            umma_tf32(acc_small, dah, dbl, 1);
+            umma_tf32(acc_big, dah, dbh, first);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs have read it
+        }
+        umma_commit(&accum_bar[set]);  // this tile's accumulators are complete
       }
-      umma_commit(&accum_bar);  // accumulator complete
     }
     __syncwarp();
   }
@@ -387,6 +477,7 @@ __device__ __forceinline__ void umma_tf32_tn(uint32_t tmem_d, uint64_t da, uint6
       : "memory");
 }
 
+template <int PF>
 __global__ void __launch_bounds__(N_THREADS, 1)
     k_gemm_tn_tf32x3(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
                      float* __restrict__ C, int64_t ldc, int M, int N, int K, int kb_per_split) {
@@ -443,7 +534,6 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     };
     // PF k-blocks of both operands in flight in registers (see the NT kernel: one block of prefetch left the
     // producers latency-bound)
-    constexpr int PF = 2;
     float4 va[PF + 1][4], vb[PF + 1][4];
     for (int p = 0; p < PF; ++p)
       if (p < num_kb) load_ab(p, va[p], vb[p]);
@@ -465,18 +555,18 @@ __global__ void __launch_bounds__(N_THREADS, 1)
           const uint32_t off = (uint32_t)((cm >> 3) * 4096 + (kr >> 2) * 512 + (kr & 3) * 128 +
                                           ((((c8 >> 1) ^ (kr & 3)) << 5) | ((c8 & 1) << 4)));
           float4 hi, lo;
-          split_tf32(va[u][i].x, hi.x, lo.x);
-          split_tf32(va[u][i].y, hi.y, lo.y);
-          split_tf32(va[u][i].z, hi.z, lo.z);
-          split_tf32(va[u][i].w, hi.w, lo.w);
+          split_tf32_trunc(va[u][i].x, hi.x, lo.x);
+          split_tf32_trunc(va[u][i].y, hi.y, lo.y);
+          split_tf32_trunc(va[u][i].z, hi.z, lo.z);
+          split_tf32_trunc(va[u][i].w, hi.w, lo.w);
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "f"(hi.x), "f"(hi.y),
                        "f"(hi.z), "f"(hi.w) : "memory");
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "f"(lo.x), "f"(lo.y),
                        "f"(lo.z), "f"(lo.w) : "memory");
-          split_tf32(vb[u][i].x, hi.x, lo.x);
-          split_tf32(vb[u][i].y, hi.y, lo.y);
-          split_tf32(vb[u][i].z, hi.z, lo.z);
-          split_tf32(vb[u][i].w, hi.w, lo.w);
+          split_tf32_trunc(vb[u][i].x, hi.x, lo.x);
+          split_tf32_trunc(vb[u][i].y, hi.y, lo.y);
+          split_tf32_trunc(vb[u][i].z, hi.z, lo.z);
+          split_tf32_trunc(vb[u][i].w, hi.w, lo.w);
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(b_hi + off), "f"(hi.x), "f"(hi.y),
                        "f"(hi.z), "f"(hi.w) : "memory");
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(b_lo + off), "f"(lo.x), "f"(lo.y),
@@ -591,6 +681,27 @@ int launch_gemm_split_b(const float* B, int64_t ldb, int N, int K, int transpose
   return rgcn_check_cuda(cudaGetLastError(), "k_split_b");
 }
 
+// grid of the persistent NT kernel: the SM count of the current device ($RGCN_GEMM_CTAS overrides; a value >= the
+// tile count gives a one-tile-per-CTA schedule)
+static int64_t nt_grid_cap() {
+  if (const char* e = std::getenv("RGCN_GEMM_CTAS")) return std::max<int64_t>(1, std::atoll(e));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+// register prefetch distance of the producers (k-blocks of the streamed operand in flight): $RGCN_GEMM_PF = 2 | 3 | 4
+static int gemm_prefetch_distance() {
+  static int pf = 0;
+  if (!pf) {
+    const char* e = std::getenv("RGCN_GEMM_PF");
+    pf = e ? std::atoi(e) : 3;
+    if (pf < 2 || pf > 4) pf = 3;
+  }
+  return pf;
+}
+
 int launch_gemm_tf32x3(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, int64_t ldb,
                        float* C, int64_t ldc, int M, int N, int K, int accumulate, cudaStream_t st) {
   if (M == 0 || N == 0) return RGCN_OK;
@@ -611,9 +722,9 @@ int launch_gemm_tf32x3(const float* A, int64_t lda, const float* Bt_hi, const fl
     rgcn_set_error("gemm_tf32x3: too many tiles");
     return RGCN_ERR_INVALID;
   }
-  dim3 grid((unsigned)tiles);
-  k_gemm_tf32x3<0><<<grid, N_THREADS, SMEM_BYTES, st>>>(A, lda, Bt_hi, Bt_lo, ldb, C, ldc, M, N, K, accumulate,
-                                                         RankEpi{});
+  dim3 grid((unsigned)std::min<int64_t>(tiles, nt_grid_cap()));   // persistent: at most one CTA per SM
+  k_gemm_tf32x3<0><<<grid, N_THREADS_NT, SMEM_BYTES, st>>>(A, lda, Bt_hi, Bt_lo, ldb, C, ldc, M, N, K, accumulate,
+                                                            (int)tiles, RankEpi{});
   ++g_rgcn_launches;
   return rgcn_check_cuda(cudaGetLastError(), "k_gemm_tf32x3");
 }
@@ -637,8 +748,14 @@ int launch_gemm_rank_tf32x3(const float* Q, int64_t ldq, const float* Bt_hi, con
     attr_set = true;
   }
   RankEpi re{gold_sig, gold_col, known, words, raw_cnt, known_cnt};
-  dim3 grid((unsigned)((int64_t)((M + BM - 1) / BM) * ((N + BN - 1) / BN)));
-  k_gemm_tf32x3<1><<<grid, N_THREADS, SMEM_BYTES, st>>>(Q, ldq, Bt_hi, Bt_lo, ldb, nullptr, 0, M, N, K, 0, re);
+  const int64_t tiles = (int64_t)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  if (tiles > 0x7fffffffLL) {
+    rgcn_set_error("gemm_rank_tf32x3: too many tiles");
+    return RGCN_ERR_INVALID;
+  }
+  dim3 grid((unsigned)std::min<int64_t>(tiles, nt_grid_cap()));
+  k_gemm_tf32x3<1><<<grid, N_THREADS_NT, SMEM_BYTES, st>>>(Q, ldq, Bt_hi, Bt_lo, ldb, nullptr, 0, M, N, K, 0,
+                                                            (int)tiles, re);
   ++g_rgcn_launches;
   return rgcn_check_cuda(cudaGetLastError(), "k_gemm_tf32x3<rank>");
 }
@@ -659,9 +776,11 @@ int launch_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t l
   if (K == 0) return RGCN_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    int rc = rgcn_check_cuda(cudaFuncSetAttribute(k_gemm_tn_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    int rc = rgcn_check_cuda(cudaFuncSetAttribute(k_gemm_tn_tf32x3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   SMEM_BYTES),
                              "cudaFuncSetAttribute(gemm tn smem)");
+    if (!rc) rc = rgcn_check_cuda(cudaFuncSetAttribute(k_gemm_tn_tf32x3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                       SMEM_BYTES), "cudaFuncSetAttribute(gemm tn smem)");
     if (rc) return rc;
     attr_set = true;
   }
@@ -673,7 +792,10 @@ int launch_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t l
   const int kb_per_split = (kb_total + splits - 1) / splits;
   splits = (kb_total + kb_per_split - 1) / kb_per_split;
   dim3 grid(tm, tn, splits);
-  k_gemm_tn_tf32x3<<<grid, N_THREADS, SMEM_BYTES, st>>>(A, lda, B, ldb, C, ldc, M, N, K, kb_per_split);
+  if (gemm_prefetch_distance() >= 3)
+    k_gemm_tn_tf32x3<3><<<grid, N_THREADS, SMEM_BYTES, st>>>(A, lda, B, ldb, C, ldc, M, N, K, kb_per_split);
+  else
+    k_gemm_tn_tf32x3<2><<<grid, N_THREADS, SMEM_BYTES, st>>>(A, lda, B, ldb, C, ldc, M, N, K, kb_per_split);
   ++g_rgcn_launches;
   return rgcn_check_cuda(cudaGetLastError(), "k_gemm_tn_tf32x3");
 }
