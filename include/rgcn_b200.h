@@ -237,6 +237,11 @@ int rgcn_block_aggregate_backward(const rgcn_graph_t* g, int32_t d, int32_t B, c
  * so each peer segment is one call (replaces an atomic index_add over 16 GB per rank at 8 GPUs). */
 int rgcn_rows_add(float* dst, const int64_t* rows, const float* src, int64_t n, int32_t d, void* stream);
 
+/* G[i] = out[i] > 0 ? dOut[i] : 0 for i < n (n % 4 == 0): the ReLU gradient of message_gcn.py:64-66 as its own pass.
+ * rgcn_block_backward applies it internally; the node-sharded layers need G before their first backward kernel
+ * (the halo-source messages run first so that their gradients can travel while the local work runs). */
+int rgcn_relu_backward(const float* dOut, const float* out, float* G, int64_t n, void* stream);
+
 /* dst[i, :] = src[rows[i], :] for i < n (rows int64, device).  The halo PUSH of the node-sharded path: `dst` may be
  * (and in that path is) a PEER GPU's buffer mapped into this process (CUDA symmetric / IPC memory), so the rows a
  * peer needs go from H straight over NVLink into the buffer its aggregation kernel reads -- no packed send buffer,

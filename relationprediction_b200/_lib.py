@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = [
     "rgcn_graph_destroy", "rgcn_graph_info",
     "rgcn_graph_export_bytes", "rgcn_graph_export",
     "rgcn_block_workspace_bytes", "rgcn_block_forward", "rgcn_block_backward",
-    "rgcn_block_aggregate_workspace_bytes", "rgcn_block_aggregate", "rgcn_block_aggregate_backward", "rgcn_rows_add", "rgcn_rows_gather",
+    "rgcn_block_aggregate_workspace_bytes", "rgcn_block_aggregate", "rgcn_block_aggregate_backward", "rgcn_rows_add", "rgcn_rows_gather", "rgcn_relu_backward",
     "rgcn_basis_workspace_bytes", "rgcn_basis_forward", "rgcn_basis_backward",
     "distmult_forward", "distmult_backward", "distmult_rank_workspace_bytes", "distmult_rank",
     "distmult_backward_slices", "rgcn_block_slice_sumsq_workspace_bytes", "rgcn_block_slice_sumsq",
@@ -104,6 +104,8 @@ def _declare(lib):
                                                   c_int64, vp]
     lib.rgcn_rows_add.restype = c_int
     lib.rgcn_rows_add.argtypes = [vp, vp, vp, c_int64, c_int32, vp]
+    lib.rgcn_relu_backward.restype = c_int
+    lib.rgcn_relu_backward.argtypes = [vp, vp, vp, c_int64, vp]
     lib.rgcn_rows_gather.restype = c_int
     lib.rgcn_rows_gather.argtypes = [vp, vp, vp, c_int64, c_int32, c_int32, vp]
     lib.rgcn_basis_workspace_bytes.restype = c_int64

@@ -420,6 +420,18 @@ def rows_add_(dst, rows, src):
     return dst
 
 
+def relu_backward(dOut, out):
+    """G = dOut * (out > 0) in one pass (rgcn_relu_backward)."""
+    lib = _lib.load()
+    dOut = dOut.contiguous()
+    _check_cuda_f32("dOut", dOut)
+    _check_cuda_f32("out", out, dOut.shape)
+    G = torch.empty_like(dOut)
+    _lib.check(lib.rgcn_relu_backward(_ptr(dOut), _ptr(out), _ptr(G), dOut.numel(), _stream(dOut.device)),
+               "rgcn_relu_backward")
+    return G
+
+
 def rows_gather_to(dst_ptr, src, rows, max_ctas=0):
     """memory at dst_ptr [len(rows), d] = src[rows] (rgcn_rows_gather).  dst_ptr is a raw device address, normally a
     PEER GPU's halo buffer mapped into this process (parallel.PeerHalo): the halo push of the node-sharded path."""

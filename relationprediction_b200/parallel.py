@@ -299,8 +299,10 @@ class _OverlappedBlockLayer(torch.autograd.Function):
         sg, B = ctx.sg, ctx.n_blocks
         p = sg.plan
         slot = ctx.slot
-        G = (dOut * (out > 0)) if ctx.relu else dOut
-        G = G.contiguous()
+        if ctx.relu and dOut.is_cuda and dOut.dtype == torch.float32 and dOut.numel() % 4 == 0:
+            G = ops.relu_backward(dOut, out)       # one pass (torch: compare + multiply, 35 GB instead of 30)
+        else:
+            G = ((dOut * (out > 0)) if ctx.relu else dOut).contiguous()
         if p.n_halo > 0:
             dHalo, dWf, dWb = ops.block_aggregate_backward(H_halo, Wf, Wb, G, sg.graph_halo, B)
         else:  # empty halo: nothing to send back, no halo contribution to the block weight gradients

@@ -3,7 +3,7 @@
 N=${1:-2}
 MODES=${2:-"peer nccl"}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parallel.py -q -m gpu -x -k "2 and (peer or device or overlapped)" > gpurun_out/r2_peer_tests_n$N.txt 2>&1
+timeout 600 python -m pytest tests/test_gpu_parallel.py -q -m gpu -x -k "${3:-2 and (peer or device or overlapped)}" > gpurun_out/r2_peer_tests_n$N.txt 2>&1
 echo "pytest rc=$?" >> gpurun_out/r2_peer_tests_n$N.txt
 tail -15 gpurun_out/r2_peer_tests_n$N.txt
 for tr in $MODES; do
