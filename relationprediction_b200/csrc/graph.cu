@@ -174,7 +174,10 @@ rgcn_graph* new_graph(int64_t M, int32_t V_dst, int32_t V_src, int32_t n_relw, i
   }
   if (const char* e = std::getenv("RGCN_SUPERTILE_ROWS")) {
     int v = std::atoi(e);
-    if (v >= 1) g->supertile_rows = v;
+    if (v >= 1) {
+      g->supertile_rows = v;
+      g->supertile_fixed = true;
+    }
   }
   // message-id permutations are only needed by rgcn_graph_export: skip them on very large graphs
   g->keep_mid = M <= (int64_t)(16 << 20);
@@ -289,10 +292,11 @@ int build(const int32_t* dst, const int32_t* src, const int32_t* relw, const flo
     });
     // weight-id major views (see RelSide)
     std::thread t2 = guarded(2, [&]() {
-      build_rel_side(g->by_rel, dst, V_dst, src, relw, norm, M, n_relw, g->supertile_rows, g->item_max);
+      build_rel_side(g->by_rel, dst, V_dst, src, relw, norm, M, n_relw, view_supertile_rows(g, V_dst, M),
+                     g->item_max);
     });
     std::thread t3 = guarded(3, [&]() {
-      build_rel_side(g->by_rel_src, src, V_src, dst, relw, norm, M, n_relw, g->supertile_rows,
+      build_rel_side(g->by_rel_src, src, V_src, dst, relw, norm, M, n_relw, view_supertile_rows(g, V_src, M),
                      g->item_max);
     });
     t0.join();

@@ -71,12 +71,31 @@ struct rgcn_graph {
   RelSide by_rel;               // weight-id major, row = dst, nbr = src  (forward, dW)
   RelSide by_rel_src;           // weight-id major, row = src, nbr = dst  (backward w.r.t. H)
   int supertile_rows = 8192;
+  bool supertile_fixed = false;  // $RGCN_SUPERTILE_ROWS given: every view uses exactly supertile_rows
   bool built_on_device = false;  // structures were built by graph_device.cu (host vectors empty)
   bool keep_mid = true;          // keep message-id permutations / original-order norm for export
   bool has_csr = true;           // by_dst / by_src built (deterministic block mode, basis layers)
   bool has_rel = true;           // by_rel / by_rel_src built (weight-id-major block kernels)
   float* d_msg_norm = nullptr;
 };
+
+// Rows per supertile of ONE weight-id-major view.  The default (8192 rows = a 16 MB accumulation window at d = 512)
+// suits views with >= ~48 messages per (supertile, weight id) work item.  A sparse view -- the halo-source view of a
+// node shard at 8 GPUs: 22 M messages over 8 M halo rows x 2000 weight ids = 11 per item -- spends its time loading
+// the item's 16 KB of block weights; there the supertiles grow (x2 steps, at most 32768 rows = a 64 MB window, still
+// L2-resident next to the evict-first gather stream) until the items are long enough.  Host and device builders
+// share this rule (bit-identical views).
+inline int view_supertile_rows(const rgcn_graph* g, int32_t n_rows, int64_t M) {
+  int rows = g->supertile_rows;
+  if (g->supertile_fixed || rows <= 0) return rows;
+  while (rows < 32768) {
+    const int64_t n_super = ((int64_t)n_rows + rows - 1) / rows;
+    const int64_t items = (n_super > 0 ? n_super : 1) * (int64_t)(g->n_relw > 0 ? g->n_relw : 1);
+    if (M >= 48 * items) break;   // >= 48 messages per (supertile, weight id) on average
+    rows *= 2;
+  }
+  return rows;
+}
 
 // graph_device.cu
 int rgcn_build_on_device(rgcn_graph* g, const int32_t* d_dst, const int32_t* d_src,

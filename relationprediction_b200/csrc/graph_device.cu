@@ -343,14 +343,15 @@ int rel_phase_a(rgcn_graph* g, RelSide& side, ViewTmp& t, const int32_t* row, in
                 int32_t* h_total /* pinned [1] */, cudaStream_t st, int64_t& bytes) {
   Scratch sc(st);
   int rc;
-  const int32_t n_super = std::max(1, (n_rows + g->supertile_rows - 1) / g->supertile_rows);
+  const int st_rows = view_supertile_rows(g, n_rows, M);
+  const int32_t n_super = std::max(1, (n_rows + st_rows - 1) / st_rows);
   side.n_super = n_super;
   const int64_t nkeys = (int64_t)n_super * g->n_relw;
   t.n_keys = (int32_t)nkeys;
   if ((rc = dalloc(&side.d_ptr, nkeys + 1, st, &bytes))) return rc;
   int32_t* perm;
   uint64_t* keys;
-  if ((rc = sort_view(sc, row, relw, M, 1, g->n_relw, g->supertile_rows, (uint64_t)nkeys,
+  if ((rc = sort_view(sc, row, relw, M, 1, g->n_relw, st_rows, (uint64_t)nkeys,
                       (uint64_t)std::max(n_rows, 1), &perm, &keys, side.d_ptr, st)))
     return rc;
   if ((rc = dalloc(&side.d_row, M, st, &bytes))) return rc;
