@@ -181,10 +181,12 @@ class PeerHalo(object):
         self.peer_halo_off = [int(table[q, 2 + me]) for q in range(P)]
         self.peer_back_off = [int(table[q, 2 + P + me]) for q in range(P)]
         self.d = int(d)
-        try:
-            symm.enable_symm_mem_for_group(group.group_name)
-        except Exception:   # newer torch enables every group implicitly
-            pass
+        with warnings.catch_warnings():   # needed by torch <= 2.8, a deprecated no-op afterwards
+            warnings.simplefilter("ignore")
+            try:
+                symm.enable_symm_mem_for_group(group.group_name)
+            except Exception:
+                pass
         self.buf = symm.empty((self.halo_rows + self.back_rows, self.d), dtype=torch.float32, device=dev)
         self.hdl = symm.rendezvous(self.buf, group)
         self.halo = self.buf[:self.halo_rows]
