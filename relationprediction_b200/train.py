@@ -205,6 +205,12 @@ def main(argv=None):
                     "ModelSaver cadence to General.ExperimentName)")
     ap.add_argument("--save-path", default=None, help="checkpoint path prefix (default: General.ExperimentName)")
     ap.add_argument("--device", default="cuda:0")
+    ap.add_argument("--repeat-sample", action="store_true",
+                    help="diagnostic: train on the FIRST sample forever (takes the host sampler out of the iteration time)")
+    ap.add_argument("--profile-iterations", type=int, default=0, metavar="N",
+                    help="diagnostic: after 50 warm-up iterations run N iterations with a device sync after every "
+                         "phase (sample wait / forward+loss / backward / optimizer), print the mean ms per phase as one "
+                         "JSON line and exit")
     args = ap.parse_args(argv)
     if (args.dataset is None) == (args.dataset_npz is None):
         ap.error("give exactly one of --dataset / --dataset-npz")
@@ -309,6 +315,50 @@ def main(argv=None):
     # sample transform of step i+1 behind the GPU work of step i
     running, it, last_avg = None, 0, None
     stream = sample_stream(sample, args.prefetch)
+    if args.repeat_sample:
+        first = next(stream)
+        stream.close()
+        stream = iter(lambda: first, None)
+    if args.profile_iterations > 0:
+        import torch
+        sync = torch.cuda.synchronize if str(args.device).startswith("cuda") else (lambda: None)
+        acc = {"sample_wait": 0.0, "forward_loss": 0.0, "backward": 0.0, "optimizer": 0.0}
+        t_free = 0.0
+        for i in range(50 + 2 * args.profile_iterations):
+            timed = 50 <= i < 50 + args.profile_iterations       # phase-synchronised iterations
+            free = i >= 50 + args.profile_iterations              # the same number of iterations, free-running
+            if free and t_free == 0.0:
+                sync()
+                t_free = -time.time()
+            t0 = time.time()
+            batch = next(stream)
+            t1 = time.time()
+            optimizer.zero_grad()
+            loss = model.train_loss(*batch)
+            if timed:
+                sync()
+            t2 = time.time()
+            loss.backward()
+            if timed:
+                sync()
+            t3 = time.time()
+            optimizer.step()
+            if timed:
+                sync()
+            t4 = time.time()
+            if timed:
+                for k, v in zip(acc, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+                    acc[k] += v
+        sync()
+        t_free += time.time()
+        n = args.profile_iterations
+        print(json.dumps({"profile_iterations": n, "phase_ms": {k: round(v / n * 1e3, 3) for k, v in acc.items()},
+                          "phase_sum_ms": round(sum(acc.values()) / n * 1e3, 3),
+                          "free_running_ms_per_iteration": round(t_free / n * 1e3, 3),
+                          "prefetch_threads": args.prefetch, "repeat_sample": bool(args.repeat_sample)}))
+        if hasattr(stream, "close"):
+            stream.close()
+        return
     t_start = time.time()
     while it < max_it:
         if args.time_budget is not None and time.time() - t_start > args.time_budget:
@@ -334,7 +384,8 @@ def main(argv=None):
         if save_every is not None and it % save_every == 0:
             model.save(save_path)
     train_seconds = time.time() - t_start
-    stream.close()
+    if hasattr(stream, "close"):
+        stream.close()
     if args.final_eval is not None:
         part = test if args.final_eval == 0 else test[:args.final_eval]
         t0 = time.time()
