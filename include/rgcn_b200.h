@@ -89,6 +89,13 @@ int rgcn_sample_edge_neighborhood(const int32_t* triples_host, int64_t E, int32_
 typedef struct rgcn_sampler rgcn_sampler_t;
 int rgcn_sampler_create(const int32_t* triples_host, int64_t E, int32_t V, rgcn_sampler_t** out);
 int rgcn_sampler_draw(const rgcn_sampler_t* sampler, int64_t sample_size, uint64_t seed, int32_t* out_edges_host);
+/* One whole training sample of train.py:140-198 in one call (so that the host threads preparing samples hold no
+ * interpreter lock): batch = rgcn_sampler_draw(batch) edges; graph_split_host [split,3] = `split` of them uniformly
+ * without replacement (np.random.choice(ids, split, replace=False)); X_host [(neg_rate+1)*batch, 3] / Y_host = the batch
+ * followed by neg_rate corrupted copies with labels 1 / 0 (common/auxilliaries.py NegativeSampler.transform: fair coin
+ * object-or-subject, uniform replacement entity).  Same stochastic process, own random stream. */
+int rgcn_sampler_draw_batch(const rgcn_sampler_t* sampler, int32_t batch, int32_t split, int32_t neg_rate, uint64_t seed,
+                            int32_t* graph_split_host, int32_t* X_host, float* Y_host);
 void rgcn_sampler_destroy(rgcn_sampler_t* sampler);
 
 /* Next row N1: global-norm clipping + Adam with TensorFlow-1.x semantics

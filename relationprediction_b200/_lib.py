@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "librgcn_b200.so")
 # every symbol include/rgcn_b200.h declares (tests check the .so exports all of them)
 EXPORTED_SYMBOLS = [
     "rgcn_version", "rgcn_last_error", "rgcn_launch_count", "rgcn_profile_enable", "rgcn_profile_read",
-    "rgcn_set_option", "rgcn_gemm_tf32x3", "rgcn_gemm_tn_tf32x3", "rgcn_graph_destroy_async", "rgcn_sample_edge_neighborhood", "rgcn_sampler_create", "rgcn_sampler_draw", "rgcn_sampler_destroy", "rgcn_sumsq_accumulate", "rgcn_adam_update",
+    "rgcn_set_option", "rgcn_gemm_tf32x3", "rgcn_gemm_tn_tf32x3", "rgcn_graph_destroy_async", "rgcn_sample_edge_neighborhood", "rgcn_sampler_create", "rgcn_sampler_draw", "rgcn_sampler_draw_batch", "rgcn_sampler_destroy", "rgcn_sumsq_accumulate", "rgcn_adam_update",
     "rgcn_graph_create", "rgcn_graph_create_messages", "rgcn_graph_create_device", "rgcn_graph_create_messages_device",
     "rgcn_graph_destroy", "rgcn_graph_info",
     "rgcn_graph_export_bytes", "rgcn_graph_export",
@@ -53,6 +53,8 @@ def _declare(lib):
     lib.rgcn_sampler_create.argtypes = [vp, c_int64, c_int32, ctypes.POINTER(vp)]
     lib.rgcn_sampler_draw.restype = c_int
     lib.rgcn_sampler_draw.argtypes = [vp, c_int64, ctypes.c_uint64, vp]
+    lib.rgcn_sampler_draw_batch.restype = c_int
+    lib.rgcn_sampler_draw_batch.argtypes = [vp, c_int32, c_int32, c_int32, ctypes.c_uint64, vp, vp, vp]
     lib.rgcn_sampler_destroy.restype = None
     lib.rgcn_sampler_destroy.argtypes = [vp]
     lib.rgcn_sumsq_accumulate.restype = c_int

@@ -56,7 +56,7 @@ struct Fenwick {
 struct rgcn_sampler {
   int64_t E = 0;
   int32_t V = 0;
-  std::vector<int32_t> sub, obj;             // endpoints of every edge
+  std::vector<int32_t> sub, obj, rel;        // endpoints and relation of every edge
   std::vector<int64_t> off;                  // V+1 list offsets
   std::vector<int32_t> inc_edge, inc_other;  // 2E entries: every edge once per endpoint
   std::vector<int32_t> pos_s, pos_o;         // where the edge sits in its subject's / object's list
@@ -74,6 +74,7 @@ int sampler_build(const int32_t* triples_host, int64_t E, int32_t V, rgcn_sample
   sp.V = V;
   sp.sub.resize((size_t)E);
   sp.obj.resize((size_t)E);
+  sp.rel.resize((size_t)E);
   sp.off.assign((size_t)V + 1, 0);
   for (int64_t e = 0; e < E; ++e) {
     const int32_t s = triples_host[3 * e], o = triples_host[3 * e + 2];
@@ -83,6 +84,7 @@ int sampler_build(const int32_t* triples_host, int64_t E, int32_t V, rgcn_sample
     }
     sp.sub[e] = s;
     sp.obj[e] = o;
+    sp.rel[e] = triples_host[3 * e + 1];
     sp.off[s + 1]++;
     sp.off[o + 1]++;
   }
@@ -221,6 +223,86 @@ extern "C" int rgcn_sampler_draw(const rgcn_sampler* sp, int64_t sample_size, ui
     return sampler_draw(*sp, sample_size, seed, out_edges_host);
   } catch (const std::bad_alloc&) {
     rgcn_set_error("rgcn_sampler_draw: out of host memory");
+    return RGCN_ERR_NOMEM;
+  }
+}
+
+// One whole training sample in a single call: the host threads that prepare samples then spend their time here, with
+// the interpreter lock released, instead of in a dozen small numpy calls that fight the training thread for it
+// (measured on FB15k-237: the iteration was 6.3 ms with the numpy pipeline on 12 threads, 2.7 ms on a repeated sample).
+//   batch edges  = sampler_draw(batch)                                  (train.py:161-198, sample_edge_neighborhood)
+//   graph_split  = `split` of them, uniformly without replacement       (train.py:147-148, np.random.choice)
+//   X, Y         = the batch followed by neg_rate corrupted copies      (common/auxilliaries.py, NegativeSampler.transform:
+//                  copy k of triple i sits at row (k+1)*batch + i; a fair coin picks object or subject, the
+//                  replacement is uniform over the V entities; labels 1 for the batch, 0 for the copies)
+extern "C" int rgcn_sampler_draw_batch(const rgcn_sampler* sp, int32_t batch, int32_t split, int32_t neg_rate,
+                                       uint64_t seed, int32_t* graph_split_host, int32_t* X_host, float* Y_host) {
+  if (!sp || batch <= 0 || batch > sp->E || split < 0 || split > batch || neg_rate < 0 || !X_host || !Y_host ||
+      (split > 0 && !graph_split_host)) {
+    rgcn_set_error("rgcn_sampler_draw_batch: need 0 < batch <= E, 0 <= split <= batch, neg_rate >= 0, outputs");
+    return RGCN_ERR_INVALID;
+  }
+  try {
+    std::vector<int32_t> ids((size_t)batch);
+    const int rc = sampler_draw(*sp, batch, seed, ids.data());
+    if (rc != RGCN_OK) return rc;
+    std::mt19937_64 rng(seed ^ 0x9e3779b97f4a7c15ull);
+    auto below = [&](uint64_t n) {   // unbiased integer in [0, n): multiply-shift with rejection (Lemire)
+      uint64_t x = rng();
+      __uint128_t m = (__uint128_t)x * n;
+      uint64_t l = (uint64_t)m;
+      if (l < n) {
+        const uint64_t t = (0 - n) % n;
+        while (l < t) {
+          x = rng();
+          m = (__uint128_t)x * n;
+          l = (uint64_t)m;
+        }
+      }
+      return (uint64_t)(m >> 64);
+    };
+    for (int32_t i = 0; i < batch; ++i) {
+      const int32_t e = ids[i];
+      X_host[3 * (size_t)i] = sp->sub[e];
+      X_host[3 * (size_t)i + 1] = sp->rel[e];
+      X_host[3 * (size_t)i + 2] = sp->obj[e];
+      Y_host[i] = 1.0f;
+    }
+    // graph split: partial Fisher-Yates over a copy of the sampled ids
+    {
+      std::vector<int32_t> pool(ids);
+      for (int32_t i = 0; i < split; ++i) {
+        const int64_t j = i + (int64_t)below((uint64_t)(batch - i));
+        std::swap(pool[i], pool[j]);
+        const int32_t e = pool[i];
+        graph_split_host[3 * (size_t)i] = sp->sub[e];
+        graph_split_host[3 * (size_t)i + 1] = sp->rel[e];
+        graph_split_host[3 * (size_t)i + 2] = sp->obj[e];
+      }
+    }
+    for (int32_t k = 0; k < neg_rate; ++k) {
+      int32_t* Xk = X_host + 3 * (size_t)(k + 1) * batch;
+      float* Yk = Y_host + (size_t)(k + 1) * batch;
+      uint64_t coins = 0;
+      int n_coins = 0;
+      for (int32_t i = 0; i < batch; ++i) {
+        if (n_coins == 0) {
+          coins = rng();
+          n_coins = 64;
+        }
+        const bool corrupt_object = coins & 1u;
+        coins >>= 1;
+        --n_coins;
+        const int32_t v = (int32_t)below((uint64_t)sp->V);
+        Xk[3 * (size_t)i] = corrupt_object ? X_host[3 * (size_t)i] : v;
+        Xk[3 * (size_t)i + 1] = X_host[3 * (size_t)i + 1];
+        Xk[3 * (size_t)i + 2] = corrupt_object ? v : X_host[3 * (size_t)i + 2];
+        Yk[i] = 0.0f;
+      }
+    }
+    return RGCN_OK;
+  } catch (const std::bad_alloc&) {
+    rgcn_set_error("rgcn_sampler_draw_batch: out of host memory");
     return RGCN_ERR_NOMEM;
   }
 }

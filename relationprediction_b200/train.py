@@ -142,6 +142,23 @@ class EdgeNeighborhoodSampler(object):
         self._lib.check(rc, "rgcn_sampler_draw")
         return out
 
+    def draw_batch(self, batch, split, neg_rate, seed=None):
+        """One whole training sample (graph_split [split,3], X [(neg_rate+1)*batch,3], Y) from ONE library call
+        (rgcn_sampler_draw_batch): edge-neighbourhood sample, graph split and negative sampling run with the interpreter
+        lock released, so sample threads do not slow the training thread down."""
+        import ctypes
+        batch, split, neg_rate = int(batch), int(split), int(neg_rate)
+        graph_split = np.empty((split, 3), dtype=np.int32)
+        X = np.empty(((neg_rate + 1) * batch, 3), dtype=np.int32)
+        Y = np.empty((neg_rate + 1) * batch, dtype=np.float32)
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1))
+        rc = self._lib.load().rgcn_sampler_draw_batch(self._h, batch, split, neg_rate, int(seed),
+                                                      ctypes.c_void_p(graph_split.ctypes.data),
+                                                      ctypes.c_void_p(X.ctypes.data), ctypes.c_void_p(Y.ctypes.data))
+        self._lib.check(rc, "rgcn_sampler_draw_batch")
+        return graph_split, X, Y
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.load().rgcn_sampler_destroy(self._h)
@@ -205,6 +222,9 @@ def main(argv=None):
                     "ModelSaver cadence to General.ExperimentName)")
     ap.add_argument("--save-path", default=None, help="checkpoint path prefix (default: General.ExperimentName)")
     ap.add_argument("--device", default="cuda:0")
+    ap.add_argument("--numpy-sampling", action="store_true",
+                    help="build the graph split and the negative samples with numpy (the reference's calls) instead of "
+                         "the library's one-call sample (rgcn_sampler_draw_batch)")
     ap.add_argument("--repeat-sample", action="store_true",
                     help="diagnostic: train on the FIRST sample forever (takes the host sampler out of the iteration time)")
     ap.add_argument("--profile-iterations", type=int, default=0, metavar="N",
@@ -269,6 +289,9 @@ def main(argv=None):
         if not encoder.needs_graph():
             X, Y = ns.transform(train)
             return (X, Y)
+        if edge_sampler is not None and not args.numpy_sampling:
+            gbs = int(general['GraphBatchSize'])   # the whole sample in one library call (no interpreter lock held)
+            return edge_sampler.draw_batch(gbs, int(float(general['GraphSplitSize']) * gbs), ns.negative_sample_rate)
         if 'GraphBatchSize' in general and int(general['GraphBatchSize']) < len(train):
             ids = edge_sampler.draw(int(general['GraphBatchSize']))
         else:

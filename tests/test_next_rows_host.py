@@ -236,3 +236,45 @@ def test_sampler_handle_matches_one_shot_and_is_thread_compatible():
     with pytest.raises(_lib.RgcnError):
         s.draw(E + 1)
     s.close()
+
+
+def test_one_call_training_sample_structure_and_distribution():
+    """rgcn_sampler_draw_batch: the batch is the edge-neighbourhood sample of the same seed, the graph split a
+    duplicate-free subset of it, the negatives follow NegativeSampler.transform's layout (copy k of triple i at row
+    (k+1)*n + i, relation kept, exactly one of subject / object replaced by a uniform entity, fair coin), labels 1/0;
+    deterministic per seed; bad sizes are refused."""
+    from relationprediction_b200 import _lib
+    from relationprediction_b200.train import EdgeNeighborhoodSampler
+    rng = np.random.RandomState(9)
+    V, E, R = 400, 6000, 7
+    tr = np.unique(np.stack([rng.randint(0, V, E), rng.randint(0, R, E), rng.randint(0, V, E)], 1).astype(np.int32), axis=0)
+    E = len(tr)
+    s = EdgeNeighborhoodSampler(tr, V)
+    n, split, k = 2000, 900, 10
+    gs, X, Y = s.draw_batch(n, split, k, seed=11)
+    assert gs.shape == (split, 3) and X.shape == ((k + 1) * n, 3) and Y.shape == ((k + 1) * n,)
+    assert np.array_equal(X[:n], tr[s.draw(n, seed=11)])            # same batch as the plain draw of that seed
+    assert (Y[:n] == 1).all() and (Y[n:] == 0).all()
+    batch = set(map(tuple, X[:n].tolist()))
+    assert len(batch) == n
+    split_rows = list(map(tuple, gs.tolist()))
+    assert len(set(split_rows)) == split and all(r in batch for r in split_rows)
+    pos, neg = np.tile(X[:n], (k, 1)), X[n:]
+    assert np.array_equal(neg[:, 1], pos[:, 1])
+    ds, do = neg[:, 0] != pos[:, 0], neg[:, 2] != pos[:, 2]
+    assert not (ds & do).any()                                       # never both ends
+    assert neg[:, [0, 2]].min() >= 0 and neg[:, [0, 2]].max() < V
+    # fair coin (a replacement equal to the original hides 1/V of the corruptions on either side)
+    assert abs(ds.mean() - 0.5) < 0.02 and abs(do.mean() - 0.5) < 0.02
+    # replacement entities uniform over V: chi-square over the object-corrupted rows
+    counts = np.bincount(neg[do, 2], minlength=V).astype(np.float64)
+    chi2 = ((counts - counts.mean()) ** 2 / counts.mean()).sum()
+    assert chi2 < V + 6 * np.sqrt(2 * V)
+    g2, X2, _ = s.draw_batch(n, split, 0, seed=11)
+    assert np.array_equal(g2, gs) and np.array_equal(X2, X[:n])          # deterministic per seed, independent of k
+    g3, X3, Y3 = s.draw_batch(n, 0, 0, seed=5)
+    assert g3.shape == (0, 3) and X3.shape == (n, 3) and (Y3 == 1).all()
+    for bad in ((0, 0, 1), (E + 1, 0, 1), (10, 11, 1), (10, 5, -1)):
+        with pytest.raises(_lib.RgcnError):
+            s.draw_batch(*bad)
+    s.close()
