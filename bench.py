@@ -255,6 +255,21 @@ def lib_stamp():
         return None
 
 
+def kernel_source_stamp():
+    """Fingerprint of the sources of the aggregation kernels whose DRAM traffic profiles/r2_traffic.json records
+    (csrc/block_staged.cu + csrc/kernels.cuh): the traffic entry is stale when THESE change, not when any other part
+    of the library does."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in ("block_staged.cu", "kernels.cuh"):
+        try:
+            with open(os.path.join(ROOT, "relationprediction_b200", "csrc", name), "rb") as fh:
+                h.update(fh.read())
+        except OSError:
+            return None
+    return h.hexdigest()[:16]
+
+
 def relerr(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
@@ -530,7 +545,7 @@ def main():
                         tj = json.load(fh)
                     ent = tj.get("%s|%s" % (args.workload, spec.get("scale", "")), {})
                     traffic = ent.get(top)
-                    stale = bool(ent.get("lib_stamp") != lib_stamp()) if traffic is not None else None
+                    stale = bool(ent.get("kernel_source_stamp") != kernel_source_stamp()) if traffic is not None else None
                 roofline = {"kernel": top + (" (rank 0 shard)" if world > 1 else ""), "bound": "hbm", "achieved": achieved,
                             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                             "traffic_stale": stale,

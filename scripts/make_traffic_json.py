@@ -33,7 +33,8 @@ def main():
         rows = list(csv.reader(open(src)))
         hdr, units = rows[0], rows[1]
         ix = {h: i for i, h in enumerate(hdr)}
-        ent = {"lib_stamp": bench.lib_stamp(), "source": os.path.basename(src)}
+        ent = {"lib_stamp": bench.lib_stamp(), "kernel_source_stamp": bench.kernel_source_stamp(),
+               "source": os.path.basename(src)}
         for r in rows[2:]:
             st = stage_of(r[ix["Kernel Name"]])
             if st is None or st in ent:
