@@ -83,10 +83,27 @@ def messages_from_triples(triples, n_relations, n_vertices, mode="canonical"):
     return dst, src, relw, norm
 
 
-def sorted_views(dst, src, relw, norm, V_dst, V_src, n_relw, supertile_rows=32768):
+def view_supertile_rows(base_rows, n_rows, M, n_relw, fixed=False):
+    """Rows per supertile of one weight-id-major view (the library's view_supertile_rows, csrc/graph.h): the base
+    size doubles, up to 32768 rows, while the view averages fewer than 48 messages per (supertile, weight id) item;
+    `fixed` = the size was forced by $RGCN_SUPERTILE_ROWS."""
+    rows = int(base_rows)
+    if fixed or rows <= 0:
+        return rows
+    while rows < 32768:
+        n_super = max(1, -(-int(n_rows) // rows))
+        if M >= 48 * n_super * max(int(n_relw), 1):
+            break
+        rows *= 2
+    return rows
+
+
+def sorted_views(dst, src, relw, norm, V_dst, V_src, n_relw, supertile_rows=32768, adaptive=False):
     """Reference (numpy lexsort, stable) for the three sorted message views the library builds.
     Not in the TF reference (it uses COO matrices); this pins the bit-exact index work of the
-    graph-prep step against an independent implementation."""
+    graph-prep step against an independent implementation.  adaptive: apply view_supertile_rows per view
+    (what the library does unless the size is forced through the environment)."""
+    base_rows = supertile_rows
     M = dst.shape[0]
     mid = np.arange(M, dtype=np.int32)
     out = {}
@@ -98,6 +115,7 @@ def sorted_views(dst, src, relw, norm, V_dst, V_src, n_relw, supertile_rows=3276
     out["src_dst"], out["src_relw"], out["src_norm"], out["src_mid"] = dst[p], relw[p], norm[p], mid[p]
     # weight-id major views keyed (supertile(row), relw, row)
     for name, row, nbr, n_rows in (("rel", dst, src, V_dst), ("rel2", src, dst, V_src)):
+        supertile_rows = view_supertile_rows(base_rows, n_rows, M, n_relw, fixed=not adaptive)
         n_super = max(1, -(-n_rows // supertile_rows))
         key = (row // supertile_rows).astype(np.int64) * n_relw + relw
         p = np.lexsort((mid, row, key))

@@ -24,7 +24,8 @@ def test_library_loads_and_exports_header_symbols():
 
 
 def _check_views(g, dst, src, relw, norm, V_dst, V_src, n_relw):
-    ref = oracle.sorted_views(dst, src, relw, norm, V_dst, V_src, n_relw, g.info()[13])
+    ref = oracle.sorted_views(dst, src, relw, norm, V_dst, V_src, n_relw, g.info()[13],
+                              adaptive="RGCN_SUPERTILE_ROWS" not in os.environ)
     pairs = [(_lib.X_DST_ROWPTR, "dst_rowptr"), (_lib.X_DST_SRC, "dst_src"), (_lib.X_DST_RELW, "dst_relw"),
              (_lib.X_DST_NORM, "dst_norm"), (_lib.X_DST_MID, "dst_mid"), (_lib.X_SRC_ROWPTR, "src_rowptr"),
              (_lib.X_SRC_DST, "src_dst"), (_lib.X_SRC_RELW, "src_relw"), (_lib.X_SRC_NORM, "src_norm"),
@@ -83,6 +84,27 @@ def test_supertiled_weight_major_views(monkeypatch):
     tr = synthetic_kg(V, R, E, seed=9, skewed=True)
     g = Graph(tr, V, R)
     assert g.info()[13] == 257 and g.info()[14] == 12
+    dst, src, relw, norm = oracle.messages_from_triples(tr, R, V)
+    _check_views(g, dst, src, relw, norm, V, V, 2 * R)
+
+
+def test_sparse_views_get_larger_supertiles():
+    """view_supertile_rows: a weight-id-major view with fewer than 48 messages per (supertile, weight id) item grows
+    its supertiles x2 up to 32768 rows; dense views keep the default 8192; the views stay exact either way."""
+    V, R = 40000, 20
+    tr = synthetic_kg(V, R, 1000, seed=3, skewed=False)            # 2000 messages over 5 x 40 default items: sparse
+    g = Graph(tr, V, R)
+    assert g.info()[13] == 8192 and g.info()[14] == 2               # capped at 32768 rows: ceil(40000 / 32768)
+    dst, src, relw, norm = oracle.messages_from_triples(tr, R, V)
+    _check_views(g, dst, src, relw, norm, V, V, 2 * R)
+    tr = synthetic_kg(V, 2, 60000, seed=4, skewed=False)           # 120000 messages over 5 x 4 items: dense
+    g = Graph(tr, V, 2)
+    assert g.info()[14] == 5
+    # in between: one doubling is enough (16384 rows: 3 supertiles x 40 weight ids x 48 <= 6000 messages)
+    tr = synthetic_kg(V, R, 3000, seed=5, skewed=False)
+    assert 3 * 40 * 48 <= 6000 < 5 * 40 * 48
+    g = Graph(tr, V, R)
+    assert g.info()[14] == 3
     dst, src, relw, norm = oracle.messages_from_triples(tr, R, V)
     _check_views(g, dst, src, relw, norm, V, V, 2 * R)
 
