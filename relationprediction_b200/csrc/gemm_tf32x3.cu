@@ -4,18 +4,22 @@
 //
 // Used for the self-loop terms of the R-GCN layer (H @ W_self, dS @ W_self^T; reference:
 // gcn_basis.py:70-71 / gcn_basis_concat.py:65-66 `tf.matmul`).  The 1e-4 parity bar rules out a
-// single TF32 pass (10-bit mantissa), so every fp32 operand is split a = a_hi + a_lo with a_hi
-// exactly representable in TF32 (round-to-nearest, cvt.rna.tf32.f32) and three MMAs are issued per
-// K-step:  a_hi*b_hi + a_hi*b_lo + a_lo*b_hi   (the a_lo*b_lo term is below fp32 rounding).
+// single TF32 pass (10-bit mantissa), so every fp32 operand is split a = a_hi + a_lo with both parts exact
+// TF32 values (the streamed operand by truncation in the producers, the small pre-split operand with
+// cvt.rna.tf32.f32) and three MMAs are issued per K-step:  a_hi*b_hi + a_hi*b_lo + a_lo*b_hi
+// (the a_lo*b_lo term is below fp32 rounding).
 //
-// Structure (one CTA per 128x128 output tile, 288 threads, 1 CTA/SM):
-//   warps 0-7  producers: global fp32 -> registers -> (hi, lo) -> st.shared in the UMMA canonical
-//              K-major SWIZZLE_128B layout for A; cp.async of the pre-split Bt_hi / Bt_lo tiles;
-//              fence.proxy.async + mbarrier arrive.  After the main loop they become the epilogue:
-//              tcgen05.ld of the accumulator rows -> global stores.
-//   warp 8     one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=128, K=8), 12 per
-//              32-wide K block, and frees smem stages / publishes the accumulator with tcgen05.commit.
-//   3-stage smem ring (64 KB per stage), accumulator 128 lanes x 128 columns of TMEM.
+// Structure of the NT kernel (PERSISTENT: min(tiles, SMs) CTAs of 416 threads, 1 CTA/SM, 128x128 tiles):
+//   warps 0-7   producers: global fp32 -> registers -> (hi, lo) -> st.shared in the UMMA canonical
+//               K-major SWIZZLE_128B layout for A; cp.async of the pre-split Bt_hi / Bt_lo tiles;
+//               fence.proxy.async + mbarrier arrive.  They run straight on into the next tile.
+//   warp 8      one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=128, K=8), 12 per 32-wide
+//               K block, frees smem stages and publishes the tile's accumulators with tcgen05.commit.
+//   warps 9-12  epilogue: tcgen05.ld of the accumulator rows (one TMEM lane quarter each) -> global
+//               stores (or the rank-counting epilogue), then `drained` so the set can be reused.
+//   3-stage smem ring (64 KB per stage); TMEM = two accumulator sets (tile parity) x {big, small} x 128
+//   columns, so the MMAs of tile t+1 overlap the epilogue of tile t.
+// The TN kernel (below) keeps one tile (x split-K) per CTA, 288 threads, four accumulators.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -34,10 +38,11 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
 constexpr int N_PRODUCERS = 256;  // 8 producer/epilogue warps + 1 MMA warp
 constexpr int N_THREADS = N_PRODUCERS + 32;
 constexpr int MMA_WARP = N_PRODUCERS / 32;
-// Four accumulators in TMEM (4 x 128 columns): the big hi*hi products and the small cross terms are
-// accumulated separately, each alternating between two accumulators per K block, and summed in fp32
-// registers in the epilogue.  The tensor core adds into its accumulator with truncation, so fewer,
-// same-magnitude additions per accumulator keep the result at SGEMM-level accuracy.
+// TMEM budget of both kernels: 4 x 128 columns.  The big hi*hi products and the small cross terms are always
+// accumulated separately and summed in fp32 registers in the epilogue (the tensor core adds into its accumulator
+// with truncation, so same-magnitude additions per accumulator keep the result at SGEMM-level accuracy).  The TN
+// kernel additionally alternates between two accumulators of each kind per K block (N_ACC = 4 for one tile); the
+// persistent NT kernel uses one of each per tile and the other half of TMEM for the next tile.
 constexpr int N_ACC = 4;
 constexpr int TMEM_COLS = N_ACC * BN;
 

@@ -154,6 +154,14 @@ class ShardPlanDevice(object):
         self.send_rows = (keys % n_nodes) - lo                  # int64, grouped by peer, ascending id inside
 
 
+def all_ranks_agree(ok, group, device):
+    """True on every rank iff `ok` is true on every rank (one MIN all-reduce): ranks must take the same branch before
+    any collective setup step, or the ones that went ahead wait forever for the one that did not."""
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(flag.item()) == 1)
+
+
 class PeerHalo(object):
     """Peer-mapped (CUDA symmetric memory) buffers for the halo exchange of ONE layer call in flight.
 
@@ -187,6 +195,15 @@ class PeerHalo(object):
                 symm.enable_symm_mem_for_group(group.group_name)
             except Exception:
                 pass
+        # The symmetric allocation bypasses torch's caching allocator: hand cached blocks back first, then let every
+        # rank check that the buffers fit (with 2 GB to spare) and AGREE on it -- a rank that ran out of memory alone
+        # would leave its peers waiting in the rendezvous.
+        need = (self.halo_rows + self.back_rows) * self.d * 4
+        torch.cuda.empty_cache()
+        free = torch.cuda.mem_get_info(dev)[0]
+        if not all_ranks_agree(free >= need + (2 << 30), group, dev):
+            raise RuntimeError("not enough free device memory on some rank for %.1f GB of peer-mapped halo buffers"
+                               % (need / 1e9))
         self.buf = symm.empty((self.halo_rows + self.back_rows, self.d), dtype=torch.float32, device=dev)
         self.hdl = symm.rendezvous(self.buf, group)
         self.halo = self.buf[:self.halo_rows]

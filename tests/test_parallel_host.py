@@ -288,3 +288,25 @@ def test_device_plan_equals_host_plan(world):
                 np.testing.assert_array_equal(getattr(dv, name).numpy(), getattr(h, name), err_msg=name)
             np.testing.assert_array_equal(dv.recv_counts, h.recv_counts)
             np.testing.assert_array_equal(dv.send_counts, h.send_counts)
+
+
+def _agree_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        res = [parallel.all_ranks_agree(True, None, "cpu"),                 # everyone fine
+               parallel.all_ranks_agree(rank != 1, None, "cpu"),            # one rank short of memory
+               parallel.all_ranks_agree(False, None, "cpu")]
+        np.save(os.path.join(out_dir, "agree_%d.npy" % rank), np.array(res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ranks_agree_before_collective_setup(tmp_path):
+    """all_ranks_agree: the peer-mapped halo buffers are only set up when EVERY rank can (a rank that cannot must take
+    all the others to the NCCL transport with it, not leave them waiting in the rendezvous)."""
+    world = 3
+    mp.spawn(_agree_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):
+        assert np.load(tmp_path / ("agree_%d.npy" % rank)).tolist() == [True, False, False]
