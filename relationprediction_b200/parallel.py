@@ -2,9 +2,9 @@
 
 Rank p owns the contiguous node range [V*p/P, V*(p+1)/P): its rows of H / out / dH and every MESSAGE
 whose destination it owns.  Sources are addressed in an extended local row space
-[local rows | halo rows]; the halo rows (unique remote sources) arrive with ONE all-to-all-v per
-layer forward, and their gradients return with one all-to-all-v per layer backward (then a local
-scatter-add).  Weights are replicated; their gradients are summed with one all-reduce.  The
+[local rows | halo rows]; the halo rows (unique remote sources) arrive once per layer forward -- pushed
+by their owners into this rank's peer-mapped halo buffer (PeerHalo), or by ONE all-to-all-v (NCCL
+transport) -- and their gradients return the same way per layer backward (then a local row add).  Weights are replicated; their gradients are summed with one all-reduce.  The
 per-message normalisation uses GLOBAL degrees, so sharded results equal the single-GPU ones.
 
 The reference has no distributed code at all (single tf.Session, train.py:278); this module is the
@@ -264,12 +264,15 @@ class _HaloExchange(torch.autograd.Function):
 
 
 class _OverlappedBlockLayer(torch.autograd.Function):
-    """Sharded block layer with the halo all-to-all hidden behind the local work.
+    """Sharded block layer with the halo exchange hidden behind the local work.
 
-    forward : start all-to-all(halo rows) || self-loop GEMM + LOCAL-source messages (rgcn_block_forward on
-              the local graph, ReLU deferred) -> wait -> HALO-source messages (rgcn_block_aggregate) -> ReLU
-    backward: G = dOut * relu'(out) -> halo-source backward first (rgcn_block_aggregate_backward) -> start
-              all-to-all(halo gradients) || local backward (rgcn_block_backward) -> wait -> scatter-add."""
+    forward : start the halo exchange || self-loop GEMM + LOCAL-source messages (rgcn_block_forward on the local
+              graph, ReLU deferred) -> wait -> HALO-source messages (rgcn_block_aggregate) -> ReLU
+    backward: G = dOut * relu'(out) -> halo-source backward first (rgcn_block_aggregate_backward) -> start the
+              gradient return || local backward (rgcn_block_backward) -> wait -> add the returned rows.
+    Exchange = peer transport (PeerHalo: rgcn_rows_gather pushes my rows into the peers' mapped halo buffers, the
+    gradients return by one peer-to-peer copy per owner, stream-ordered cross-GPU barriers) or, when that is not
+    available / not wanted, NCCL all-to-all-v of packed rows in both directions."""
 
     @staticmethod
     def forward(ctx, H_local, Wf, Wb, Ws, sg, n_blocks, drop_mask, keep, relu):
