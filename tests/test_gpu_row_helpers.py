@@ -29,7 +29,7 @@ def test_row_helpers_match_torch_indexing(n_rows, d, n):
     out = torch.randn(n_rows, d, device="cuda", generator=g)
     dOut = torch.randn(n_rows, d, device="cuda", generator=g)
     G = ops.relu_backward(dOut, out)
-    assert torch.equal(G, dOut * (out > 0))
+    assert torch.equal(G, torch.where(out > 0, dOut, torch.zeros_like(dOut)))
 
 
 def test_row_helpers_reject_bad_arguments():
