@@ -714,6 +714,10 @@ int launch_gemm_tf32x3(const float* A, int64_t lda, const float* Bt_hi, const fl
     rgcn_set_error("gemm_tf32x3: K, N and leading dimensions must be multiples of 4");
     return RGCN_ERR_INVALID;
   }
+  if (K == 0) {   // empty contraction: C = 0 (or unchanged); the kernel would publish accumulators no MMA ever wrote
+    if (accumulate) return RGCN_OK;
+    return rgcn_check_cuda(cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st), "memset(C)");
+  }
   static bool attr_set = false;
   if (!attr_set) {
     int rc = rgcn_check_cuda(cudaFuncSetAttribute(k_gemm_tf32x3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -740,8 +744,8 @@ int launch_gemm_rank_tf32x3(const float* Q, int64_t ldq, const float* Bt_hi, con
                             int N, int K, const float* gold_sig, const int32_t* gold_col, const uint32_t* known,
                             int words, int32_t* raw_cnt, int32_t* known_cnt, cudaStream_t st) {
   if (M == 0 || N == 0) return RGCN_OK;
-  if (K % 4 != 0 || ldq % 4 != 0 || ldb % 4 != 0) {
-    rgcn_set_error("gemm_rank_tf32x3: K and leading dimensions must be multiples of 4");
+  if (K <= 0 || K % 4 != 0 || ldq % 4 != 0 || ldb % 4 != 0) {
+    rgcn_set_error("gemm_rank_tf32x3: K > 0; K and leading dimensions must be multiples of 4");
     return RGCN_ERR_INVALID;
   }
   static bool attr_set = false;
